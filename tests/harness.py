@@ -199,3 +199,45 @@ def write_png(path, rgb8):
     with open(path, "wb") as f:
         f.write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 2, 0, 0, 0)) +
                 chunk(b"IDAT", zlib.compress(raw, 6)) + chunk(b"IEND", b""))
+
+
+class CudaBackend(Backend):
+    """The product: vkrt_cuda_* through ctypes (vkrt_b200.CudaContext)."""
+    prefix = "vkrt_cuda_"
+
+    def __init__(self, **kw):
+        import vkrt_b200
+        self.vk = vkrt_b200
+        self.cc = vkrt_b200.CudaContext(**kw)
+        super().__init__(self.cc.lib)
+        self.ctx = self.cc.ctx
+        self.build_stats = None
+        self.frame_stats = []
+
+    def last_error(self):
+        return (self.lib.vkrt_cuda_last_error(self.ctx) or b"").decode()
+
+    def build_accel(self):
+        self.build_stats = self.cc.build_accel()
+
+    def render_frame(self, sd):
+        self.frame_stats.append(self.cc.render_frame(sd))
+
+    def trace_rays(self, rays, any_hit=False):
+        return self.cc.trace_rays(rays, any_hit)[0]
+
+    def close(self):
+        self.cc.close()
+        self.ctx = None
+
+
+def compare_images(a, b, name=""):
+    """Robust image comparison for stochastic renders that share the RNG stream but differ in transcendental rounding."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    d = np.abs(a - b)
+    scale = np.maximum(np.abs(a), np.abs(b)) + 1e-3
+    rel = d / scale
+    return dict(name=name, rmse=float(np.sqrt(np.mean(d ** 2))), mean_abs=float(d.mean()), max_abs=float(d.max()),
+                frac_rel_gt_1e3=float((rel > 1e-3).mean()), frac_rel_gt_1e2=float((rel > 1e-2).mean()),
+                mean_a=float(a.mean()), mean_b=float(b.mean()))

@@ -1,0 +1,55 @@
+// build.h — host-side interface of the GPU BVH builder (bvh_build.cu).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/vkrt_shared.h"
+#include "accel.cuh"
+
+namespace vk {
+
+struct BuildTarget {
+    Bvh8Node* nodesOut = nullptr;
+    uint32_t nodeBase = 0;
+    const ShaderVertex* vertices = nullptr;
+    const uint32_t* indices = nullptr;
+    uint32_t vertexBase = 0, indexBase = 0;
+    ::float4* trianglesOut = nullptr;
+    uint32_t primBase = 0;
+    const InstanceRecord* instanceRecords = nullptr;
+    InstanceRecord* instancesOut = nullptr;
+};
+
+void launchRelocateNodes(const Bvh8Node* src, Bvh8Node* dst, uint32_t count, uint32_t oldBase, uint32_t newBase, cudaStream_t st);
+
+// Scratch memory + launch sequence for one BVH build at a time (reused across BLASes and the TLAS).
+class AccelBuilder {
+public:
+    ~AccelBuilder() { release(); }
+    bool reserve(uint32_t primCount);
+    void release();
+    // nodesOut must have room for max(triCount, 1) nodes starting at nodeBase; trianglesOut for triCount triangles at primBase.
+    bool buildBlas(cudaStream_t st, const ShaderVertex* vertices, const uint32_t* indices, uint32_t vertexBase, uint32_t indexBase,
+                   uint32_t triCount, Bvh8Node* nodesOut, uint32_t nodeBase, ::float4* trianglesOut, uint32_t primBase,
+                   ::float4* blasBoundsOut, uint32_t* outNodeCount, uint32_t* outPrimCount);
+    bool buildTlas(cudaStream_t st, const ::float4* blasBounds, const uint32_t* instanceBlas, const float* world3x4,
+                   const InstanceRecord* records, uint32_t instanceCount, Bvh8Node* nodesOut, uint32_t nodeBase,
+                   InstanceRecord* instancesOut, uint32_t* outNodeCount, uint32_t* outPrimCount);
+    char err[512] = {0};
+
+private:
+    bool buildFromBoxes(cudaStream_t st, uint32_t n, const BuildTarget& tgt, uint32_t* outNodeCount, uint32_t* outPrimCount);
+    uint32_t capacity = 0;
+    ::float4 *primLo = nullptr, *primHi = nullptr;
+    uint64_t* keys[2] = {nullptr, nullptr};
+    uint32_t* vals[2] = {nullptr, nullptr};
+    uint32_t *tileHist = nullptr, *digitTotals = nullptr;
+    ::float4 *nodeLo = nullptr, *nodeHi = nullptr;
+    uint32_t *parent = nullptr, *arrival = nullptr, *subFirst = nullptr, *subCount = nullptr;
+    uint2* work[2] = {nullptr, nullptr};
+    uint32_t* counters = nullptr;
+    int* bounds = nullptr;
+    const uint32_t* sortedVals = nullptr;
+};
+
+} // namespace vk

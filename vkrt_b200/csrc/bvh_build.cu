@@ -1,0 +1,705 @@
+// bvh_build.cu — GPU acceleration-structure builder for sm_100a.
+//
+// Replaces the driver builds recorded by the reference in src/core/render/accel/blas.c:222-262
+// (vkCmdBuildAccelerationStructuresKHR, one BLAS per unique geometry) and src/core/render/accel/tlas.c:236-289,535-559
+// (TLAS over one instance per mesh).  Pipeline per BVH (BLAS over triangles, TLAS over instance boxes):
+//   1. primitive AABBs + scene bounds                         (k_triangle_bounds / k_instance_bounds)
+//   2. Morton codes of the box centres, 3*b bits              (k_morton)
+//   3. hand-written LSD radix sort, 8-bit digits, no CUB      (k_rs_histogram / k_rs_scan_* / k_rs_scatter)
+//   4. Karras 2012 binary radix tree                          (k_hierarchy)
+//   5. bottom-up AABB refit with per-node arrival counters    (k_refit)
+//   6. greedy surface-area collapse to compressed 8-wide nodes (k_collapse), level by level
+// All stages stream their inputs with coalesced 8/16-byte accesses; the sort is the HBM-bound part
+// (DESIGN.md "Build" gives the algorithmic bytes per triangle).
+#include <cfloat>
+#include <cstdio>
+#include <vector>
+
+#include "accel.cuh"
+#include "build.h"
+#include "vmath.cuh"
+
+namespace vk {
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            snprintf(err, sizeof(err), "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return false;                                                                          \
+        }                                                                                          \
+    } while (0)
+
+// ---- ordered-int float atomics for the bounds reduction --------------------------------------------------------------
+__device__ __forceinline__ int floatToOrdered(float f) {
+    int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float orderedToFloat(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+__global__ void k_init_bounds(int* bounds) {
+    if (threadIdx.x < 3) bounds[threadIdx.x] = floatToOrdered(FLT_MAX);
+    else if (threadIdx.x < 6) bounds[threadIdx.x] = floatToOrdered(-FLT_MAX);
+}
+
+__device__ __forceinline__ void reduceBounds(float3 lo, float3 hi, bool valid, int* bounds) {
+    // warp reduce then one atomic per warp per component
+    if (!valid) { lo = float3(FLT_MAX); hi = float3(-FLT_MAX); }
+    for (int o = 16; o > 0; o >>= 1) {
+        lo.x = fminf(lo.x, __shfl_xor_sync(0xffffffffu, lo.x, o));
+        lo.y = fminf(lo.y, __shfl_xor_sync(0xffffffffu, lo.y, o));
+        lo.z = fminf(lo.z, __shfl_xor_sync(0xffffffffu, lo.z, o));
+        hi.x = fmaxf(hi.x, __shfl_xor_sync(0xffffffffu, hi.x, o));
+        hi.y = fmaxf(hi.y, __shfl_xor_sync(0xffffffffu, hi.y, o));
+        hi.z = fmaxf(hi.z, __shfl_xor_sync(0xffffffffu, hi.z, o));
+    }
+    if ((threadIdx.x & 31) == 0 && lo.x <= hi.x) {
+        atomicMin(&bounds[0], floatToOrdered(lo.x));
+        atomicMin(&bounds[1], floatToOrdered(lo.y));
+        atomicMin(&bounds[2], floatToOrdered(lo.z));
+        atomicMax(&bounds[3], floatToOrdered(hi.x));
+        atomicMax(&bounds[4], floatToOrdered(hi.y));
+        atomicMax(&bounds[5], floatToOrdered(hi.z));
+    }
+}
+
+// Pads a box by 2^-20 of its largest absolute coordinate so that the (rounded) watertight test can never accept a
+// hit outside the boxes that cull for it.
+__device__ __forceinline__ void padBox(float3& lo, float3& hi) {
+    float m = fmaxf(fmaxf(fmaxf(fabsf(lo.x), fabsf(hi.x)), fmaxf(fabsf(lo.y), fabsf(hi.y))), fmaxf(fabsf(lo.z), fabsf(hi.z)));
+    float eps = m * 9.5367431640625e-07f;
+    lo = lo - float3(eps);
+    hi = hi + float3(eps);
+}
+
+__global__ void k_triangle_bounds(const ShaderVertex* __restrict__ vertices, const uint32_t* __restrict__ indices, uint32_t vertexBase,
+                                  uint32_t indexBase, uint32_t triCount, ::float4* __restrict__ primLo, ::float4* __restrict__ primHi,
+                                  int* bounds) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = t < triCount;
+    float3 lo(FLT_MAX), hi(-FLT_MAX);
+    if (valid) {
+        for (int k = 0; k < 3; k++) {
+            uint32_t vi = indices[indexBase + t * 3u + k] + vertexBase;
+            ::float4 p = *reinterpret_cast<const ::float4*>(vertices[vi].position);
+            float3 v(p.x, p.y, p.z);
+            lo = min(lo, v);
+            hi = max(hi, v);
+        }
+        padBox(lo, hi);
+        primLo[t] = make_float4(lo.x, lo.y, lo.z, 0.0f);
+        primHi[t] = make_float4(hi.x, hi.y, hi.z, 0.0f);
+    }
+    reduceBounds(lo, hi, valid, bounds);
+}
+
+// World-space AABB of every instance = transformed corners of its BLAS root box (conservative), padded.
+__global__ void k_instance_bounds(const ::float4* __restrict__ blasBounds, const uint32_t* __restrict__ instanceBlas,
+                                  const float* __restrict__ world3x4, uint32_t instanceCount, ::float4* __restrict__ primLo,
+                                  ::float4* __restrict__ primHi, int* bounds) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = i < instanceCount;
+    float3 lo(FLT_MAX), hi(-FLT_MAX);
+    if (valid) {
+        ::float4 blo = blasBounds[instanceBlas[i] * 2u], bhi = blasBounds[instanceBlas[i] * 2u + 1u];
+        const float* m = world3x4 + (size_t)i * 12;
+        if (blo.x <= bhi.x) {
+            for (int k = 0; k < 8; k++) {
+                float3 p((k & 1) ? bhi.x : blo.x, (k & 2) ? bhi.y : blo.y, (k & 4) ? bhi.z : blo.z);
+                float3 w(m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3], m[4] * p.x + m[5] * p.y + m[6] * p.z + m[7],
+                         m[8] * p.x + m[9] * p.y + m[10] * p.z + m[11]);
+                lo = min(lo, w);
+                hi = max(hi, w);
+            }
+            padBox(lo, hi);
+            // a second, slightly larger pad absorbs the rounding of the 8 corner transforms themselves
+            padBox(lo, hi);
+        } else {  // empty BLAS: degenerate box at the instance origin
+            lo = hi = float3(m[3], m[7], m[11]);
+        }
+        primLo[i] = make_float4(lo.x, lo.y, lo.z, 0.0f);
+        primHi[i] = make_float4(hi.x, hi.y, hi.z, 0.0f);
+    }
+    reduceBounds(lo, hi, valid, bounds);
+}
+
+// ---- Morton codes ----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t spread21(uint64_t x) {
+    x &= 0x1fffffull;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+
+__global__ void k_morton(const ::float4* __restrict__ primLo, const ::float4* __restrict__ primHi, uint32_t n, const int* __restrict__ bounds,
+                         uint32_t bitsPerAxis, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float3 blo(orderedToFloat(bounds[0]), orderedToFloat(bounds[1]), orderedToFloat(bounds[2]));
+    float3 bhi(orderedToFloat(bounds[3]), orderedToFloat(bounds[4]), orderedToFloat(bounds[5]));
+    ::float4 lo = primLo[i], hi = primHi[i];
+    float3 c((lo.x + hi.x) * 0.5f, (lo.y + hi.y) * 0.5f, (lo.z + hi.z) * 0.5f);
+    float3 ext = bhi - blo;
+    float scale = float(1u << bitsPerAxis);
+    float3 nrm((ext.x > 0.0f ? (c.x - blo.x) / ext.x : 0.0f), (ext.y > 0.0f ? (c.y - blo.y) / ext.y : 0.0f),
+               (ext.z > 0.0f ? (c.z - blo.z) / ext.z : 0.0f));
+    uint32_t maxq = (1u << bitsPerAxis) - 1u;
+    uint32_t qx = min((uint32_t)fmaxf(nrm.x * scale, 0.0f), maxq);
+    uint32_t qy = min((uint32_t)fmaxf(nrm.y * scale, 0.0f), maxq);
+    uint32_t qz = min((uint32_t)fmaxf(nrm.z * scale, 0.0f), maxq);
+    keys[i] = (spread21(qx) << 2) | (spread21(qy) << 1) | spread21(qz);
+    vals[i] = i;
+}
+
+// ---- LSD radix sort (64-bit keys, 32-bit values), 8-bit digits -------------------------------------------------------
+// Tile = 8 warps x 16 rounds x 32 keys = 4096 keys; warp w owns the contiguous chunk [w*512, (w+1)*512) of the tile so
+// that stability only needs (a) per-warp digit counts, (b) an exclusive prefix over warps, (c) in-round match_any ranks.
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = 8;
+constexpr int RS_ROUNDS = 16;
+constexpr int RS_TILE = RS_THREADS * RS_ROUNDS;
+
+__device__ __forceinline__ void warpDigitCount(uint32_t (*warpHist)[256], int warp, uint32_t digit, bool valid) {
+    unsigned active = __ballot_sync(0xffffffffu, valid);
+    if (valid) {
+        unsigned mask = __match_any_sync(active, digit);
+        int leader = __ffs(mask) - 1;
+        if ((int)(threadIdx.x & 31) == leader) warpHist[warp][digit] += __popc(mask);
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(RS_THREADS) k_rs_histogram(const uint64_t* __restrict__ keys, uint32_t n, uint32_t shift,
+                                                             uint32_t numTiles, uint32_t* __restrict__ tileHist) {
+    __shared__ uint32_t warpHist[RS_WARPS][256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&warpHist[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t base = blockIdx.x * RS_TILE + warp * (RS_ROUNDS * 32);
+#pragma unroll 4
+    for (int r = 0; r < RS_ROUNDS; r++) {
+        uint32_t idx = base + r * 32 + lane;
+        bool valid = idx < n;
+        uint32_t digit = valid ? (uint32_t)((keys[idx] >> shift) & 0xffu) : 0u;
+        warpDigitCount(warpHist, warp, digit, valid);
+    }
+    __syncthreads();
+    uint32_t total = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; w++) total += warpHist[w][threadIdx.x];
+    tileHist[threadIdx.x * numTiles + blockIdx.x] = total;  // digit-major so that one block can scan one digit
+}
+
+// One block per digit: exclusive scan of that digit's per-tile counts (in place) + digit total.
+__global__ void __launch_bounds__(1024) k_rs_scan_tiles(uint32_t* __restrict__ tileHist, uint32_t numTiles, uint32_t* __restrict__ digitTotals) {
+    __shared__ uint32_t warpSums[32];
+    __shared__ uint32_t carry;
+    uint32_t* row = tileHist + (size_t)blockIdx.x * numTiles;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < numTiles; base += 1024) {
+        uint32_t i = base + threadIdx.x;
+        uint32_t v = i < numTiles ? row[i] : 0u;
+        uint32_t x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if ((int)(threadIdx.x & 31) >= o) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) warpSums[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t s = warpSums[threadIdx.x];
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t y = __shfl_up_sync(0xffffffffu, s, o);
+                if ((int)threadIdx.x >= o) s += y;
+            }
+            warpSums[threadIdx.x] = s;
+        }
+        __syncthreads();
+        uint32_t warpOffset = (threadIdx.x >> 5) ? warpSums[(threadIdx.x >> 5) - 1] : 0u;
+        uint32_t c = carry;
+        if (i < numTiles) row[i] = c + warpOffset + x - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = c + warpOffset + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) digitTotals[blockIdx.x] = carry;
+}
+
+__global__ void __launch_bounds__(256) k_rs_scan_digits(uint32_t* __restrict__ digitTotals) {
+    __shared__ uint32_t s[256];
+    s[threadIdx.x] = digitTotals[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0;
+        for (int i = 0; i < 256; i++) {
+            uint32_t v = s[i];
+            s[i] = acc;
+            acc += v;
+        }
+    }
+    __syncthreads();
+    digitTotals[256 + threadIdx.x] = s[threadIdx.x];  // exclusive digit bases
+}
+
+__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t* __restrict__ keysIn, const uint32_t* __restrict__ valsIn,
+                                                           uint64_t* __restrict__ keysOut, uint32_t* __restrict__ valsOut, uint32_t n,
+                                                           uint32_t shift, uint32_t numTiles, const uint32_t* __restrict__ tileHist,
+                                                           const uint32_t* __restrict__ digitTotals) {
+    __shared__ uint32_t warpHist[RS_WARPS][256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&warpHist[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t base = blockIdx.x * RS_TILE + warp * (RS_ROUNDS * 32);
+    uint64_t key[RS_ROUNDS];
+#pragma unroll
+    for (int r = 0; r < RS_ROUNDS; r++) {
+        uint32_t idx = base + r * 32 + lane;
+        bool valid = idx < n;
+        key[r] = valid ? keysIn[idx] : 0ull;
+        warpDigitCount(warpHist, warp, (uint32_t)((key[r] >> shift) & 0xffu), valid);
+    }
+    __syncthreads();
+    {   // thread d: turn per-warp counts of digit d into global output offsets
+        const uint32_t d = threadIdx.x;
+        uint32_t running = digitTotals[256 + d] + tileHist[d * numTiles + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; w++) {
+            uint32_t c = warpHist[w][d];
+            warpHist[w][d] = running;
+            running += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_ROUNDS; r++) {
+        uint32_t idx = base + r * 32 + lane;
+        bool valid = idx < n;
+        uint32_t digit = (uint32_t)((key[r] >> shift) & 0xffu);
+        unsigned active = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            unsigned mask = __match_any_sync(active, digit);
+            uint32_t rank = __popc(mask & ((1u << lane) - 1u));
+            uint32_t off = warpHist[warp][digit];
+            __syncwarp(mask);
+            if (rank == 0) warpHist[warp][digit] = off + __popc(mask);
+            uint32_t pos = off + rank;
+            keysOut[pos] = key[r];
+            valsOut[pos] = valsIn[idx];
+        }
+        __syncwarp();
+    }
+}
+
+// ---- Karras 2012 hierarchy -------------------------------------------------------------------------------------------
+__device__ __forceinline__ int deltaKeys(const uint64_t* __restrict__ keys, int n, int i, uint64_t ki, int j) {
+    if (j < 0 || j >= n) return -1;
+    uint64_t kj = keys[j];
+    if (ki == kj) return 64 + __clz((uint32_t)(i ^ j));
+    return __clzll((long long)(ki ^ kj));
+}
+
+// Node numbering: internal i in [0, n-1); leaf k stored at (n-1)+k. lo.w / hi.w of internal nodes hold the child indices.
+__global__ void k_hierarchy(const uint64_t* __restrict__ keys, uint32_t n, ::float4* __restrict__ nodeLo, ::float4* __restrict__ nodeHi,
+                            uint32_t* __restrict__ parent, uint32_t* __restrict__ subFirst, uint32_t* __restrict__ subCount) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int N = (int)n;
+    if (i >= N - 1) return;
+    uint64_t ki = keys[i];
+    int d = (deltaKeys(keys, N, i, ki, i + 1) - deltaKeys(keys, N, i, ki, i - 1)) >= 0 ? 1 : -1;
+    int dmin = deltaKeys(keys, N, i, ki, i - d);
+    int lmax = 2;
+    while (deltaKeys(keys, N, i, ki, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+        if (deltaKeys(keys, N, i, ki, i + (l + t) * d) > dmin) l += t;
+    int j = i + l * d;
+    int dnode = deltaKeys(keys, N, i, ki, j);
+    int s = 0;
+    int t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (deltaKeys(keys, N, i, ki, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    int gamma = i + s * d + (d < 0 ? d : 0);
+    int lo = i < j ? i : j, hi = i < j ? j : i;
+    uint32_t left = (lo == gamma) ? (uint32_t)(N - 1 + gamma) : (uint32_t)gamma;
+    uint32_t right = (hi == gamma + 1) ? (uint32_t)(N - 1 + gamma + 1) : (uint32_t)(gamma + 1);
+    nodeLo[i].w = __uint_as_float(left);
+    nodeHi[i].w = __uint_as_float(right);
+    parent[left] = (uint32_t)i;
+    parent[right] = (uint32_t)i;
+    subFirst[i] = (uint32_t)lo;
+    subCount[i] = (uint32_t)(hi - lo + 1);
+    if (i == 0) parent[0] = 0xFFFFFFFFu;
+}
+
+__global__ void k_leaves(const ::float4* __restrict__ primLo, const ::float4* __restrict__ primHi, const uint32_t* __restrict__ sortedVals,
+                         uint32_t n, ::float4* __restrict__ nodeLo, ::float4* __restrict__ nodeHi, uint32_t* __restrict__ subFirst,
+                         uint32_t* __restrict__ subCount, uint32_t* __restrict__ parent) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    uint32_t p = sortedVals[k];
+    ::float4 lo = primLo[p], hi = primHi[p];
+    lo.w = __uint_as_float(p);  // leaves carry the original primitive index
+    hi.w = __uint_as_float(0xFFFFFFFFu);
+    nodeLo[n - 1 + k] = lo;
+    nodeHi[n - 1 + k] = hi;
+    subFirst[n - 1 + k] = k;
+    subCount[n - 1 + k] = 1;
+    if (n == 1) parent[0] = 0xFFFFFFFFu;
+}
+
+__global__ void k_refit(uint32_t n, ::float4* nodeLo, ::float4* nodeHi, const uint32_t* __restrict__ parent, uint32_t* arrival) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n || n < 2) return;
+    uint32_t cur = parent[n - 1 + k];
+    while (cur != 0xFFFFFFFFu) {
+        __threadfence();
+        if (atomicAdd(&arrival[cur], 1u) == 0u) return;  // first child to arrive: the sibling will finish this node
+        volatile ::float4* vlo = nodeLo;
+        volatile ::float4* vhi = nodeHi;
+        uint32_t l = __float_as_uint(vlo[cur].w), r = __float_as_uint(vhi[cur].w);
+        float lx0 = vlo[l].x, ly0 = vlo[l].y, lz0 = vlo[l].z, hx0 = vhi[l].x, hy0 = vhi[l].y, hz0 = vhi[l].z;
+        float lx1 = vlo[r].x, ly1 = vlo[r].y, lz1 = vlo[r].z, hx1 = vhi[r].x, hy1 = vhi[r].y, hz1 = vhi[r].z;
+        vlo[cur].x = fminf(lx0, lx1); vlo[cur].y = fminf(ly0, ly1); vlo[cur].z = fminf(lz0, lz1);
+        vhi[cur].x = fmaxf(hx0, hx1); vhi[cur].y = fmaxf(hy0, hy1); vhi[cur].z = fmaxf(hz0, hz1);
+        cur = parent[cur];
+    }
+}
+
+// ---- collapse to compressed 8-wide nodes -----------------------------------------------------------------------------
+struct CollapseParams {
+    const ::float4* nodeLo;
+    const ::float4* nodeHi;
+    const uint32_t* subFirst;
+    const uint32_t* subCount;
+    const uint32_t* sortedVals;   // sorted position -> original primitive index
+    uint32_t primCount;
+    uint32_t maxLeaf;             // 3 for triangles, 1 for instances
+    Bvh8Node* nodesOut;           // global node array
+    uint32_t nodeBase;            // global index of this BVH's root node
+    uint32_t* counters;           // [0] work-out count, [1] nodes allocated (local), [2] primitives emitted (local)
+    // triangle emission
+    const ShaderVertex* vertices;
+    const uint32_t* indices;
+    uint32_t vertexBase, indexBase;
+    ::float4* trianglesOut;         // global triangle array (3 ::float4 per triangle)
+    uint32_t primBase;            // global primitive index of this BVH's first emitted primitive
+    // instance emission
+    const InstanceRecord* instanceRecords;  // by instance index
+    InstanceRecord* instancesOut;           // in TLAS leaf order
+};
+
+__device__ __forceinline__ float boxHalfArea(::float4 lo, ::float4 hi) {
+    float ex = hi.x - lo.x, ey = hi.y - lo.y, ez = hi.z - lo.z;
+    return ex * ey + ey * ez + ez * ex;
+}
+
+__global__ void __launch_bounds__(64) k_collapse(CollapseParams P, const uint2* __restrict__ workIn, uint32_t workCount, uint2* __restrict__ workOut) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= workCount) return;
+    const uint2 w = workIn[t];
+    const uint32_t n = P.primCount;
+    const uint32_t b2 = w.x;
+    auto isLeafLike = [&](uint32_t node) { return node >= n - 1 || P.subCount[node] <= P.maxLeaf; };
+
+    uint32_t child[8];
+    float area[8];
+    int nc = 0;
+    if (isLeafLike(b2)) {
+        child[nc++] = b2;
+    } else {
+        child[0] = __float_as_uint(P.nodeLo[b2].w);
+        child[1] = __float_as_uint(P.nodeHi[b2].w);
+        nc = 2;
+        for (int k = 0; k < 2; k++) area[k] = isLeafLike(child[k]) ? -1.0f : boxHalfArea(P.nodeLo[child[k]], P.nodeHi[child[k]]);
+        while (nc < 8) {
+            int best = -1;
+            float bestArea = -1.0f;
+            for (int k = 0; k < nc; k++)
+                if (area[k] > bestArea) { bestArea = area[k]; best = k; }
+            if (best < 0) break;
+            uint32_t c = child[best];
+            uint32_t l = __float_as_uint(P.nodeLo[c].w), r = __float_as_uint(P.nodeHi[c].w);
+            child[best] = l;
+            area[best] = isLeafLike(l) ? -1.0f : boxHalfArea(P.nodeLo[l], P.nodeHi[l]);
+            child[nc] = r;
+            area[nc] = isLeafLike(r) ? -1.0f : boxHalfArea(P.nodeLo[r], P.nodeHi[r]);
+            nc++;
+        }
+    }
+
+    // node frame
+    ::float4 nlo = P.nodeLo[b2], nhi = P.nodeHi[b2];
+    if (nc == 1 && child[0] == b2) { /* single leaf-like root: frame is its own box */ }
+    float3 center((nlo.x + nhi.x) * 0.5f, (nlo.y + nhi.y) * 0.5f, (nlo.z + nhi.z) * 0.5f);
+
+    // greedy slot assignment: slot bit set = child on the positive side of that axis (x: bit0, y: bit1, z: bit2)
+    ::float4 clo[8], chi[8];
+    float cost[8][8];
+    for (int k = 0; k < nc; k++) {
+        clo[k] = P.nodeLo[child[k]];
+        chi[k] = P.nodeHi[child[k]];
+        float3 c((clo[k].x + chi[k].x) * 0.5f - center.x, (clo[k].y + chi[k].y) * 0.5f - center.y, (clo[k].z + chi[k].z) * 0.5f - center.z);
+        for (int s = 0; s < 8; s++) cost[k][s] = ((s & 1) ? c.x : -c.x) + ((s & 2) ? c.y : -c.y) + ((s & 4) ? c.z : -c.z);
+    }
+    int slotOf[8];
+    int childAt[8];
+    for (int k = 0; k < 8; k++) { slotOf[k] = -1; childAt[k] = -1; }
+    for (int it = 0; it < nc; it++) {
+        float bestCost = -FLT_MAX;
+        int bk = -1, bs = -1;
+        for (int k = 0; k < nc; k++) {
+            if (slotOf[k] >= 0) continue;
+            for (int s = 0; s < 8; s++) {
+                if (childAt[s] >= 0) continue;
+                if (cost[k][s] > bestCost) { bestCost = cost[k][s]; bk = k; bs = s; }
+            }
+        }
+        slotOf[bk] = bs;
+        childAt[bs] = bk;
+    }
+
+    // quantisation exponents: smallest e with extent <= 255 * 2^e
+    Bvh8Node node;
+    node.px = nlo.x; node.py = nlo.y; node.pz = nlo.z;
+    float ext[3] = {nhi.x - nlo.x, nhi.y - nlo.y, nhi.z - nlo.z};
+    uint8_t eb[3];
+    float inv2e[3], pow2e[3];
+    for (int a = 0; a < 3; a++) {
+        int e;
+        if (!(ext[a] > 0.0f)) {
+            e = -126;
+        } else {
+            e = (int)ceilf(log2f(ext[a] * (1.0f / 255.0f)));
+            if (e < -126) e = -126;
+            while (ext[a] > 255.0f * __uint_as_float((uint32_t)(e + 127) << 23)) e++;
+        }
+        eb[a] = (uint8_t)(e + 127);
+        pow2e[a] = __uint_as_float((uint32_t)eb[a] << 23);
+        inv2e[a] = 1.0f / pow2e[a];
+    }
+    node.ex = eb[0]; node.ey = eb[1]; node.ez = eb[2];
+
+    // allocation
+    uint32_t nInternal = 0, nPrims = 0;
+    for (int k = 0; k < nc; k++) {
+        if (isLeafLike(child[k])) nPrims += (child[k] >= n - 1) ? 1u : P.subCount[child[k]];
+        else nInternal++;
+    }
+    uint32_t childBaseLocal = nInternal ? atomicAdd(&P.counters[1], nInternal) : 0u;
+    uint32_t primBaseLocal = nPrims ? atomicAdd(&P.counters[2], nPrims) : 0u;
+    uint32_t workBase = nInternal ? atomicAdd(&P.counters[0], nInternal) : 0u;
+    node.childBase = P.nodeBase + childBaseLocal;
+    node.primBase = P.primBase + primBaseLocal;
+    node.imask = 0;
+
+    uint32_t internalRank = 0, primOffset = 0;
+    const float p3[3] = {nlo.x, nlo.y, nlo.z};
+    for (int s = 0; s < 8; s++) {
+        int k = childAt[s];
+        if (k < 0) {
+            node.meta[s] = 0;
+            node.qlox[s] = node.qloy[s] = node.qloz[s] = 255;  // inverted box: never hit
+            node.qhix[s] = node.qhiy[s] = node.qhiz[s] = 0;
+            continue;
+        }
+        const float lo3[3] = {clo[k].x, clo[k].y, clo[k].z}, hi3[3] = {chi[k].x, chi[k].y, chi[k].z};
+        uint8_t ql[3], qh[3];
+        for (int a = 0; a < 3; a++) {
+            float fl = floorf((lo3[a] - p3[a]) * inv2e[a]);
+            float fh = ceilf((hi3[a] - p3[a]) * inv2e[a]);
+            fl = fminf(fmaxf(fl, 0.0f), 255.0f);
+            fh = fminf(fmaxf(fh, 0.0f), 255.0f);
+            // make the decoded box provably conservative under the decode arithmetic p + q * 2^e
+            while (fl > 0.0f && p3[a] + fl * pow2e[a] > lo3[a]) fl -= 1.0f;
+            while (fh < 255.0f && p3[a] + fh * pow2e[a] < hi3[a]) fh += 1.0f;
+            ql[a] = (uint8_t)fl;
+            qh[a] = (uint8_t)fh;
+        }
+        node.qlox[s] = ql[0]; node.qloy[s] = ql[1]; node.qloz[s] = ql[2];
+        node.qhix[s] = qh[0]; node.qhiy[s] = qh[1]; node.qhiz[s] = qh[2];
+        uint32_t c = child[k];
+        if (!isLeafLike(c)) {
+            node.imask |= (uint8_t)(1u << s);
+            node.meta[s] = (uint8_t)((1u << 5) | (24u + (uint32_t)s));
+            workOut[workBase + internalRank] = make_uint2(c, childBaseLocal + internalRank);
+            internalRank++;
+        } else {
+            uint32_t cnt = (c >= n - 1) ? 1u : P.subCount[c];
+            uint32_t first = P.subFirst[c];
+            uint32_t unary = cnt == 1 ? 1u : (cnt == 2 ? 3u : 7u);
+            node.meta[s] = (uint8_t)((unary << 5) | primOffset);
+            for (uint32_t q = 0; q < cnt; q++) {
+                uint32_t prim = P.sortedVals[first + q];
+                uint32_t outIndex = P.primBase + primBaseLocal + primOffset + q;
+                if (P.trianglesOut) {
+                    ::float4 v[3];
+                    for (int kk = 0; kk < 3; kk++) {
+                        uint32_t vi = P.indices[P.indexBase + prim * 3u + kk] + P.vertexBase;
+                        v[kk] = *reinterpret_cast<const ::float4*>(P.vertices[vi].position);
+                    }
+                    v[0].w = __uint_as_float(prim);
+                    v[1].w = 0.0f;
+                    v[2].w = 0.0f;
+                    P.trianglesOut[(size_t)outIndex * 3 + 0] = v[0];
+                    P.trianglesOut[(size_t)outIndex * 3 + 1] = v[1];
+                    P.trianglesOut[(size_t)outIndex * 3 + 2] = v[2];
+                } else {
+                    P.instancesOut[outIndex] = P.instanceRecords[prim];
+                }
+            }
+            primOffset += cnt;
+        }
+    }
+    P.nodesOut[P.nodeBase + w.y] = node;
+}
+
+// Copies a finished BVH from the worst-case-sized scratch array to its final, compacted position; internal-child links
+// are absolute node indices and move by (newBase - oldBase).
+__global__ void k_relocate_nodes(const Bvh8Node* __restrict__ src, Bvh8Node* __restrict__ dst, uint32_t count, uint32_t oldBase, uint32_t newBase) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    Bvh8Node n = src[i];
+    n.childBase = n.childBase - oldBase + newBase;
+    dst[i] = n;
+}
+void launchRelocateNodes(const Bvh8Node* src, Bvh8Node* dst, uint32_t count, uint32_t oldBase, uint32_t newBase, cudaStream_t st) {
+    if (count) k_relocate_nodes<<<(count + 255) / 256, 256, 0, st>>>(src, dst, count, oldBase, newBase);
+}
+
+// ----------------------------------------------------------------------------------------------------------------------
+// Host driver
+// ----------------------------------------------------------------------------------------------------------------------
+static uint32_t ceilLog2(uint32_t v) {
+    uint32_t r = 0;
+    while ((1ull << r) < v) r++;
+    return r;
+}
+
+void AccelBuilder::release() {
+    auto F = [](void* p) { if (p) cudaFree(p); };
+    F(primLo); F(primHi); F(keys[0]); F(keys[1]); F(vals[0]); F(vals[1]); F(tileHist); F(digitTotals); F(nodeLo); F(nodeHi);
+    F(parent); F(arrival); F(subFirst); F(subCount); F(work[0]); F(work[1]); F(counters); F(bounds);
+    primLo = primHi = nodeLo = nodeHi = nullptr;
+    keys[0] = keys[1] = nullptr;
+    vals[0] = vals[1] = nullptr;
+    tileHist = digitTotals = parent = arrival = subFirst = subCount = counters = nullptr;
+    work[0] = work[1] = nullptr;
+    bounds = nullptr;
+    capacity = 0;
+}
+
+bool AccelBuilder::reserve(uint32_t n) {
+    if (n <= capacity) return true;
+    release();
+    uint32_t cap = n < 1024 ? 1024 : n;
+    uint32_t tiles = (cap + RS_TILE - 1) / RS_TILE;
+    CK(cudaMalloc(&primLo, sizeof(::float4) * cap));
+    CK(cudaMalloc(&primHi, sizeof(::float4) * cap));
+    for (int k = 0; k < 2; k++) {
+        CK(cudaMalloc(&keys[k], sizeof(uint64_t) * cap));
+        CK(cudaMalloc(&vals[k], sizeof(uint32_t) * cap));
+        CK(cudaMalloc(&work[k], sizeof(uint2) * cap));
+    }
+    CK(cudaMalloc(&tileHist, sizeof(uint32_t) * 256 * tiles));
+    CK(cudaMalloc(&digitTotals, sizeof(uint32_t) * 512));
+    CK(cudaMalloc(&nodeLo, sizeof(::float4) * 2 * cap));
+    CK(cudaMalloc(&nodeHi, sizeof(::float4) * 2 * cap));
+    CK(cudaMalloc(&parent, sizeof(uint32_t) * 2 * cap));
+    CK(cudaMalloc(&arrival, sizeof(uint32_t) * cap));
+    CK(cudaMalloc(&subFirst, sizeof(uint32_t) * 2 * cap));
+    CK(cudaMalloc(&subCount, sizeof(uint32_t) * 2 * cap));
+    CK(cudaMalloc(&counters, sizeof(uint32_t) * 4));
+    CK(cudaMalloc(&bounds, sizeof(int) * 8));
+    capacity = cap;
+    return true;
+}
+
+// Steps 2-6 for primitives whose boxes are already in primLo/primHi (bounds reduced into `bounds`).
+bool AccelBuilder::buildFromBoxes(cudaStream_t st, uint32_t n, const BuildTarget& tgt, uint32_t* outNodeCount, uint32_t* outPrimCount) {
+    const int TB = 256;
+    const uint32_t grid = (n + TB - 1) / TB;
+    uint32_t bitsPerAxis = ceilLog2(n < 2 ? 2 : n) / 3 + 7;
+    if (bitsPerAxis > 21) bitsPerAxis = 21;
+    const uint32_t keyBits = bitsPerAxis * 3;
+    k_morton<<<grid, TB, 0, st>>>(primLo, primHi, n, bounds, bitsPerAxis, keys[0], vals[0]);
+    const uint32_t tiles = (n + RS_TILE - 1) / RS_TILE;
+    int cur = 0;
+    for (uint32_t shift = 0; shift < keyBits; shift += 8) {
+        k_rs_histogram<<<tiles, RS_THREADS, 0, st>>>(keys[cur], n, shift, tiles, tileHist);
+        k_rs_scan_tiles<<<256, 1024, 0, st>>>(tileHist, tiles, digitTotals);
+        k_rs_scan_digits<<<1, 256, 0, st>>>(digitTotals);
+        k_rs_scatter<<<tiles, RS_THREADS, 0, st>>>(keys[cur], vals[cur], keys[1 - cur], vals[1 - cur], n, shift, tiles, tileHist, digitTotals);
+        cur = 1 - cur;
+    }
+    sortedVals = vals[cur];
+    k_leaves<<<grid, TB, 0, st>>>(primLo, primHi, vals[cur], n, nodeLo, nodeHi, subFirst, subCount, parent);
+    if (n > 1) {
+        k_hierarchy<<<grid, TB, 0, st>>>(keys[cur], n, nodeLo, nodeHi, parent, subFirst, subCount);
+        CK(cudaMemsetAsync(arrival, 0, sizeof(uint32_t) * n, st));
+        k_refit<<<grid, TB, 0, st>>>(n, nodeLo, nodeHi, parent, arrival);
+    }
+    // collapse
+    CollapseParams P = {};
+    P.nodeLo = nodeLo; P.nodeHi = nodeHi; P.subFirst = subFirst; P.subCount = subCount; P.sortedVals = vals[cur];
+    P.primCount = n;
+    P.maxLeaf = tgt.instancesOut ? 1u : 3u;
+    P.nodesOut = tgt.nodesOut; P.nodeBase = tgt.nodeBase; P.counters = counters;
+    P.vertices = tgt.vertices; P.indices = tgt.indices; P.vertexBase = tgt.vertexBase; P.indexBase = tgt.indexBase;
+    P.trianglesOut = tgt.trianglesOut; P.primBase = tgt.primBase;
+    P.instanceRecords = tgt.instanceRecords; P.instancesOut = tgt.instancesOut;
+    uint32_t initCounters[4] = {0u, 1u, 0u, 0u};  // node 0 (root) is pre-allocated
+    CK(cudaMemcpyAsync(counters, initCounters, sizeof(initCounters), cudaMemcpyHostToDevice, st));
+    uint2 rootWork = make_uint2(0u, 0u);  // bvh2 node 0 (for n == 1 that is the single leaf) -> local bvh8 node 0
+    CK(cudaMemcpyAsync(work[0], &rootWork, sizeof(uint2), cudaMemcpyHostToDevice, st));
+    uint32_t workCount = 1;
+    int wq = 0;
+    uint32_t hostCounters[4];
+    while (workCount > 0) {
+        k_collapse<<<(workCount + 63) / 64, 64, 0, st>>>(P, work[wq], workCount, work[1 - wq]);
+        CK(cudaMemcpyAsync(hostCounters, counters, sizeof(hostCounters), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        workCount = hostCounters[0];
+        uint32_t zero = 0;
+        CK(cudaMemcpyAsync(counters, &zero, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        wq = 1 - wq;
+    }
+    *outNodeCount = hostCounters[1];
+    *outPrimCount = hostCounters[2];
+    CK(cudaGetLastError());
+    return true;
+}
+
+bool AccelBuilder::buildBlas(cudaStream_t st, const ShaderVertex* vertices, const uint32_t* indices, uint32_t vertexBase, uint32_t indexBase,
+                             uint32_t triCount, Bvh8Node* nodesOut, uint32_t nodeBase, ::float4* trianglesOut, uint32_t primBase,
+                             ::float4* blasBoundsOut, uint32_t* outNodeCount, uint32_t* outPrimCount) {
+    if (!reserve(triCount)) return false;
+    k_init_bounds<<<1, 32, 0, st>>>(bounds);
+    k_triangle_bounds<<<(triCount + 255) / 256, 256, 0, st>>>(vertices, indices, vertexBase, indexBase, triCount, primLo, primHi, bounds);
+    BuildTarget tgt = {};
+    tgt.nodesOut = nodesOut; tgt.nodeBase = nodeBase; tgt.vertices = vertices; tgt.indices = indices;
+    tgt.vertexBase = vertexBase; tgt.indexBase = indexBase; tgt.trianglesOut = trianglesOut; tgt.primBase = primBase;
+    if (!buildFromBoxes(st, triCount, tgt, outNodeCount, outPrimCount)) return false;
+    // BLAS root box (LBVH node 0 after refit; for a single triangle node 0 is that leaf)
+    CK(cudaMemcpyAsync(blasBoundsOut, nodeLo, sizeof(::float4), cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(blasBoundsOut + 1, nodeHi, sizeof(::float4), cudaMemcpyDeviceToDevice, st));
+    return true;
+}
+
+bool AccelBuilder::buildTlas(cudaStream_t st, const ::float4* blasBounds, const uint32_t* instanceBlas, const float* world3x4,
+                             const InstanceRecord* records, uint32_t instanceCount, Bvh8Node* nodesOut, uint32_t nodeBase,
+                             InstanceRecord* instancesOut, uint32_t* outNodeCount, uint32_t* outPrimCount) {
+    if (!reserve(instanceCount)) return false;
+    k_init_bounds<<<1, 32, 0, st>>>(bounds);
+    k_instance_bounds<<<(instanceCount + 255) / 256, 256, 0, st>>>(blasBounds, instanceBlas, world3x4, instanceCount, primLo, primHi, bounds);
+    BuildTarget tgt = {};
+    tgt.nodesOut = nodesOut; tgt.nodeBase = nodeBase; tgt.instanceRecords = records; tgt.instancesOut = instancesOut;
+    return buildFromBoxes(st, instanceCount, tgt, outNodeCount, outPrimCount);
+}
+
+} // namespace vk

@@ -1,0 +1,310 @@
+// trace.cuh — persistent-thread traversal of the two-level compressed 8-wide BVH.
+//
+// This kernel is what the reference obtains from the driver with TraceRay (src/shaders/rt/queries/scene_query.slang:10-42
+// closest hit, RAY_FLAG_NONE, mask 0xff; src/shaders/rt/queries/shadow_query.slang:8-28 first-hit-terminate) plus the tiny hit
+// shaders (entry/path/closest_hit.slang, miss.slang, any_hit.slang; entry/shadow/*.slang).
+//
+// Design (B200, no RT cores):
+//   * one launch processes one bounce's extension-ray queue AND the previous shade's shadow-ray queue as a single work
+//     list; rays are read/written as 16-byte SoA vectors (coalesced: lane i <-> ray base+i);
+//   * persistent warps (grid = k * 148 SMs) pull rays with a warp-aggregated atomic; a warp refills its idle lanes as soon
+//     as fewer than REFILL_THRESHOLD lanes are still traversing (Aila & Laine 2009 dynamic fetch), so a long ray does
+//     not hold 31 idle lanes hostage;
+//   * traversal stack: uint2 entries (node group / primitive group, Ylitie et al. 2017) in per-thread local memory (L1);
+//   * 80-byte nodes are fetched as five 128-bit loads, triangles as three; everything read-only goes through LDG.
+#pragma once
+#include "intersect.cuh"
+#include "scene_view.cuh"
+
+namespace vk {
+
+constexpr int TRACE_STACK = 40;
+constexpr int TRACE_BLOCK = 128;
+constexpr int REFILL_THRESHOLD = 20;
+constexpr uint32_t SHADOW_KIND_SCALAR = 1u << 31;  // in ShadowTarget.statePos: contribution goes to the scalar lane (hero fallback)
+
+struct TraceParams {
+    SceneView scene;
+    // extension rays (closest hit)
+    const ::float4* rayO;        // origin.xyz, tMin
+    const ::float4* rayD;        // direction.xyz, tMax
+    const uint32_t* raySeed;     // rng at ray start; read only when an alpha-tested instance is met
+    ::uint4* hitA;               // instance, primitive, t bits, u bits
+    float* hitB;                 // v
+    const uint32_t* extCount;    // device-resident queue length
+    // shadow rays (any hit); results are applied in place
+    const ::float4* shO;
+    const ::float4* shD;
+    const ::float4* shContribution;  // rgb / 4 wavelengths, already multiplied by throughput
+    const ::uint2* shTarget;         // x = sample-record index, y = new path-state position (0x7fffffff = path ended) | SHADOW_KIND_SCALAR
+    const uint32_t* shSeed;
+    const uint32_t* shCount;
+    ::float4* radiance;          // per sample-record accumulators
+    float* radianceScalar;       // hero mode: single-wavelength lane after dispersive collapse
+    uint32_t* pathFlags;         // new path-state flags (bit 0 = prevVertexNeeAllowed)
+    uint32_t* shadowResult;      // optional (trace_rays API): 0 visible, 1 occluded, 2 unsupported transmission
+    // bookkeeping
+    uint32_t* workCounter;       // zero-initialised per launch
+    unsigned long long* stats;   // optional: [0] nodes visited, [1] triangles tested, [2] instances entered
+};
+
+__device__ __forceinline__ uint32_t extractByte(uint32_t v, int i) { return (v >> (i * 8)) & 0xffu; }
+
+// Intersects the 8 children of one compressed node; returns the hit mask: bits 24..31 = internal children ordered by
+// (slot ^ octinv) (nearest = highest bit), bits 0..23 = primitives of the leaf children.
+__device__ __forceinline__ uint32_t intersectNode8(const Bvh8Node* __restrict__ node, const float3& o, const float3& idir, uint32_t octinv,
+                                                   float tMin, float tMax, uint32_t& childBase, uint32_t& primBase, uint32_t& imask) {
+    const ::float4* q = reinterpret_cast<const ::float4*>(node);
+    const ::float4 n0 = __ldg(q), n1 = __ldg(q + 1), n2 = __ldg(q + 2), n3 = __ldg(q + 3), n4 = __ldg(q + 4);
+    const uint32_t ebits = __float_as_uint(n0.w);
+    imask = ebits >> 24;
+    childBase = __float_as_uint(n1.x);
+    primBase = __float_as_uint(n1.y);
+    const float ax = __uint_as_float((ebits & 0xffu) << 23) * idir.x;
+    const float ay = __uint_as_float(((ebits >> 8) & 0xffu) << 23) * idir.y;
+    const float az = __uint_as_float(((ebits >> 16) & 0xffu) << 23) * idir.z;
+    const float bx = (n0.x - o.x) * idir.x, by = (n0.y - o.y) * idir.y, bz = (n0.z - o.z) * idir.z;
+    const bool negx = idir.x < 0.0f, negy = idir.y < 0.0f, negz = idir.z < 0.0f;
+    uint32_t hitmask = 0;
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        const uint32_t meta4 = __float_as_uint(half ? n1.w : n1.z);
+        const uint32_t lox4 = __float_as_uint(half ? n2.y : n2.x), loy4 = __float_as_uint(half ? n2.w : n2.z);
+        const uint32_t loz4 = __float_as_uint(half ? n3.y : n3.x), hix4 = __float_as_uint(half ? n3.w : n3.z);
+        const uint32_t hiy4 = __float_as_uint(half ? n4.y : n4.x), hiz4 = __float_as_uint(half ? n4.w : n4.z);
+        const uint32_t nx4 = negx ? hix4 : lox4, fx4 = negx ? lox4 : hix4;
+        const uint32_t ny4 = negy ? hiy4 : loy4, fy4 = negy ? loy4 : hiy4;
+        const uint32_t nz4 = negz ? hiz4 : loz4, fz4 = negz ? loz4 : hiz4;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t meta = extractByte(meta4, j);
+            if (meta == 0u) continue;
+            const float tnx = fmaf(float(extractByte(nx4, j)), ax, bx), tfx = fmaf(float(extractByte(fx4, j)), ax, bx);
+            const float tny = fmaf(float(extractByte(ny4, j)), ay, by), tfy = fmaf(float(extractByte(fy4, j)), ay, by);
+            const float tnz = fmaf(float(extractByte(nz4, j)), az, bz), tfz = fmaf(float(extractByte(fz4, j)), az, bz);
+            const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tMin));
+            const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tMax));
+            if (tn * 0.999999f <= tf * 1.000001f) {
+                const int slot = half * 4 + j;
+                if (imask & (1u << slot)) hitmask |= 1u << (24 + (slot ^ octinv));
+                else hitmask |= ((meta >> 5) & 7u) << (meta & 31u);
+            }
+        }
+    }
+    return hitmask;
+}
+
+struct LaneRay {
+    float3 o, d;        // world ray
+    float tMin, tBest;
+    uint32_t index;     // position in the combined work list
+    uint32_t hitInst, hitPrim;
+    float hitU, hitV;
+    bool anyHit, sawTransmissive, active;
+};
+
+template <bool COUNT>
+__global__ void __launch_bounds__(TRACE_BLOCK) k_trace(const TraceParams P) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t extCount = P.extCount ? *P.extCount : 0u;
+    const uint32_t shCount = P.shCount ? *P.shCount : 0u;
+    const uint32_t total = extCount + shCount;
+    const AccelView& A = P.scene.accel;
+
+    uint2 stack[TRACE_STACK];
+    int sp = 0;
+    LaneRay R;
+    R.active = false;
+    // traversal registers
+    float3 o, d, idir;
+    uint32_t octinv = 0;
+    bool inBlas = false;
+    int blasBase = 0;
+    uint32_t curInst = 0, curFlags = 0;
+    RayShear shear;
+    uint2 G = make_uint2(0u, 0u);
+    bool exhausted = false;
+    unsigned long long nNodes = 0, nTris = 0, nInst = 0;
+
+    while (true) {
+        // ---- refill idle lanes ----------------------------------------------------------------------------------
+        if (!exhausted) {
+            const unsigned idle = __ballot_sync(0xffffffffu, !R.active);
+            if (idle) {
+                uint32_t base = 0;
+                const int leader = __ffs(idle) - 1;
+                if (lane == leader) base = atomicAdd(P.workCounter, (uint32_t)__popc(idle));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (!R.active) {
+                    const uint32_t idx = base + __popc(idle & ((1u << lane) - 1u));
+                    if (idx < total) {
+                        R.index = idx;
+                        R.anyHit = idx >= extCount;
+                        ::float4 ro, rd;
+                        if (!R.anyHit) { ro = __ldg(P.rayO + idx); rd = __ldg(P.rayD + idx); }
+                        else { ro = __ldg(P.shO + (idx - extCount)); rd = __ldg(P.shD + (idx - extCount)); }
+                        R.o = float3(ro.x, ro.y, ro.z);
+                        R.d = float3(rd.x, rd.y, rd.z);
+                        R.tMin = ro.w;
+                        R.tBest = rd.w;
+                        R.hitInst = VKRT_INVALID_INDEX;
+                        R.hitPrim = VKRT_INVALID_INDEX;
+                        R.hitU = R.hitV = 0.0f;
+                        R.sawTransmissive = false;
+                        R.active = true;
+                        o = R.o; d = R.d;
+                        idir = safeInvDir(d);
+                        octinv = 7u ^ ((d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u));
+                        inBlas = false;
+                        sp = 0;
+                        G = make_uint2(A.tlasRoot, 0x80000000u);
+                        if (A.instanceCount == 0u) G = make_uint2(0u, 0u);
+                    }
+                }
+                if (base + (uint32_t)__popc(idle) >= total) exhausted = true;
+            }
+        }
+        if (__ballot_sync(0xffffffffu, R.active) == 0u) break;
+
+        // ---- traverse until this lane finishes or the warp wants a refill ------------------------------------------
+        while (R.active) {
+            uint2 Gt = make_uint2(0u, 0u);
+            if (G.y & 0xff000000u) {
+                const int bit = 31 - __clz(G.y & 0xff000000u);
+                const uint32_t slot = (uint32_t)(bit - 24) ^ octinv;
+                G.y &= ~(1u << bit);
+                if (G.y & 0xff000000u) { if (sp < TRACE_STACK) stack[sp++] = G; }
+                const uint32_t nodeIndex = G.x + __popc(G.y & 0xffu & ((1u << slot) - 1u));
+                uint32_t childBase, primBase, imask;
+                const uint32_t hits = intersectNode8(A.nodes + nodeIndex, o, idir, octinv, R.tMin, R.tBest, childBase, primBase, imask);
+                if (COUNT) nNodes++;
+                G = make_uint2(childBase, (hits & 0xff000000u) | imask);
+                Gt = make_uint2(primBase, hits & 0x00ffffffu);
+            } else {
+                Gt = G;
+                G = make_uint2(0u, 0u);
+            }
+
+            while (Gt.y) {
+                const int i = __ffs(Gt.y) - 1;
+                Gt.y &= Gt.y - 1u;
+                const uint32_t primIndex = Gt.x + (uint32_t)i;
+                if (!inBlas) {
+                    // TLAS leaf = instance: park the remaining TLAS work and descend into the BLAS
+                    if (Gt.y) { if (sp < TRACE_STACK) stack[sp++] = Gt; }
+                    if (G.y & 0xff000000u) { if (sp < TRACE_STACK) stack[sp++] = G; }
+                    G = make_uint2(0u, 0u);
+                    Gt.y = 0u;
+                    const InstanceRecord* rec = A.instances + primIndex;
+                    const ::uint4 meta = __ldg(reinterpret_cast<const ::uint4*>(rec) + 3);
+                    const bool skip = (meta.y & INSTANCE_FLAG_EMPTY) || (R.anyHit && R.sawTransmissive && (meta.y & INSTANCE_FLAG_TRANSMISSIVE));
+                    if (!skip) {
+                        const ::float4 r0 = __ldg(reinterpret_cast<const ::float4*>(rec));
+                        const ::float4 r1 = __ldg(reinterpret_cast<const ::float4*>(rec) + 1);
+                        const ::float4 r2 = __ldg(reinterpret_cast<const ::float4*>(rec) + 2);
+                        const float4 i0(r0.x, r0.y, r0.z, r0.w), i1(r1.x, r1.y, r1.z, r1.w), i2(r2.x, r2.y, r2.z, r2.w);
+                        const float3 oo = xformPoint(i0, i1, i2, R.o);
+                        const float3 od = xformVector(i0, i1, i2, R.d);
+                        if (makeRayShear(od, shear)) {
+                            o = oo; d = od;
+                            idir = safeInvDir(d);
+                            octinv = 7u ^ ((d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u));
+                            inBlas = true;
+                            blasBase = sp;
+                            curInst = meta.z;
+                            curFlags = meta.y;
+                            G = make_uint2(meta.x, 0x80000000u);
+                            if (COUNT) nInst++;
+                        }
+                    }
+                    break;
+                }
+                // triangle
+                const ::float4* tri = A.triangles + (size_t)primIndex * 3;
+                const ::float4 a = __ldg(tri), b = __ldg(tri + 1), c = __ldg(tri + 2);
+                if (COUNT) nTris++;
+                float t, u, v;
+                if (!watertightTriangle(o, shear, float3(a.x, a.y, a.z), float3(b.x, b.y, b.z), float3(c.x, c.y, c.z), t, u, v)) continue;
+                if (!(t > R.tMin)) continue;
+                const uint32_t prim = __float_as_uint(a.w);
+                bool closer = t < R.tBest;
+                if (!closer && t == R.tBest && R.hitInst != VKRT_INVALID_INDEX)
+                    closer = curInst < R.hitInst || (curInst == R.hitInst && prim < R.hitPrim);
+                if (!closer) continue;
+                if (curFlags & INSTANCE_FLAG_ALPHA_TESTED) {
+                    const uint32_t seed = R.anyHit ? __ldg(P.shSeed + (R.index - extCount)) : (P.raySeed ? __ldg(P.raySeed + R.index) : 0u);
+                    if (!alphaHitAccepted(P.scene, curInst, prim, float2(u, v), seed)) continue;
+                }
+                if (R.anyHit) {
+                    if (curFlags & INSTANCE_FLAG_TRANSMISSIVE) {
+                        R.sawTransmissive = true;   // keep looking for an opaque occluder, but not in this instance
+                        sp = blasBase;
+                        G = make_uint2(0u, 0u);
+                        Gt.y = 0u;
+                    } else {
+                        R.hitInst = curInst;        // occluded: done
+                        R.hitPrim = prim;
+                        sp = 0;
+                        inBlas = false;
+                        G = make_uint2(0u, 0u);
+                        Gt.y = 0u;
+                    }
+                    break;
+                }
+                R.hitInst = curInst;
+                R.hitPrim = prim;
+                R.tBest = t;
+                R.hitU = u;
+                R.hitV = v;
+            }
+
+            if ((G.y & 0xff000000u) == 0u) {
+                if (inBlas && sp == blasBase) {  // BLAS exhausted: back to the world-space ray
+                    inBlas = false;
+                    o = R.o; d = R.d;
+                    idir = safeInvDir(d);
+                    octinv = 7u ^ ((d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u));
+                }
+                if (sp == 0) {
+                    // ---- ray finished: write back ----------------------------------------------------------------
+                    if (!R.anyHit) {
+                        P.hitA[R.index] = make_uint4(R.hitInst, R.hitPrim, __float_as_uint(R.hitInst != VKRT_INVALID_INDEX ? R.tBest : 0.0f),
+                                                      __float_as_uint(R.hitU));
+                        P.hitB[R.index] = R.hitV;
+                    } else {
+                        const uint32_t k = R.index - extCount;
+                        const bool occluded = R.hitInst != VKRT_INVALID_INDEX;
+                        if (P.shadowResult) P.shadowResult[k] = occluded ? 1u : (R.sawTransmissive ? 2u : 0u);
+                        if (P.shTarget) {
+                            const ::uint2 target = __ldg(P.shTarget + k);
+                            if (!occluded && !R.sawTransmissive) {
+                                const ::float4 c = __ldg(P.shContribution + k);
+                                if (target.y & SHADOW_KIND_SCALAR) {
+                                    P.radianceScalar[target.x] += c.x;
+                                } else {
+                                    ::float4 r = P.radiance[target.x];
+                                    r.x += c.x; r.y += c.y; r.z += c.z; r.w += c.w;
+                                    P.radiance[target.x] = r;
+                                }
+                            } else if (!occluded) {  // unsupported transmission: NEE is not trusted at this vertex
+                                const uint32_t pos = target.y & 0x7fffffffu;
+                                if (pos != 0x7fffffffu) P.pathFlags[pos] &= ~1u;
+                            }
+                        }
+                    }
+                    R.active = false;
+                    break;
+                }
+                G = stack[--sp];
+            }
+            if (!exhausted && __popc(__activemask()) < REFILL_THRESHOLD) break;
+        }
+    }
+    if (COUNT && P.stats) {
+        atomicAdd(&P.stats[0], nNodes);
+        atomicAdd(&P.stats[1], nTris);
+        atomicAdd(&P.stats[2], nInst);
+    }
+}
+
+} // namespace vk

@@ -1,0 +1,848 @@
+// wavefront.cu — raygen / shade / film kernels of the wavefront path tracer (sm_100a).
+//
+// Restates, stage by stage, the reference's raygen megakernels:
+//   src/shaders/entry/path/raygen_{rgb,spectral_single,spectral_hero}.slang          -> k_raygen + k_film
+//   src/shaders/integrator/path/{rgb,spectral_single,spectral_hero}/integrator.slang  -> k_shade<MODE> (one depth per launch)
+//   src/shaders/integrator/path/writeback.slang                                       -> k_film
+// RNG order per path is the reference's: the single uint rng travels in the path state and is
+// consumed as jitter(2) [, wavelength(1)], then per depth NEE(4) -> BSDF selector + lobe -> RR(1).
+#include <cooperative_groups.h>
+
+#include "wavefront.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace vk {
+
+constexpr int MODE_RGB = 0, MODE_SINGLE = 1, MODE_HERO = 2;
+
+// ---- pinned-arithmetic camera (camera/ray.slang:15-30): identical roundings to the oracle so that primary rays, and
+// therefore primary-hit ids, are bit-exact ---------------------------------------------------------------------------
+__device__ __forceinline__ float4 mulMat4Exact(const float* m, float4 v) {
+    auto row = [&](int r) {
+        return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[r], v.x), __fmul_rn(m[4 + r], v.y)), __fmul_rn(m[8 + r], v.z)), __fmul_rn(m[12 + r], v.w));
+    };
+    return float4(row(0), row(1), row(2), row(3));
+}
+__device__ __forceinline__ Ray makePrimaryRayExact(const SceneData& scene, int px, int py, float2 jitter) {
+    const int ox = int(scene.viewportRect[0]), oy = int(scene.viewportRect[1]);
+    const float vw = float(scene.viewportRect[2]), vh = float(scene.viewportRect[3]);
+    const float vx = __fadd_rn(__fadd_rn(float(px - ox), 0.5f), jitter.x);
+    const float vy = __fadd_rn(__fadd_rn(float(py - oy), 0.5f), jitter.y);
+    const float u = __fdiv_rn(vx, vw), v = __fdiv_rn(vy, vh);
+    const float nx = __fsub_rn(__fmul_rn(u, 2.0f), 1.0f), ny = __fsub_rn(__fmul_rn(v, 2.0f), 1.0f);
+    const float4 viewDir = mulMat4Exact(scene.projInverse, float4(nx, ny, 1.0f, 1.0f));
+    const float4 org = mulMat4Exact(scene.viewInverse, float4(0.0f, 0.0f, 0.0f, 1.0f));
+    const float4 dir = mulMat4Exact(scene.viewInverse, float4(viewDir.x, viewDir.y, viewDir.z, 0.0f));
+    const float len2 = __fadd_rn(__fadd_rn(__fmul_rn(dir.x, dir.x), __fmul_rn(dir.y, dir.y)), __fmul_rn(dir.z, dir.z));
+    const float inv = __fdiv_rn(1.0f, __fsqrt_rn(len2));
+    Ray r;
+    r.origin = float3(org.x, org.y, org.z);
+    r.direction = float3(__fmul_rn(dir.x, inv), __fmul_rn(dir.y, inv), __fmul_rn(dir.z, inv));
+    r.tMin = RAY_T_MIN;
+    r.tMax = RAY_T_MAX;
+    return r;
+}
+
+__device__ __forceinline__ ::float4 toF4(float3 v, float w) { return make_float4(v.x, v.y, v.z, w); }
+__device__ __forceinline__ ::float4 toF4(float4 v) { return make_float4(v.x, v.y, v.z, v.w); }
+__device__ __forceinline__ float4 fromF4(::float4 v) { return float4(v.x, v.y, v.z, v.w); }
+
+__device__ __forceinline__ uint32_t allocSlots(uint32_t* counter) {
+    cg::coalesced_group g = cg::coalesced_threads();
+    uint32_t base = 0;
+    if (g.thread_rank() == 0) base = atomicAdd(counter, g.size());
+    return g.shfl(base, 0) + g.thread_rank();
+}
+
+__device__ __forceinline__ float4 heroWavelengths(float unit) {
+    return WAVELENGTH_MIN_NM + frac(unit + float4(0.0f, 0.25f, 0.5f, 0.75f)) * WAVELENGTH_RANGE_NM;
+}
+
+// ----------------------------------------------------------------------------------------------------------------------
+// raygen: RaygenPixelState + PathCommonState.initCommon (integrator/path/state.slang:60-79,140-146,160-196)
+// ----------------------------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) k_raygen(const FrameParams fp) {
+    const uint32_t lpc = fp.tiles.localPixelCount;
+    const uint32_t total = fp.chunkSamples * lpc;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        // zero the sample record (coalesced)
+        fp.rec.radiance[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        fp.rec.featA[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        fp.rec.featB[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        fp.rec.follow[t] = 0.0f;
+        if (MODE == MODE_HERO) fp.rec.radianceScalar[t] = 0.0f;
+        const uint32_t s = t / lpc, lp = t - s * lpc;
+        uint32_t gx, gy;
+        if (!localPixelToGlobal(fp.tiles, fp.tiles.localToGlobalTile, lp, gx, gy)) continue;
+        if (!insideViewport(fp.sd, (int)gx, (int)gy)) continue;
+        const float prevW = fp.film.accum[fp.readIndex][lp].w;
+        const uint32_t previousSamples = (uint32_t)(prevW + 0.5f);
+        const uint32_t sampleIndex = fp.chunkFirstSample + s;
+        uint32_t rng = initPixelSeed((int)gx, (int)gy, fp.sd.frameNumber, previousSamples + sampleIndex);
+        const float jx = rand(rng);
+        const float jy = rand(rng);
+        const Ray ray = makePrimaryRayExact(fp.sd, (int)gx, (int)gy, float2(__fsub_rn(jx, 0.5f), __fsub_rn(jy, 0.5f)));
+        float unit = 0.0f;
+        if (MODE != MODE_RGB) {
+            unit = sampleUniformWavelengthUnit(rng, previousSamples + sampleIndex);
+            fp.rec.unitWavelength[t] = unit;
+        }
+        const uint32_t j = allocSlots(fp.extCount);
+        const PathState& S = fp.st[0];
+        S.rayO[j] = toF4(ray.origin, ray.tMin);
+        S.rayD[j] = toF4(ray.direction, ray.tMax);
+        S.record[j] = t;
+        S.rng[j] = rng;
+        if (MODE == MODE_RGB) {
+            S.flags[j] = 0u;
+            S.thr[j] = make_float4(1.f, 1.f, 1.f, 0.f);
+        } else if (MODE == MODE_SINGLE) {
+            S.flags[j] = 0u;
+            const float lambda = WAVELENGTH_MIN_NM + saturate(unit) * WAVELENGTH_RANGE_NM;
+            S.thr[j] = make_float4(1.f, lambda, 0.f, 0.f);
+        } else {
+            S.flags[j] = PF_HERO_ACTIVE;
+            S.thr[j] = make_float4(1.f, 1.f, 1.f, 1.f);
+            S.techPdf[j] = make_float4(1.f, 1.f, 1.f, 1.f);
+            S.prevVertexTechPdf[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            S.prevBsdfTechPdf[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            S.heroMisc[j] = make_float4(unit, 1.f, 0.f, 0.f);
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------------------
+// Surface reconstruction (geometry/surface/reconstruct.slang:8-49, integrator/path/surface_state.slang:8-31)
+// ----------------------------------------------------------------------------------------------------------------------
+struct SurfaceShadingData {
+    uint32_t materialIndex;
+    uint32_t frontFace;
+    float3 shadingNormal, geometricNormal;
+    float4 tangent;
+    SurfaceTextureData textureData;
+};
+
+__device__ __forceinline__ SurfaceShadingData reconstructSurfaceShading(const SceneView& sc, const MeshInfo& mesh, uint32_t prim, float2 bary,
+                                                                        float3 worldRayDir) {
+    TriangleVertices tv;
+    loadTriangleVertices(sc, mesh, prim, tv);
+    float3 objectNormal = safeNormalize(interp3(unpackOctNormal(tv.v0.packedNormal), unpackOctNormal(tv.v1.packedNormal),
+                                                unpackOctNormal(tv.v2.packedNormal), bary));
+    float4 objectTangent = interp4(unpackOctTangent(tv.v0.packedTangent), unpackOctTangent(tv.v1.packedTangent),
+                                   unpackOctTangent(tv.v2.packedTangent), bary);
+    float handedness = objectTangent.w < 0.0f ? -1.0f : 1.0f;
+    float3 shadingNormalUnoriented = meshTransformNormal(mesh, objectNormal);
+    float facing = dot(shadingNormalUnoriented, worldRayDir) > 0.0f ? -1.0f : 1.0f;
+    float3 p0(tv.v0.position[0], tv.v0.position[1], tv.v0.position[2]);
+    float3 p1(tv.v1.position[0], tv.v1.position[1], tv.v1.position[2]);
+    float3 p2(tv.v2.position[0], tv.v2.position[1], tv.v2.position[2]);
+    float3 worldEdge1 = meshTransformVector(mesh, p1 - p0);
+    float3 worldEdge2 = meshTransformVector(mesh, p2 - p0);
+    float3 geometricNormal = safeNormalize(cross(worldEdge1, worldEdge2));
+    if (surfaceTransformSign(mesh) < 0.0f) geometricNormal = -geometricNormal;
+    SurfaceShadingData hit;
+    hit.materialIndex = mesh.materialIndex;
+    hit.frontFace = dot(geometricNormal, worldRayDir) < 0.0f ? 1u : 0u;
+    hit.shadingNormal = shadingNormalUnoriented * facing;
+    hit.geometricNormal = hit.frontFace != 0u ? geometricNormal : -geometricNormal;
+    hit.tangent = float4(safeNormalize(meshTransformVector(mesh, objectTangent.xyz())) * facing, handedness);
+    hit.textureData = evaluateSurfaceTextureData(tv, bary);
+    return hit;
+}
+
+// material/textures.slang:123-155
+__device__ __forceinline__ void applySurfaceTextures(const SceneView& sc, Material& m, const SurfaceTextureData& s) {
+    float4 bc = sampleBaseColorTexture(sc, m, s);
+    m.baseColor[0] *= bc.x * s.color.x;
+    m.baseColor[1] *= bc.y * s.color.y;
+    m.baseColor[2] *= bc.z * s.color.z;
+    float4 mr = sampleMetallicRoughnessTexture(sc, m, s);
+    m.roughness = saturate(m.roughness * mr.y);
+    m.metallic = saturate(m.metallic * mr.z);
+    float4 et = sampleEmissiveTexture(sc, m, s);
+    float3 emission = float3(m.emissionColor[0], m.emissionColor[1], m.emissionColor[2]) * m.emissionLuminance * et.xyz();
+    float emissionMax = maxComponent(emission);
+    if (emissionMax > 0.0f) {
+        float3 ec = emission / emissionMax;
+        m.emissionColor[0] = ec.x; m.emissionColor[1] = ec.y; m.emissionColor[2] = ec.z;
+        m.emissionLuminance = emissionMax;
+    } else {
+        m.emissionColor[0] = m.emissionColor[1] = m.emissionColor[2] = 1.0f;
+        m.emissionLuminance = 0.0f;
+    }
+}
+__device__ __forceinline__ float3 applyNormalTexture(const SceneView& sc, const Material& m, const SurfaceTextureData& s, const ShadingBasis& basis) {
+    if (m.normalTextureIndex == VKRT_INVALID_INDEX) return basis.normal;
+    float3 ns = sampleNormalTexture(sc, m, s).xyz() * 2.0f - 1.0f;
+    ns.x *= m.normalTextureScale;
+    ns.y *= m.normalTextureScale;
+    ns = safeNormalize(ns);
+    return safeNormalize(basis.tangent * ns.x + basis.bitangent * ns.y + basis.normal * ns.z);
+}
+
+__device__ __forceinline__ Material loadMaterial(const Material* p) {
+    // 272-byte material = 17 x 16-byte read-only loads (L1/L2 resident: a scene has few materials)
+    Material m;
+    const ::float4* q = reinterpret_cast<const ::float4*>(p);
+    ::float4* d = reinterpret_cast<::float4*>(&m);
+#pragma unroll
+    for (int i = 0; i < 17; i++) d[i] = __ldg(q + i);
+    return m;
+}
+__device__ __forceinline__ MeshInfo loadMeshInfo(const MeshInfo* p) {
+    MeshInfo m;
+    const ::float4* q = reinterpret_cast<const ::float4*>(p);
+    ::float4* d = reinterpret_cast<::float4*>(&m);
+#pragma unroll
+    for (int i = 0; i < 5; i++) d[i] = __ldg(q + i);
+    return m;
+}
+
+// light/environment.slang:9-27
+__device__ __forceinline__ float3 sampleEnvironmentRadiance(const SceneView& sc, const SceneData& scene, float3 worldDir) {
+    if (scene.environmentTextureIndex == VKRT_INVALID_INDEX)
+        return float3(scene.environmentLight[0], scene.environmentLight[1], scene.environmentLight[2]);
+    float3 dir = normalize(worldDir);
+    float phi = atan2f(dir.y, dir.x) + scene.environmentRotation * (PI / 180.0f);
+    float theta = acosf(clamp(dir.z, -1.0f, 1.0f));
+    float2 uv(frac(phi * (0.5f * INV_PI) + 0.5f), theta * INV_PI);
+    float3 radiance = sampleTextureBilinear(sc, scene.environmentTextureIndex, uv, VKRT_TEXTURE_WRAP_REPEAT, VKRT_TEXTURE_WRAP_CLAMP_TO_EDGE).xyz();
+    return radiance * scene.environmentLight[3];
+}
+
+// light/direct/light_sampling.slang:9-63
+struct DirectLightSurfaceSample {
+    float3 emission, wi;
+    float shadowDistance, pdfSolidAngle;
+    bool valid;
+};
+__device__ __forceinline__ DirectLightSurfaceSample sampleDirectLightSurface(const SceneView& sc, const SceneData& scene, float3 hitPoint, uint& rng) {
+    DirectLightSurfaceSample s;
+    s.valid = false;
+    s.shadowDistance = s.pdfSolidAngle = 0.0f;
+    const uint meshCount = scene.emissiveMeshCount;
+    if (meshCount == 0u) return s;
+    const uint meshIdx = sampleAlias(rand(rng), meshCount, 0u, sc.meshAliasQ, sc.meshAliasIdx);
+    const EmissiveMesh em = sc.emissiveMeshes[meshIdx];
+    if (em.triCount == 0u) return s;
+    const uint localTri = sampleAlias(rand(rng), em.triCount, em.triOffset, sc.triAliasQ, sc.triAliasIdx);
+    const ::float4* tp = reinterpret_cast<const ::float4*>(sc.emissiveTriangles + em.triOffset + localTri);
+    const ::float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+    const float u1 = rand(rng);
+    const float u2 = rand(rng);
+    const float sqrtU1 = sqrt(u1);
+    const float b1 = u2 * sqrtU1;
+    const float b2 = (1.0f - u2) * sqrtU1;
+    const float3 v0(t0.x, t0.y, t0.z), e1(t1.x, t1.y, t1.z), e2(t2.x, t2.y, t2.z);
+    const float3 position = v0 + b1 * e1 + b2 * e2;
+    const float3 normal = safeNormalize(cross(e1, e2));
+    s.emission = float3(em.emission[0], em.emission[1], em.emission[2]);
+    const float pdf = em.pmfMesh * em.invTotalArea;
+    if (!(pdf > 0.0f)) return s;
+    const float3 toLight = position - hitPoint;
+    const float d2 = dot(toLight, toLight);
+    if (d2 <= 0.0f) return s;
+    const float invD = rsqrt(d2);
+    const float distance = d2 * invD;
+    s.wi = toLight * invD;
+    const float cosLight = abs(dot(s.wi, normal));
+    if (cosLight <= 0.0f) return s;
+    s.pdfSolidAngle = pdf * d2 / cosLight;
+    if (s.pdfSolidAngle <= 0.0f) return s;
+    s.shadowDistance = distance - SHADOW_DISTANCE_OFFSET;
+    if (s.shadowDistance <= 0.0f) return s;
+    s.valid = true;
+    return s;
+}
+
+// light/direct/mis_weights.slang:6-42
+__device__ __forceinline__ float lightPdfAreaToSolidAngle(float lightPdfArea, float3 gn, float3 rd, float hitDistance) {
+    if (lightPdfArea <= 0.0f) return 0.0f;
+    float d2 = hitDistance * hitDistance;
+    if (d2 <= 0.0f) return 0.0f;
+    float cosLight = abs(dot(rd, gn));
+    if (cosLight <= 0.0f) return 0.0f;
+    return lightPdfArea * d2 / cosLight;
+}
+__device__ __forceinline__ float computeSpectralMISWeight(float4 sampled, float4 alternate) {
+    float denom = dot(sampled, float4(1.0f)) + dot(alternate, float4(1.0f));
+    return denom > 0.0f ? sampled.x / denom : 0.0f;
+}
+
+// ----------------------------------------------------------------------------------------------------------------------
+// shade: one path vertex (the body of the reference's depth loop between two TraceRay calls)
+// ----------------------------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(128) k_shade(const FrameParams fp, const uint32_t depth) {
+    const uint32_t count = fp.extCount[depth];
+    const PathState& S = fp.st[depth & 1u];
+    const PathState& N = fp.st[(depth & 1u) ^ 1u];
+    const SceneView& sc = fp.scene;
+    const SceneData& scene = fp.sd;
+    const SpectralTables& T = sc.spectral;
+    const uint32_t lpc = fp.tiles.localPixelCount;
+    const bool neeEnabled = (fp.modeFlags & MODE_NEE_ENABLED) && !(fp.modeFlags & MODE_BSDF_ONLY);
+    const bool neeOnly = (fp.modeFlags & MODE_NEE_ONLY) != 0u;
+
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const ::float4 ro = S.rayO[i], rd = S.rayD[i];
+        const ::uint4 ha = fp.hitA[i];
+        const uint32_t rec = S.record[i];
+        uint32_t rng = S.rng[i];
+        uint32_t flags = S.flags[i];
+        const ::float4 thrRaw = S.thr[i];
+        Ray ray;
+        ray.origin = float3(ro.x, ro.y, ro.z);
+        ray.direction = float3(rd.x, rd.y, rd.z);
+        const uint32_t hitInst = ha.x, hitPrim = ha.y;
+        const float hitT = __uint_as_float(ha.z);
+        const uint32_t sampleInChunk = rec / lpc;
+        const uint32_t lp = rec - sampleInChunk * lpc;
+        const uint32_t sampleIndex = fp.chunkFirstSample + sampleInChunk;
+
+        // ---- unpack mode state ---------------------------------------------------------------------------------
+        float3 thrRgb(0.0f);
+        float thrScalar = 0.0f, prevBsdfPdf = 0.0f, lambdaScalar = 0.0f, unit = 0.0f;
+        float4 thr4(0.0f), wl4(0.0f), techPdf(0.0f);
+        bool heroActive = false;
+        if (MODE == MODE_RGB) {
+            thrRgb = float3(thrRaw.x, thrRaw.y, thrRaw.z);
+            prevBsdfPdf = thrRaw.w;
+        } else if (MODE == MODE_SINGLE) {
+            thrScalar = thrRaw.x;
+            lambdaScalar = thrRaw.y;
+            prevBsdfPdf = thrRaw.z;
+        } else {
+            thr4 = fromF4(thrRaw);
+            const ::float4 misc = S.heroMisc[i];
+            unit = misc.x;
+            thrScalar = misc.y;
+            prevBsdfPdf = misc.z;
+            wl4 = heroWavelengths(unit);
+            lambdaScalar = wl4.x;
+            heroActive = (flags & PF_HERO_ACTIVE) != 0u;
+            techPdf = fromF4(S.techPdf[i]);
+        }
+        MediumState medium;
+        medium.flags = (flags >> 1) & 3u;
+        if (medium.absorptionActive()) {
+            const ::float4 sg = S.sigma[i];
+            medium.absorptionSigma = float3(sg.x, sg.y, sg.z);
+            medium.spectralAbsorptionSigma = fromF4(sg);
+            if (MODE == MODE_SINGLE || (MODE == MODE_HERO && !heroActive)) medium.spectralAbsorptionSigma = float4(sg.x);
+        }
+
+        // ---- miss: environment (loop.slang:4-6, */transport.slang accumulate*Environment) -------------------------
+        if (hitInst == VKRT_INVALID_INDEX) {
+            if (!neeOnly && !mediumHasActiveBoundary(medium)) {
+                const float3 env = sampleEnvironmentRadiance(sc, scene, ray.direction);
+                if (MODE == MODE_RGB) {
+                    ::float4 r = fp.rec.radiance[rec];
+                    const float3 c = thrRgb * env;
+                    r.x += c.x; r.y += c.y; r.z += c.z;
+                    fp.rec.radiance[rec] = r;
+                } else if (MODE == MODE_SINGLE) {
+                    fp.rec.radiance[rec].x += thrScalar * spectralScalarFromLinearSrgb(T, env, lambdaScalar);
+                } else if (heroActive) {
+                    const float4 c = thr4 * heroWavelengthBalanceWeight(techPdf) * spectralScalarFromLinearSrgb4(T, env, wl4);
+                    ::float4 r = fp.rec.radiance[rec];
+                    r.x += c.x; r.y += c.y; r.z += c.z; r.w += c.w;
+                    fp.rec.radiance[rec] = r;
+                } else {
+                    fp.rec.radianceScalar[rec] += thrScalar * spectralScalarFromLinearSrgb(T, env, lambdaScalar);
+                }
+            }
+            continue;
+        }
+
+        // ---- medium transmittance along the segment (apply*MediumTransmittance) ------------------------------------
+        if (medium.absorptionActive()) {
+            if (MODE == MODE_RGB) thrRgb *= mediumTransmittance(medium, hitT);
+            else if (MODE == MODE_HERO && heroActive) thr4 *= mediumSpectralTransmittance(medium, hitT);
+            else thrScalar *= mediumTransmittance(medium, hitT).x;
+        }
+        {
+            const bool alive = MODE == MODE_RGB ? anyGreater(thrRgb, 0.0f)
+                                                : ((MODE == MODE_HERO && heroActive) ? anyGreater(thr4, 0.0f) : thrScalar > 0.0f);
+            if (!alive) continue;
+        }
+
+        // ---- surface (PathSurfaceState.__init) -----------------------------------------------------------------------
+        const MeshInfo mesh = loadMeshInfo(sc.meshInfos + hitInst);
+        const float3 hitPoint = ray.origin + ray.direction * hitT;
+        SurfaceShadingData surface = reconstructSurfaceShading(sc, mesh, hitPrim, float2(__uint_as_float(ha.w), fp.hitB[i]), ray.direction);
+        Material material = loadMaterial(sc.materials + surface.materialIndex);
+        {
+            const ShadingBasis unperturbed = makeShadingBasis(surface.shadingNormal, surface.tangent);
+            surface.shadingNormal = applyNormalTexture(sc, material, surface.textureData, unperturbed);
+        }
+        surface.shadingNormal = sanitizeShadingNormal(surface.shadingNormal, surface.geometricNormal, -ray.direction);
+        const ShadingBasis basis = makeShadingBasis(surface.shadingNormal, surface.tangent);
+        applySurfaceTextures(sc, material, surface.textureData);
+        const BSDFMaterial bm(material);
+
+        // ---- primary-surface debug views (integrator/path/debug.slang:31-64) -----------------------------------------
+        if (sampleIndex == 0u && depth == 0u && scene.debugMode != VKRT_DEBUG_MODE_NONE) {
+            const uint32_t dm = scene.debugMode;
+            bool handled = true;
+            float3 c(0.0f);
+            if (dm == VKRT_DEBUG_MODE_NORMALS) c = surface.shadingNormal * 0.5f + 0.5f;
+            else if (dm == VKRT_DEBUG_MODE_DEPTH) c = float3(1.0f / (1.0f + hitT));
+            else if (dm == VKRT_DEBUG_MODE_BASE_COLOR_MAP) c = sampleBaseColorTexture(sc, material, surface.textureData).xyz();
+            else if (dm == VKRT_DEBUG_MODE_METALLIC_MAP) c = float3(sampleMetallicRoughnessTexture(sc, material, surface.textureData).z);
+            else if (dm == VKRT_DEBUG_MODE_ROUGHNESS_MAP) c = float3(sampleMetallicRoughnessTexture(sc, material, surface.textureData).y);
+            else if (dm == VKRT_DEBUG_MODE_NORMAL_MAP) c = sampleNormalTexture(sc, material, surface.textureData).xyz();
+            else if (dm == VKRT_DEBUG_MODE_EMISSIVE_MAP) c = sampleEmissiveTexture(sc, material, surface.textureData).xyz();
+            else handled = false;
+            if (handled) {
+                fp.film.debugColor[lp] = toF4(c, 1.0f);
+                continue;
+            }
+        }
+
+        // ---- denoiser features (loop.slang:83-103) ----------------------------------------------------------------
+        {
+            const bool follow = materialDenoiserShouldFollowSpecularHit(bm, surface.frontFace);
+            if (depth == 0u) fp.rec.follow[rec] = follow ? 1.0f : 0.0f;
+            if (!(flags & PF_FEATURES_RESOLVED) && !follow) {
+                fp.rec.featA[rec] = toF4(materialDenoiserAlbedo(bm), 1.0f);
+                fp.rec.featB[rec] = toF4(surface.shadingNormal, float(depth + 1u));
+                flags |= PF_FEATURES_RESOLVED;
+            }
+        }
+
+        const float stateWavelength = MODE == MODE_RGB ? 0.0f : lambdaScalar;
+        const BSDFState state(bm, worldToLocal(-ray.direction, basis), surface.frontFace, stateWavelength, MODE == MODE_RGB ? 0u : 1u);
+        const bool currentVertexNeeAllowed = !medium.refractiveActive();
+
+        // ---- next-event estimation (light/direct/*.slang); the shadow ray is traced by the next k_trace launch ---------
+        bool shadowPending = false;
+        ::float4 shadowO, shadowD, shadowC;
+        uint32_t shadowSeed = 0u;
+        bool shadowScalarLane = false;
+        if (neeEnabled && currentVertexNeeAllowed && cosTheta(state.wo) > 0.0f) {
+            const DirectLightSurfaceSample ls = sampleDirectLightSurface(sc, scene, hitPoint, rng);
+            if (ls.valid) {
+                const float3 shadowOffset = dot(ls.wi, surface.geometricNormal) >= 0.0f ? surface.geometricNormal : -surface.geometricNormal;
+                const float3 shadowOrigin = hitPoint + shadowOffset * SHADOW_ORIGIN_OFFSET;
+                const float3 wiLocal = worldToLocal(ls.wi, basis);
+                // common.slang:47-50 rejects the sample after the visibility test; evaluating it first and skipping the
+                // ray is equivalent for the radiance and only changes what "unsupported transmission" can observe when the
+                // contribution is zero anyway -- so the shadow ray is always traced when the light sample is valid.
+                float4 c(0.0f);
+                const bool refractiveReject = materialMediumIsRefractive(state.material) && cosTheta(wiLocal) <= 0.0f;
+                if (!refractiveReject) {
+                    if (MODE == MODE_RGB) {
+                        const BSDFEval e = evalBSDF(T, state, wiLocal);
+                        if (e.pdf > 0.0f) {
+                            const float misWeight = powerHeuristic(ls.pdfSolidAngle, e.pdf);
+                            const float3 fCos = e.value * absCosTheta(wiLocal);
+                            const float3 r = misWeight * mediumTransmittance(medium, ls.shadowDistance) * fCos * ls.emission / ls.pdfSolidAngle;
+                            const float3 tr = thrRgb * r;
+                            c = float4(tr.x, tr.y, tr.z, 0.0f);
+                        }
+                    } else if (MODE == MODE_HERO && heroActive) {
+                        float4 localTp(0.0f);
+                        const float4 fCos = evalSpectralBSDF(T, state, wiLocal, wl4, localTp) * absCosTheta(wiLocal);
+                        const float misWeight = computeSpectralMISWeight(techPdf * ls.pdfSolidAngle, techPdf * localTp);
+                        if (misWeight > 0.0f) {
+                            c = thr4 * (misWeight * mediumSpectralTransmittance(medium, ls.shadowDistance) * fCos *
+                                        spectralScalarFromLinearSrgb4(T, ls.emission, wl4) / ls.pdfSolidAngle);
+                        }
+                    } else {
+                        const BSDFEval e = evalSingleWavelengthBSDF(T, state, wiLocal);
+                        if (e.pdf > 0.0f) {
+                            const float sv = e.value.x * absCosTheta(wiLocal) * spectralScalarFromLinearSrgb(T, ls.emission, lambdaScalar);
+                            const float misWeight = powerHeuristic(ls.pdfSolidAngle, e.pdf);
+                            c.x = thrScalar * (misWeight * mediumTransmittance(medium, ls.shadowDistance).x * sv / ls.pdfSolidAngle);
+                            shadowScalarLane = MODE == MODE_HERO;
+                        }
+                    }
+                }
+                shadowPending = true;
+                shadowO = toF4(shadowOrigin, RAY_T_MIN);
+                shadowD = toF4(ls.wi, ls.shadowDistance);
+                shadowC = toF4(c);
+                shadowSeed = rng;
+            }
+        }
+
+        // ---- emission seen by BSDF sampling (integrator.slang:79-85; hero: integrator.slang:98-126) -------------------
+        if (!neeOnly) {
+            const float3 emission = float3(material.emissionColor[0], material.emissionColor[1], material.emissionColor[2]) * material.emissionLuminance;
+            if (anyGreater(emission, 0.0f)) {
+                const bool misActive = (fp.modeFlags & MODE_NEE_ENABLED) && (flags & PF_PREV_VERTEX_NEE_ALLOWED) && depth > 0u;
+                if (MODE == MODE_HERO && heroActive) {
+                    float misWeight = heroWavelengthBalanceWeight(techPdf);
+                    if (misActive) {
+                        const float lp2 = lightPdfAreaToSolidAngle(mesh.lightPdfArea, surface.geometricNormal, ray.direction, hitT);
+                        const float4 pv = fromF4(S.prevVertexTechPdf[i]), pb = fromF4(S.prevBsdfTechPdf[i]);
+                        misWeight = computeSpectralMISWeight(pv * pb, pv * lp2);
+                    }
+                    const float4 c = thr4 * (spectralScalarFromLinearSrgb4(T, emission, wl4) * misWeight);
+                    ::float4 r = fp.rec.radiance[rec];
+                    r.x += c.x; r.y += c.y; r.z += c.z; r.w += c.w;
+                    fp.rec.radiance[rec] = r;
+                } else {
+                    float misWeight = 1.0f;
+                    if (misActive && prevBsdfPdf > 0.0f) {
+                        const float lp2 = lightPdfAreaToSolidAngle(mesh.lightPdfArea, surface.geometricNormal, ray.direction, hitT);
+                        misWeight = lp2 <= 0.0f ? 1.0f : powerHeuristic(prevBsdfPdf, lp2);
+                    }
+                    if (MODE == MODE_RGB) {
+                        const float3 c = thrRgb * (emission * misWeight);
+                        ::float4 r = fp.rec.radiance[rec];
+                        r.x += c.x; r.y += c.y; r.z += c.z;
+                        fp.rec.radiance[rec] = r;
+                    } else {
+                        const float c = thrScalar * (spectralScalarFromLinearSrgb(T, emission, lambdaScalar) * misWeight);
+                        if (MODE == MODE_SINGLE) fp.rec.radiance[rec].x += c;
+                        else fp.rec.radianceScalar[rec] += c;
+                    }
+                }
+            }
+        }
+        if ((fp.modeFlags & MODE_BOUNCE_COUNT) && sampleIndex == 0u) fp.film.bounceCount[lp] = depth + 1u;
+
+        // ---- sample the next direction (sample*NextDirection) -------------------------------------------------------
+        bool pathContinues = true;
+        uint32_t isTransmission = 0u;
+        float3 wi(0.0f);
+        float4 newPrevVertexTechPdf(0.0f), newPrevBsdfTechPdf(0.0f);
+        if (MODE == MODE_HERO && heroActive) {
+            const SpectralBSDFSample smp = sampleSpectralBSDF(T, state, basis, wl4, rng);
+            if (!smp.isUsable()) pathContinues = false;
+            if (pathContinues) {
+                newPrevVertexTechPdf = techPdf;
+                newPrevBsdfTechPdf = smp.techniquePdf;
+                techPdf *= smp.techniquePdf;
+                thr4 *= smp.weight;
+                if (!anyGreater(thr4, 0.0f)) pathContinues = false;
+            }
+            if (pathContinues) {
+                if (smp.isTransmission != 0u && materialMediumIsRefractive(bm) && bm.abbeNumber > 0.0f) {
+                    // dispersive collapse (spectral_hero/transport.slang:77-87). The 4-lane radiance stays in the record and
+                    // is converted to XYZ by the film kernel together with the scalar lane.
+                    thrScalar = thr4.x;
+                    thr4 = float4(0.0f);
+                    prevBsdfPdf = smp.techniquePdf.x;
+                    heroActive = false;
+                    flags &= ~PF_HERO_ACTIVE;
+                }
+                isTransmission = smp.isTransmission;
+                wi = smp.wi;
+            }
+        } else {
+            const BSDFSample smp = sampleBSDF(T, state, basis, rng);
+            if (!smp.isUsable()) pathContinues = false;
+            if (pathContinues) {
+                if (MODE == MODE_RGB) {
+                    thrRgb *= smp.weight;
+                    if (!anyGreater(thrRgb, 0.0f)) pathContinues = false;
+                } else {
+                    thrScalar *= smp.weight.x;
+                    if (thrScalar <= 0.0f) pathContinues = false;
+                }
+                prevBsdfPdf = smp.pdf;
+                isTransmission = smp.isTransmission;
+                wi = smp.wi;
+            }
+        }
+
+        if (pathContinues) {
+            // medium update + NEE bookkeeping (integrator.slang:96-98)
+            if (MODE == MODE_RGB) updateMediumStateFromTransmission(T, bm, surface.frontFace, isTransmission, 0.0f, 0u, medium);
+            else if (MODE == MODE_HERO && heroActive) updateMediumStateFromTransmissionSpectral(T, bm, surface.frontFace, isTransmission, wl4, medium);
+            else updateMediumStateFromTransmission(T, bm, surface.frontFace, isTransmission, lambdaScalar, 1u, medium);
+            const bool sampledPathNeeAllowed = currentVertexNeeAllowed && isTransmission == 0u;  // shadow kernel clears it on "unsupported"
+            flags = (flags & ~(PF_PREV_VERTEX_NEE_ALLOWED | PF_MEDIUM_REFRACTIVE | PF_MEDIUM_ABSORPTION)) |
+                    (sampledPathNeeAllowed ? PF_PREV_VERTEX_NEE_ALLOWED : 0u) | (medium.flags << 1);
+            // Russian roulette (integrator.slang:100-106)
+            if (depth + 1u >= scene.rrMinDepth) {
+                float cp;
+                if (MODE == MODE_RGB) cp = clamp(maxComponent(thrRgb), RR_MIN_CONTINUE_PROB, RR_MAX_CONTINUE_PROB);
+                else if (MODE == MODE_HERO && heroActive) cp = clamp(maxComponent4(thr4), RR_MIN_CONTINUE_PROB, RR_MAX_CONTINUE_PROB);
+                else cp = clamp(thrScalar, RR_MIN_CONTINUE_PROB, RR_MAX_CONTINUE_PROB);
+                if (rand(rng) > cp) {
+                    pathContinues = false;
+                } else if (MODE == MODE_RGB) {
+                    thrRgb /= cp;
+                } else if (MODE == MODE_HERO && heroActive) {
+                    techPdf *= float4(cp);
+                    thr4 /= cp;
+                } else {
+                    thrScalar /= cp;
+                }
+            }
+        }
+        if (depth + 1u >= scene.rrMaxDepth) pathContinues = false;
+
+        // ---- write the continuing path at its new (compacted) position ------------------------------------------------
+        uint32_t newPos = 0x7fffffffu;
+        if (pathContinues) {
+            newPos = allocSlots(fp.extCount + depth + 1u);
+            const float3 off = isTransmission != 0u ? -surface.geometricNormal : surface.geometricNormal;
+            N.rayO[newPos] = toF4(hitPoint + off * SHADOW_ORIGIN_OFFSET, RAY_T_MIN);
+            N.rayD[newPos] = toF4(wi, RAY_T_MAX);
+            N.record[newPos] = rec;
+            N.rng[newPos] = rng;
+            N.flags[newPos] = flags;
+            if (MODE == MODE_RGB) {
+                N.thr[newPos] = toF4(thrRgb, prevBsdfPdf);
+                if (medium.absorptionActive()) N.sigma[newPos] = toF4(medium.absorptionSigma, 0.0f);
+            } else if (MODE == MODE_SINGLE) {
+                N.thr[newPos] = make_float4(thrScalar, lambdaScalar, prevBsdfPdf, 0.0f);
+                if (medium.absorptionActive()) N.sigma[newPos] = toF4(medium.absorptionSigma, 0.0f);
+            } else {
+                N.thr[newPos] = toF4(thr4);
+                N.heroMisc[newPos] = make_float4(unit, thrScalar, prevBsdfPdf, 0.0f);
+                N.techPdf[newPos] = toF4(techPdf);
+                N.prevVertexTechPdf[newPos] = toF4(newPrevVertexTechPdf);
+                N.prevBsdfTechPdf[newPos] = toF4(newPrevBsdfTechPdf);
+                if (medium.absorptionActive())
+                    N.sigma[newPos] = heroActive ? toF4(medium.spectralAbsorptionSigma) : toF4(medium.absorptionSigma, 0.0f);
+            }
+        }
+        if (shadowPending) {
+            const uint32_t k = allocSlots(fp.shCount + depth);
+            fp.shO[k] = shadowO;
+            fp.shD[k] = shadowD;
+            fp.shContribution[k] = shadowC;
+            fp.shTarget[k] = make_uint2(rec, newPos | (shadowScalarLane ? SHADOW_KIND_SCALAR : 0u));
+            fp.shSeed[k] = shadowSeed;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------------------
+// film (integrator/path/writeback.slang:9-123, film/tonemap.slang)
+// ----------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float3 blendAccumulatedValue(float3 prev, float prevW, float3 cur, float curW) {
+    const float total = prevW + curW;
+    if (total <= 0.0f) return float3(0.0f);
+    return (prev * prevW + cur * curW) / total;
+}
+__device__ __forceinline__ ::uint2 packHalf4(float4 v) {
+    return make_uint2((uint32_t)f32_to_f16(v.x) | ((uint32_t)f32_to_f16(v.y) << 16), (uint32_t)f32_to_f16(v.z) | ((uint32_t)f32_to_f16(v.w) << 16));
+}
+__device__ __forceinline__ float4 unpackHalf4(::uint2 p) {
+    return float4(f16_to_f32((uint16_t)(p.x & 0xffffu)), f16_to_f32((uint16_t)(p.x >> 16)), f16_to_f32((uint16_t)(p.y & 0xffffu)),
+                  f16_to_f32((uint16_t)(p.y >> 16)));
+}
+__device__ __forceinline__ uint32_t unorm16(float v) { return (uint32_t)__float2int_rn(saturate(v) * 65535.0f); }
+__device__ __forceinline__ ::uint2 packUnorm16x4(float4 v) {
+    return make_uint2(unorm16(v.x) | (unorm16(v.y) << 16), unorm16(v.z) | (unorm16(v.w) << 16));
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k_film(const FrameParams fp, const int firstChunk, const int lastChunk) {
+    const uint32_t lpc = fp.tiles.localPixelCount;
+    const SceneData& scene = fp.sd;
+    for (uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x; lp < lpc; lp += gridDim.x * blockDim.x) {
+        uint32_t gx, gy;
+        const bool valid = localPixelToGlobal(fp.tiles, fp.tiles.localToGlobalTile, lp, gx, gy);
+        const int w = 1 - fp.readIndex;
+        if (!valid || !insideViewport(scene, (int)gx, (int)gy)) {  // raygen_rgb.slang:6-12
+            if (lastChunk) {
+                fp.film.accum[w][lp] = make_float4(0.f, 0.f, 0.f, 0.f);
+                fp.film.albedo[w][lp] = make_uint2(0u, 0u);
+                fp.film.normal[w][lp] = make_uint2(0u, 0u);
+                fp.film.output[lp] = make_uint2(0u, 0u);
+            }
+            continue;
+        }
+        // sum this chunk's samples in sample order
+        float3 radiance(0.0f), albedo(0.0f), normal(0.0f);
+        float weight = 0.0f, fdepth = 0.0f, follow = 0.0f;
+        if (!firstChunk) {
+            const ::float4 a = fp.film.frameRadiance[lp], b = fp.film.frameFeatA[lp], c = fp.film.frameFeatB[lp];
+            radiance = float3(a.x, a.y, a.z);
+            albedo = float3(b.x, b.y, b.z); weight = b.w;
+            normal = float3(c.x, c.y, c.z); fdepth = c.w;
+            follow = fp.film.frameFollow[lp];
+        }
+        for (uint32_t s = 0; s < fp.chunkSamples; s++) {
+            const uint32_t rec = s * lpc + lp;
+            const ::float4 r = fp.rec.radiance[rec];
+            if (MODE == MODE_RGB) {
+                radiance += float3(r.x, r.y, r.z);
+            } else if (MODE == MODE_SINGLE) {
+                WavelengthSample ws;
+                ws.lambdaNm = WAVELENGTH_MIN_NM + saturate(fp.rec.unitWavelength[rec]) * WAVELENGTH_RANGE_NM;
+                ws.invPdf = WAVELENGTH_RANGE_NM;
+                radiance += spectralSampleToXYZ(r.x, ws);
+            } else {
+                const float4 wl = heroWavelengths(fp.rec.unitWavelength[rec]);
+                float3 xyz = spectralSample4ToXYZ(float4(r.x, r.y, r.z, r.w), wl, float4(WAVELENGTH_RANGE_NM));
+                WavelengthSample ws;
+                ws.lambdaNm = wl.x;
+                ws.invPdf = WAVELENGTH_RANGE_NM;
+                xyz += spectralSampleToXYZ(fp.rec.radianceScalar[rec], ws);
+                radiance += xyz;
+            }
+            const ::float4 fa = fp.rec.featA[rec], fb = fp.rec.featB[rec];
+            albedo += float3(fa.x, fa.y, fa.z);
+            normal += float3(fb.x, fb.y, fb.z);
+            weight += fa.w;
+            fdepth += fb.w;
+            follow += fp.rec.follow[rec];
+        }
+        if (!lastChunk) {
+            fp.film.frameRadiance[lp] = toF4(radiance, 0.0f);
+            fp.film.frameFeatA[lp] = toF4(albedo, weight);
+            fp.film.frameFeatB[lp] = toF4(normal, fdepth);
+            fp.film.frameFollow[lp] = follow;
+            continue;
+        }
+        const uint32_t spp = max(scene.samplesPerPixel, 1u);
+        const ::float4 prevAcc = fp.film.accum[fp.readIndex][lp];
+        const uint32_t previousSamples = (uint32_t)(prevAcc.w + 0.5f);
+        bool debugOut = false;
+        float3 debugRadiance(0.0f);
+        if (scene.debugMode != VKRT_DEBUG_MODE_NONE) {
+            const ::float4 dc = fp.film.debugColor[lp];
+            if (scene.debugMode == VKRT_DEBUG_MODE_SELECTION_MASK) {
+                debugOut = true;
+                debugRadiance = float3(0.05f);
+            } else if (dc.w > 0.0f) {
+                debugOut = true;
+                debugRadiance = float3(dc.x, dc.y, dc.z);
+            } else if (fp.modeFlags & MODE_BOUNCE_COUNT) {
+                const float t = clamp(float(fp.film.bounceCount[lp]) / max(float(scene.rrMaxDepth), 1.0f), 0.0f, 1.0f);
+                debugOut = true;
+                debugRadiance = float3(t, 1.0f - t, 0.0f);
+            }
+        }
+        if (!debugOut) {  // finalizeFrameAccumulation + applyFrameDebugOverrides
+            radiance /= float(spp);
+            if (weight > 0.0f) { albedo /= weight; normal /= weight; }
+            else { albedo = float3(0.0f); normal = float3(0.0f); }
+            if (fp.modeFlags & MODE_DN_ALBEDO) { debugOut = true; debugRadiance = albedo; }
+            else if (fp.modeFlags & MODE_DN_NORMAL) { debugOut = true; debugRadiance = weight > 0.0f ? normal * 0.5f + 0.5f : float3(0.0f); }
+            else if (fp.modeFlags & MODE_DN_VALIDITY) { debugOut = true; debugRadiance = float3(saturate(weight / float(spp))); }
+            else if (fp.modeFlags & MODE_DN_DEPTH) {
+                float nd = 0.0f;
+                if (weight > 0.0f) nd = saturate((fdepth / weight - 1.0f) / max(float(scene.rrMaxDepth - 1u), 1.0f));
+                debugOut = true;
+                debugRadiance = float3(nd);
+            } else if (fp.modeFlags & MODE_DN_FOLLOW) {
+                debugOut = true;
+                debugRadiance = lerp(float3(0.05f), float3(1.0f, 0.6f, 0.0f), saturate(follow / float(spp)));
+            }
+        }
+        if (debugOut) {  // writeDebugFrameOutputs
+            fp.film.accum[w][lp] = toF4(debugRadiance, 0.0f);
+            fp.film.albedo[w][lp] = make_uint2(0u, 0u);
+            fp.film.normal[w][lp] = make_uint2(0u, 0u);
+            fp.film.output[lp] = packUnorm16x4(float4(encodeDisplayColor(debugRadiance), 1.0f));
+            continue;
+        }
+        // writeAccumulatedFrameOutputs
+        const float4 prevAlbedo = unpackHalf4(fp.film.albedo[fp.readIndex][lp]);
+        const float4 prevNormal = unpackHalf4(fp.film.normal[fp.readIndex][lp]);
+        const float previousWeight = float(previousSamples);
+        const float totalWeight = previousWeight + float(spp);
+        const float3 accumulated = blendAccumulatedValue(float3(prevAcc.x, prevAcc.y, prevAcc.z), previousWeight, radiance, float(spp));
+        const float3 accAlbedo = blendAccumulatedValue(prevAlbedo.xyz(), prevAlbedo.w, albedo, weight);
+        const float3 accNormal = blendAccumulatedValue(prevNormal.xyz(), prevNormal.w, normal, weight);
+        fp.film.accum[w][lp] = toF4(accumulated, totalWeight);
+        fp.film.albedo[w][lp] = packHalf4(float4(accAlbedo, prevAlbedo.w + weight));
+        fp.film.normal[w][lp] = packHalf4(float4(accNormal, prevNormal.w + weight));
+        const float3 display = MODE == MODE_RGB ? mapSceneColorToDisplay(scene, accumulated) : mapSceneColorToDisplay(scene, xyzToLinearSrgb(accumulated));
+        fp.film.output[lp] = packUnorm16x4(float4(display, 1.0f));
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------------------
+// primary visibility AOVs (HITID_CENTER: captureSelectionHit, debug.slang:21-29; HITID_S0: frame 0, sample 0)
+// ----------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_primary_raygen(const FrameParams fp, const int jittered) {
+    const uint32_t lpc = fp.tiles.localPixelCount;
+    for (uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x; lp < lpc; lp += gridDim.x * blockDim.x) {
+        fp.film.hitId[lp] = make_uint2(VKRT_INVALID_INDEX, VKRT_INVALID_INDEX);
+        fp.film.hitTuv[lp] = make_float4(0.f, 0.f, 0.f, 0.f);
+        uint32_t gx, gy;
+        if (!localPixelToGlobal(fp.tiles, fp.tiles.localToGlobalTile, lp, gx, gy)) continue;
+        if (!insideViewport(fp.sd, (int)gx, (int)gy)) continue;
+        float2 jitter(0.0f);
+        uint32_t rng = 0u;
+        if (jittered) {
+            rng = initPixelSeed((int)gx, (int)gy, 0u, 0u);
+            const float jx = rand(rng);
+            const float jy = rand(rng);
+            jitter = float2(__fsub_rn(jx, 0.5f), __fsub_rn(jy, 0.5f));
+        }
+        const Ray ray = makePrimaryRayExact(fp.sd, (int)gx, (int)gy, jitter);
+        const uint32_t j = allocSlots(fp.extCount);
+        fp.st[0].rayO[j] = toF4(ray.origin, ray.tMin);
+        fp.st[0].rayD[j] = toF4(ray.direction, ray.tMax);
+        fp.st[0].record[j] = lp;
+        fp.st[0].rng[j] = rng;
+    }
+}
+__global__ void __launch_bounds__(256) k_primary_store(const FrameParams fp) {
+    const uint32_t count = fp.extCount[0];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const ::uint4 h = fp.hitA[i];
+        const uint32_t lp = fp.st[0].record[i];
+        fp.film.hitId[lp] = make_uint2(h.x, h.y);
+        fp.film.hitTuv[lp] = make_float4(__uint_as_float(h.z), __uint_as_float(h.w), fp.hitB[i], 0.0f);
+    }
+}
+
+// Tile-compact -> full-frame row-major (read_aov, import_gathered). elemSize in 4-byte words per pixel.
+__global__ void __launch_bounds__(256) k_untile(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, TileMap tm, const uint32_t* __restrict__ l2g,
+                                                uint32_t words, uint32_t srcStridePixels) {
+    for (uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x; lp < tm.localPixelCount; lp += gridDim.x * blockDim.x) {
+        uint32_t gx, gy;
+        if (!localPixelToGlobal(tm, l2g, lp, gx, gy)) continue;
+        const size_t d = ((size_t)gy * tm.width + gx) * words;
+        const size_t s = ((size_t)lp) * words;
+        (void)srcStridePixels;
+        for (uint32_t k = 0; k < words; k++) dst[d + k] = src[s + k];
+    }
+}
+
+int traceBlocksPerSm(bool count) {
+    int n = 0;
+    if (count) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace<true>, TRACE_BLOCK, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace<false>, TRACE_BLOCK, 0);
+    return n > 0 ? n : 1;
+}
+int shadeBlocksPerSm(int mode) {
+    int n = 0;
+    if (mode == MODE_RGB) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shade<MODE_RGB>, 128, 0);
+    else if (mode == MODE_SINGLE) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shade<MODE_SINGLE>, 128, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shade<MODE_HERO>, 128, 0);
+    return n > 0 ? n : 1;
+}
+
+// ---- host-side launch helpers (called from api.cu) ---------------------------------------------------------------------
+void launchRaygen(int mode, const FrameParams& fp, int grid, cudaStream_t st) {
+    if (mode == MODE_RGB) k_raygen<MODE_RGB><<<grid, 256, 0, st>>>(fp);
+    else if (mode == MODE_SINGLE) k_raygen<MODE_SINGLE><<<grid, 256, 0, st>>>(fp);
+    else k_raygen<MODE_HERO><<<grid, 256, 0, st>>>(fp);
+}
+void launchShade(int mode, const FrameParams& fp, uint32_t depth, int grid, cudaStream_t st) {
+    if (mode == MODE_RGB) k_shade<MODE_RGB><<<grid, 128, 0, st>>>(fp, depth);
+    else if (mode == MODE_SINGLE) k_shade<MODE_SINGLE><<<grid, 128, 0, st>>>(fp, depth);
+    else k_shade<MODE_HERO><<<grid, 128, 0, st>>>(fp, depth);
+}
+void launchFilm(int mode, const FrameParams& fp, int firstChunk, int lastChunk, int grid, cudaStream_t st) {
+    if (mode == MODE_RGB) k_film<MODE_RGB><<<grid, 256, 0, st>>>(fp, firstChunk, lastChunk);
+    else if (mode == MODE_SINGLE) k_film<MODE_SINGLE><<<grid, 256, 0, st>>>(fp, firstChunk, lastChunk);
+    else k_film<MODE_HERO><<<grid, 256, 0, st>>>(fp, firstChunk, lastChunk);
+}
+void launchTrace(const TraceParams& tp, bool count, int grid, cudaStream_t st) {
+    if (count) k_trace<true><<<grid, TRACE_BLOCK, 0, st>>>(tp);
+    else k_trace<false><<<grid, TRACE_BLOCK, 0, st>>>(tp);
+}
+void launchPrimaryRaygen(const FrameParams& fp, int jittered, int grid, cudaStream_t st) { k_primary_raygen<<<grid, 256, 0, st>>>(fp, jittered); }
+void launchPrimaryStore(const FrameParams& fp, int grid, cudaStream_t st) { k_primary_store<<<grid, 256, 0, st>>>(fp); }
+void launchUntile(const void* src, void* dst, const TileMap& tm, const uint32_t* l2g, uint32_t words, int grid, cudaStream_t st) {
+    k_untile<<<grid, 256, 0, st>>>((const uint32_t*)src, (uint32_t*)dst, tm, l2g, words, 0u);
+}
+
+} // namespace vk
