@@ -5,7 +5,7 @@
  * "host scene data is ready" and "accumulation image can be read back" — i.e. the Vulkan
  * acceleration-structure code (src/core/render/accel/{blas,tlas}.c), the command recording
  * (src/core/runtime/command/record.c:448-486,577-599) and the Slang shaders
- * (src/shaders/**) — is replaced by the functions below.  Plain pointers and sizes only;
+ * (everything under src/shaders) — is replaced by the functions below.  Plain pointers and sizes only;
  * every upload copies, every read-back fills a caller buffer; the API is single-threaded
  * and non-reentrant, exactly like the reference's VKRT_* API (src/core/api/vkrt.h).
  *
