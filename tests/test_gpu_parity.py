@@ -1,0 +1,189 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bars (DESIGN.md "Parity"):
+  * integer / index work is bit-exact: primary-hit {instance, primitive} ids, and also the hit's t/u/v bits, because the
+    camera, instance-transform and ray/triangle arithmetic are pinned to identical IEEE roundings on both sides;
+  * radiance is floating point through libm/CUDA transcendentals (sin, cos, exp, log, pow, acos, atan2) that differ by an
+    ulp and get amplified chaotically along a path, so images are compared per pixel with a relative tolerance and a bounded
+    outlier fraction: at least 99.5 % of pixels within 1e-3 relative, and image RMSE <= 2 % of the mean radiance.
+"""
+import numpy as np
+import pytest
+
+import harness as H
+import scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_ids(o, g, sd):
+    o.trace_primary(sd)
+    g.trace_primary(sd)
+    for which in (H.AOV_HITID_CENTER, H.AOV_HITID_S0):
+        a, b = o.read(which), g.read(which)
+        assert np.array_equal(a, b), "hit ids differ in %d pixels" % int((a != b).any(axis=-1).sum())
+    ta, tb = o.read(H.AOV_HIT_TUV), g.read(H.AOV_HIT_TUV)
+    assert np.array_equal(ta.view(np.uint32), tb.view(np.uint32))
+
+
+def _check_images(o, g, frac=0.995, rel_rmse=0.02):
+    a, b = o.read(H.AOV_ACCUM), g.read(H.AOV_ACCUM)
+    assert np.array_equal(a[..., 3], b[..., 3])  # sample counts are integers
+    c = H.compare_images(a[..., :3], b[..., :3])
+    assert 1.0 - c["frac_rel_gt_1e3"] >= frac, c
+    assert c["rmse"] <= rel_rmse * max(c["mean_a"], 1e-6), c
+    # feature AOVs are resolved at the first non-specular hit: essentially exact
+    for which in (H.AOV_ALBEDO, H.AOV_NORMAL):
+        fa, fb = o.read(which).astype(np.float32), g.read(which).astype(np.float32)
+        assert (np.abs(fa - fb) > 2e-3).mean() < 0.005
+    oa, ob = o.read(H.AOV_OUTPUT).astype(np.int64), g.read(H.AOV_OUTPUT).astype(np.int64)
+    assert (np.abs(oa - ob) > 64).mean() < 0.01  # 16-bit display values
+
+
+def test_cornell_rgb_ids_and_images():
+    w = h = 128
+    prep = scenes.cornell(w, h, spp=4)
+    o, g = scenes.both_backends(prep, w, h)
+    _check_ids(o, g, prep["sceneData"])
+    o.render(prep["sceneData"], frames=3)
+    g.render(prep["sceneData"], frames=3)
+    _check_images(o, g)
+
+
+def test_cornell_glass_medium_and_unsupported_transmission():
+    w = h = 96
+    prep = scenes.cornell(w, h, spp=4, glass=True)
+    prep["materials"][7]["absorptionCoefficient"] = 2.0
+    prep["materials"][7]["attenuationColor"] = (0.4, 0.8, 0.9)
+    o, g = scenes.both_backends(prep, w, h)
+    _check_ids(o, g, prep["sceneData"])
+    o.render(prep["sceneData"], frames=2)
+    g.render(prep["sceneData"], frames=2)
+    _check_images(o, g, frac=0.99, rel_rmse=0.05)
+
+
+def test_instanced_two_level_bvh():
+    w, h = 160, 96
+    prep = scenes.instanced(w, h, count=64, spp=2)
+    o, g = scenes.both_backends(prep, w, h)
+    assert g.build_stats.uniqueGeometries == 3 and g.build_stats.instanceCount == 66
+    _check_ids(o, g, prep["sceneData"])
+    o.render(prep["sceneData"], frames=2)
+    g.render(prep["sceneData"], frames=2)
+    _check_images(o, g, frac=0.99, rel_rmse=0.05)
+
+
+def test_soup_ids_and_random_rays():
+    w, h = 128, 96
+    prep = scenes.soup(60000, w, h, spp=1)
+    o, g = scenes.both_backends(prep, w, h)
+    _check_ids(o, g, prep["sceneData"])
+    rng = np.random.default_rng(9)
+    n = 50000
+    org = rng.uniform(-1.2, 1.2, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    rays = np.concatenate([org, np.full((n, 1), 1e-3, np.float32), d, np.full((n, 1), 1e4, np.float32)], axis=1)
+    assert np.array_equal(o.trace_rays(rays), g.trace_rays(rays))
+    rays[:, 7] = 0.5
+    assert np.array_equal(o.trace_rays(rays, any_hit=True)[:, 0], g.trace_rays(rays, any_hit=True)[:, 0])
+
+
+@pytest.mark.parametrize("debug_mode", [1, 2, 3, 4, 5, 12, 13, 14, 15, 16])
+def test_debug_views(debug_mode):
+    w = h = 64
+    prep = scenes.cornell(w, h, spp=2, debug_mode=debug_mode)
+    o, g = scenes.both_backends(prep, w, h)
+    o.render(prep["sceneData"], frames=1)
+    g.render(prep["sceneData"], frames=1)
+    a, b = o.read(H.AOV_ACCUM), g.read(H.AOV_ACCUM)
+    c = H.compare_images(a[..., :3], b[..., :3])
+    assert c["frac_rel_gt_1e2"] < 0.01, c
+
+
+def test_nee_only_plus_bsdf_only_equals_full():
+    """The reference's own validation views (constants.h:39-40): with MIS the two techniques partition the estimator,
+    so E[NEE-only] + E[BSDF-only] = E[full]. Checked on the GPU alone at moderate spp."""
+    w = h = 48
+    means = {}
+    for mode in (0, 4, 5):
+        prep = scenes.cornell(w, h, spp=64, debug_mode=mode)
+        g = H.CudaBackend()
+        g.upload(prep)
+        g.resize(w, h)
+        g.render(prep["sceneData"], frames=4)
+        means[mode] = g.read(H.AOV_ACCUM)[..., :3].astype(np.float64).mean()
+        g.close()
+    assert abs(means[4] + means[5] - means[0]) < 0.03 * means[0], means
+
+
+def test_accumulation_is_a_running_mean_and_deterministic():
+    w = h = 64
+    prep = scenes.cornell(w, h, spp=4)
+    g1, g2 = H.CudaBackend(), H.CudaBackend(max_paths=w * h * 2)  # second context forces 2 sample chunks per frame
+    for g in (g1, g2):
+        g.upload(prep)
+        g.resize(w, h)
+        g.render(prep["sceneData"], frames=3)
+    a, b = g1.read(H.AOV_ACCUM), g2.read(H.AOV_ACCUM)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), "chunked and unchunked frames must be bit-identical"
+    assert np.all(a[..., 3] == 12.0)
+    g1.reset()
+    g1.render(prep["sceneData"], frames=3)
+    assert np.array_equal(a.view(np.uint32), g1.read(H.AOV_ACCUM).view(np.uint32)), "re-render must be bit-identical"
+
+
+def test_tile_partition_matches_single_gpu():
+    """Two ranks on one device: the union of their tile-compact films equals the single-rank image bit for bit."""
+    w, h = 200, 120  # not a multiple of the tile size
+    prep = scenes.cornell(w, h, spp=2)
+    full = H.CudaBackend()
+    full.upload(prep)
+    full.resize(w, h)
+    full.render(prep["sceneData"], frames=2)
+    ref = full.read(H.AOV_ACCUM)
+    acc = np.zeros_like(ref)
+    for r in range(2):
+        g = H.CudaBackend(rank=r, world_size=2)
+        g.upload(prep)
+        g.resize(w, h)
+        g.render(prep["sceneData"], frames=2)
+        part = g.read(H.AOV_ACCUM)  # pixels of other ranks read back as zero
+        assert np.all((part[..., 3] == 0) | (part[..., 3] == 4))
+        acc += part
+        g.close()
+    assert np.array_equal(acc.view(np.uint32), ref.view(np.uint32))
+
+
+@pytest.mark.parametrize("sampling", [0, 1])
+def test_cornell_spectral(sampling):
+    """renderMode = spectral, single-wavelength (0) and hero-wavelength (1) sampling; accumulation holds XYZ."""
+    w = h = 96
+    prep = scenes.cornell(w, h, spp=4, render_mode=1, spectral_sampling=sampling)
+    o, g = scenes.both_backends(prep, w, h, spectral=True)
+    _check_ids(o, g, prep["sceneData"])
+    o.render(prep["sceneData"], frames=2)
+    g.render(prep["sceneData"], frames=2)
+    _check_images(o, g, frac=0.99, rel_rmse=0.05)
+
+
+def test_dispersive_glass_hero_collapse():
+    """Rough glass with an Abbe number: hero paths collapse to one wavelength on refraction (spectral_hero/transport.slang:77-87)."""
+    w = h = 96
+    prep = scenes.cornell(w, h, spp=4, glass=True, render_mode=1, spectral_sampling=1)
+    prep["materials"][7]["abbeNumber"] = 25.0
+    prep["materials"][7]["absorptionCoefficient"] = 1.5
+    prep["materials"][7]["attenuationColor"] = (0.9, 0.6, 0.3)
+    o, g = scenes.both_backends(prep, w, h, spectral=True)
+    o.render(prep["sceneData"], frames=2)
+    g.render(prep["sceneData"], frames=2)
+    _check_images(o, g, frac=0.985, rel_rmse=0.08)
+
+
+def test_spectral_without_table_fails():
+    w = h = 32
+    prep = scenes.cornell(w, h, spp=1, render_mode=1)
+    g = H.CudaBackend()
+    g.upload(prep)
+    g.resize(w, h)
+    with pytest.raises(Exception):
+        g.render(prep["sceneData"], frames=1)
