@@ -58,7 +58,8 @@ typedef struct vkrt_cuda_create_info {
 enum {
     VKRT_CUDA_FLAG_NONE = 0u,
     VKRT_CUDA_FLAG_COUNT_RAYS = 1u << 0,    /* per-frame ray/node/triangle counters (instrumented build of the same kernels) */
-    VKRT_CUDA_FLAG_NO_MATERIAL_SORT = 1u << 1 /* shade in queue order instead of material-sorted order */
+    VKRT_CUDA_FLAG_NO_MATERIAL_SORT = 1u << 1, /* shade in queue order instead of material-sorted order */
+    VKRT_CUDA_FLAG_STAGE_TIMING = 1u << 2     /* vkrt_cuda_render_frame records a CUDA event after every launch and fills traceMs / shadeMs */
 };
 
 typedef struct vkrt_cuda_build_stats {
@@ -75,9 +76,10 @@ typedef struct vkrt_cuda_build_stats {
 
 typedef struct vkrt_cuda_frame_stats {
     float frameMs;       /* device time of the whole frame (CUDA events on the render stream) */
-    float traceMs;       /* device time inside traversal kernels (sum over bounces) */
-    float shadeMs;       /* device time inside raygen + shading + film kernels */
+    float traceMs;       /* device time inside traversal kernels (sum over bounces); needs VKRT_CUDA_FLAG_STAGE_TIMING */
+    float shadeMs;       /* device time inside raygen + shading + film kernels; needs VKRT_CUDA_FLAG_STAGE_TIMING */
     uint32_t kernelLaunches;
+    uint32_t traceLaunches; /* traversal launches among kernelLaunches */
     uint64_t paths;      /* camera paths started = local pixels * spp */
     uint64_t extensionRays; /* closest-hit rays traced */
     uint64_t shadowRays;    /* any-hit rays traced */

@@ -18,6 +18,7 @@ HOST_LIB_PATH = os.path.join(_HERE, "libvkrt_host.so")
 AOV_ACCUM, AOV_ALBEDO, AOV_NORMAL, AOV_OUTPUT, AOV_HITID_CENTER, AOV_HITID_S0, AOV_HIT_TUV = range(7)
 FLAG_COUNT_RAYS = 1
 FLAG_NO_MATERIAL_SORT = 2
+FLAG_STAGE_TIMING = 4
 
 VKRT_SUCCESS = 0
 _ERRORS = {0: "SUCCESS", -1: "INVALID_ARGUMENT", -2: "OPERATION_FAILED", -3: "OUT_OF_MEMORY", -4: "DEVICE_LOST",
@@ -43,7 +44,7 @@ class BuildStats(C.Structure):
 
 class FrameStats(C.Structure):
     _fields_ = [("frameMs", C.c_float), ("traceMs", C.c_float), ("shadeMs", C.c_float), ("kernelLaunches", C.c_uint32),
-                ("paths", C.c_uint64), ("extensionRays", C.c_uint64), ("shadowRays", C.c_uint64), ("nodesVisited", C.c_uint64),
+                ("traceLaunches", C.c_uint32), ("paths", C.c_uint64), ("extensionRays", C.c_uint64), ("shadowRays", C.c_uint64), ("nodesVisited", C.c_uint64),
                 ("trianglesTested", C.c_uint64), ("instancesEntered", C.c_uint64)]
 
 
@@ -74,7 +75,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or CUDA_LIB_PATH
+    p = path or os.environ.get("VKRT_CUDA_LIB") or CUDA_LIB_PATH  # VKRT_CUDA_LIB: A/B-test an alternative build of the same ABI
     if not os.path.exists(p):
         raise ImportError("vkrt_b200: %s not found. The CUDA extension is required (there is no CPU path); run `make -C %s`." % (p, _HERE))
     lib = C.CDLL(p)

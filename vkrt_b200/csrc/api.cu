@@ -29,6 +29,7 @@ void launchTrace(const TraceParams& tp, bool count, int grid, cudaStream_t st);
 void launchPrimaryRaygen(const FrameParams& fp, int jittered, int grid, cudaStream_t st);
 void launchPrimaryStore(const FrameParams& fp, int grid, cudaStream_t st);
 void launchUntile(const void* src, void* dst, const TileMap& tm, const uint32_t* l2g, uint32_t words, int grid, cudaStream_t st);
+void launchMeshTrig(const MeshInfo* infos, MeshTrig* out, uint32_t count, cudaStream_t st);
 int traceBlocksPerSm(bool count);
 int shadeBlocksPerSm(int mode);
 }  // namespace vk
@@ -97,6 +98,7 @@ struct vkrt_cuda_ctx {
     std::vector<uint8_t> hostAlpha;
     std::vector<Material> hostMaterials;
     DevBuf<MeshInfo> meshInfos;
+    DevBuf<MeshTrig> meshTrig;
     DevBuf<Material> materials;
     DevBuf<EmissiveMesh> emissiveMeshes;
     DevBuf<EmissiveTriangle> emissiveTriangles;
@@ -141,6 +143,11 @@ struct vkrt_cuda_ctx {
     DevBuf<uint8_t> gathered; // rank 0: concatenated tile-compact buffers of all ranks
     bool filmIsFullFrame[8] = {false};
     DevBuf<uint8_t> fullFrame[4];  // rank 0 after gather: accum, albedo, normal, output (row-major)
+
+    // per-launch stage timing (VKRT_CUDA_FLAG_STAGE_TIMING): event after every launch, kind 0 = raygen/shade/film, 1 = trace
+    std::vector<cudaEvent_t> stageEvents;
+    std::vector<int> stageKinds;
+    size_t stageUsed = 0;
 
     // nccl
     NcclApi nccl;
@@ -209,6 +216,7 @@ SceneView makeSceneView(vkrt_cuda_ctx* c) {
     v.vertices = c->vertices.p;
     v.indices = c->indices.p;
     v.meshInfos = c->meshInfos.p;
+    v.meshTrig = c->meshTrig.p;
     v.materials = c->materials.p;
     v.emissiveMeshes = c->emissiveMeshes.p;
     v.emissiveTriangles = c->emissiveTriangles.p;
@@ -342,6 +350,20 @@ VKRT_Result enqueueFrame(vkrt_cuda_ctx* ctx, const SceneData* sceneData, uint32_
     const bool count = (ctx->flags & VKRT_CUDA_FLAG_COUNT_RAYS) != 0;
     cudaStream_t st = ctx->stream;
     uint32_t nl = 0;
+    const bool timing = launches != nullptr && (ctx->flags & VKRT_CUDA_FLAG_STAGE_TIMING) != 0;
+    ctx->stageUsed = 0;
+    ctx->stageKinds.clear();
+    auto mark = [&](int kind) {
+        if (!timing) return;
+        if (ctx->stageUsed == ctx->stageEvents.size()) {
+            cudaEvent_t e = nullptr;
+            if (cudaEventCreate(&e) != cudaSuccess) return;
+            ctx->stageEvents.push_back(e);
+        }
+        cudaEventRecord(ctx->stageEvents[ctx->stageUsed++], st);
+        ctx->stageKinds.push_back(kind);
+    };
+    mark(-1);
     if (sd.debugMode != VKRT_DEBUG_MODE_NONE) {
         CU(cudaMemsetAsync(fp.film.debugColor, 0, lpc * sizeof(::float4), st));
         CU(cudaMemsetAsync(fp.film.bounceCount, 0, lpc * sizeof(uint32_t), st));
@@ -352,17 +374,22 @@ VKRT_Result enqueueFrame(vkrt_cuda_ctx* ctx, const SceneData* sceneData, uint32_
         CU(cudaMemsetAsync(ctx->counters.p, 0, sizeof(uint32_t) * MAX_DEPTH_SLOTS * 3, st));
         launchRaygen(mode, fp, ctx->shadeGrid[mode] * 2, st);
         nl++;
+        mark(0);
         for (uint32_t d = 0; d < sd.rrMaxDepth; d++) {
             launchTrace(makeTraceParams(ctx, d, true, d > 0), count, ctx->traceGrid, st);
+            mark(1);
             launchShade(mode, fp, d, ctx->shadeGrid[mode], st);
+            mark(0);
             nl += 2;
         }
         if (sd.rrMaxDepth > 0) {
             launchTrace(makeTraceParams(ctx, sd.rrMaxDepth, false, true), count, ctx->traceGrid, st);
             nl++;
+            mark(1);
         }
         launchFilm(mode, fp, s0 == 0, s0 + fp.chunkSamples >= spp, ctx->smCount * 4, st);
         nl++;
+        mark(0);
     }
     CU(cudaGetLastError());
     ctx->readIndex = 1 - ctx->readIndex;  // frame.c:386-388
@@ -447,6 +474,7 @@ VKRT_CUDA_API void vkrt_cuda_destroy(vkrt_cuda_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->comm && ctx->nccl.CommDestroy) ctx->nccl.CommDestroy(ctx->comm);
     for (auto* t : ctx->texturePixels) delete t;
+    for (cudaEvent_t e : ctx->stageEvents) cudaEventDestroy(e);
     if (ctx->evA) cudaEventDestroy(ctx->evA);
     if (ctx->evB) cudaEventDestroy(ctx->evB);
     cudaStream_t st = ctx->stream;
@@ -478,6 +506,8 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_set_instances(vkrt_cuda_ctx* ctx, const Mesh
     if (alphaTested) ctx->hostAlpha.assign(alphaTested, alphaTested + instanceCount);
     else ctx->hostAlpha.assign(instanceCount, 0);
     CU(ctx->meshInfos.upload(infos, instanceCount, ctx->stream));
+    CU(ctx->meshTrig.alloc(instanceCount));
+    launchMeshTrig(ctx->meshInfos.p, ctx->meshTrig.p, instanceCount, ctx->stream);
     CU(ctx->world3x4.upload(world3x4, (size_t)instanceCount * 12, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->accelValid = false;
@@ -743,6 +773,12 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_render_frame(vkrt_cuda_ctx* ctx, const Scene
         memset(outStats, 0, sizeof(*outStats));
         cudaEventElapsedTime(&outStats->frameMs, ctx->evA, ctx->evB);
         outStats->kernelLaunches = launches;
+        for (size_t k = 1; k < ctx->stageUsed; k++) {
+            float ms = 0.0f;
+            if (cudaEventElapsedTime(&ms, ctx->stageEvents[k - 1], ctx->stageEvents[k]) != cudaSuccess) continue;
+            if (ctx->stageKinds[k] == 1) { outStats->traceMs += ms; outStats->traceLaunches++; }
+            else outStats->shadeMs += ms;
+        }
         const uint32_t spp = std::max(sceneData->samplesPerPixel, 1u);
         // counters hold the LAST chunk only; ray totals are exact when the frame fits one chunk (the common case)
         uint32_t host[MAX_DEPTH_SLOTS * 2];

@@ -16,6 +16,7 @@ struct SceneView {
     const ShaderVertex* vertices;
     const uint32_t* indices;
     const MeshInfo* meshInfos;
+    const MeshTrig* meshTrig;  // per mesh, written by k_mesh_trig at set_instances time
     const Material* materials;
     const EmissiveMesh* emissiveMeshes;
     const EmissiveTriangle* emissiveTriangles;
@@ -101,12 +102,17 @@ __device__ __forceinline__ float2 transformTextureUv(float2 uv, const float* tr,
     float s = sinf(rotation), co = cosf(rotation);
     return float2(co * scaled.x - s * scaled.y, s * scaled.x + co * scaled.y) + float2(tr[2], tr[3]);
 }
+static __device__ __noinline__ float4 sampleMaterialTextureBound(const SceneView& sc, uint32_t textureIndex, uint32_t packedWrap, ::float4 transform,
+                                                                 float rotation, float2 uv) {
+    const float tr[4] = {transform.x, transform.y, transform.z, transform.w};
+    return sampleTextureBilinear(sc, textureIndex, transformTextureUv(uv, tr, rotation), wrapModeOrDefault(packedWrap & 0xffffu),
+                                 wrapModeOrDefault((packedWrap >> 16) & 0xffffu));
+}
 __device__ __forceinline__ float4 sampleMaterialTexture(const SceneView& sc, uint32_t textureIndex, uint32_t packedWrap, const float* transform,
                                                         float rotation, uint32_t texcoordSet, const SurfaceTextureData& s, float4 fallback) {
-    if (textureIndex == VKRT_INVALID_INDEX) return fallback;
+    if (textureIndex == VKRT_INVALID_INDEX) return fallback;  // the common case: untextured slot, nothing else is executed
     float2 uv = texcoordSet == 1u ? s.texcoord1 : s.texcoord0;
-    return sampleTextureBilinear(sc, textureIndex, transformTextureUv(uv, transform, rotation), wrapModeOrDefault(packedWrap & 0xffffu),
-                                 wrapModeOrDefault((packedWrap >> 16) & 0xffffu));
+    return sampleMaterialTextureBound(sc, textureIndex, packedWrap, make_float4(transform[0], transform[1], transform[2], transform[3]), rotation, uv);
 }
 __device__ __forceinline__ uint32_t materialTexcoordSet(const Material& m, uint32_t slot) { return (m.textureTexcoordSets >> (slot * 8u)) & 0xffu; }
 __device__ __forceinline__ float4 sampleBaseColorTexture(const SceneView& sc, const Material& m, const SurfaceTextureData& s) {

@@ -1,6 +1,9 @@
 // shading.cuh — device restatement of vkrt's Slang shading library (src/shaders/{sampling,camera,utility,bsdf,film,geometry}).
 // Every block cites the reference file:line it follows. Device-only code; the wavefront kernels in wavefront.cu call it.
 #define VK_D __device__ __forceinline__
+// Out-of-line on purpose: k_shade is instruction-fetch bound when the closure code is inlined at every call site
+// (717 KB of SASS in hero mode, profiles/r01_shade_hero_baseline.txt); one copy per function keeps it I-cache resident.
+#define VK_NOINLINE static __device__ __noinline__
 #pragma once
 #include "vmath.cuh"
 #include "../../include/vkrt_shared.h"
@@ -155,7 +158,10 @@ VK_D uint rgb2specFindInterval(const SpectralTables& t, float x) {
     return min(uint(left), t.info.res - 2u);
 }
 
-VK_D float3 rgb2specFetch(const SpectralTables& t, float3 rgb) {
+VK_NOINLINE float3 rgb2specFetchTable(const float* __restrict__ table, uint tableRes, uint scaleOffset, uint dataOffset, float3 rgb) {
+    SpectralTables t;
+    t.info.res = tableRes; t.info.scaleOffset = scaleOffset; t.info.dataOffset = dataOffset;
+    t.table = table;
     float z = max(rgb.x, max(rgb.y, rgb.z));
     if (z <= RGB2SPEC_EPSILON) return float3(0.0f);
     uint dominantChannel = 0u;
@@ -187,6 +193,9 @@ VK_D float3 rgb2specFetch(const SpectralTables& t, float3 rgb) {
                             z1;
     }
     return coeff;
+}
+VK_D float3 rgb2specFetch(const SpectralTables& t, float3 rgb) {
+    return rgb2specFetchTable(t.table, t.info.res, t.info.scaleOffset, t.info.dataOffset, rgb);
 }
 VK_D float rgb2specEvalCoeffs(float3 coeff, float lambdaNm) {
     float x = (coeff.x * lambdaNm + coeff.y) * lambdaNm + coeff.z;
@@ -415,7 +424,7 @@ VK_D float fresnelDielectric(float cosT, float eta) {
     float rPerp = (cosI - eta * cosTt) / max(cosI + eta * cosTt, 1e-6f);
     return 0.5f * (rPar * rPar + rPerp * rPerp);
 }
-VK_D float3 fresnelConductor(float cosT, float3 eta, float3 k) {
+VK_NOINLINE float3 fresnelConductor(float cosT, float3 eta, float3 k) {
     float cosI = saturate(cosT);
     float cos2I = cosI * cosI;
     float sin2I = max(1.0f - cos2I, 0.0f);
@@ -685,7 +694,7 @@ VK_D BSDFEval evalLambertian(float3 diffuseColor, float3 wi) {
     e.pdf = cosineHemispherePdf(wi);
     return e;
 }
-VK_D BSDFEval evalOrenNayar(float3 diffuseColor, float roughness, float3 wo, float3 wi) {
+VK_NOINLINE BSDFEval evalOrenNayar(float3 diffuseColor, float roughness, float3 wo, float3 wi) {
     BSDFEval e;
     if (cosTheta(wo) <= 0.0f || cosTheta(wi) <= 0.0f) return e;
     float sigma = saturate(roughness) * (0.5f * PI);
@@ -707,7 +716,7 @@ VK_D BSDFEval evalOrenNayar(float3 diffuseColor, float roughness, float3 wo, flo
     e.pdf = cosineHemispherePdf(wi);
     return e;
 }
-VK_D BSDFEval evalFakeSubsurface(float3 diffuseColor, float roughness, float3 wo, float3 wi) {
+VK_NOINLINE BSDFEval evalFakeSubsurface(float3 diffuseColor, float roughness, float3 wo, float3 wi) {
     BSDFEval e;
     if (cosTheta(wo) <= 0.0f || cosTheta(wi) <= 0.0f) return e;
     float3 h = safeNormalize(wo + wi);
@@ -742,7 +751,7 @@ VK_D float clearcoatDistribution(float cosThetaM, float alpha) {
     float denom = PI * logf(alpha2) * (1.0f + (alpha2 - 1.0f) * cosThetaM * cosThetaM);
     return (alpha2 - 1.0f) / min(denom, -CLEARCOAT_EPSILON);
 }
-VK_D BSDFEval evalClearcoat(float clearcoatWeight, float3 wo, float3 wi, const ClearcoatParams& p) {
+VK_NOINLINE BSDFEval evalClearcoat(float clearcoatWeight, float3 wo, float3 wi, const ClearcoatParams& p) {
     BSDFEval e;
     if (clearcoatWeight <= 0.0f || cosTheta(wo) <= 0.0f || cosTheta(wi) <= 0.0f) return e;
     float3 h = safeNormalize(wo + wi);
@@ -757,7 +766,7 @@ VK_D BSDFEval evalClearcoat(float clearcoatWeight, float3 wo, float3 wi, const C
     e.pdf = pdfM / max(4.0f * woDotH, CLEARCOAT_EPSILON);
     return e;
 }
-VK_D bool sampleClearcoat(float3 wo, const ClearcoatParams& p, uint& rng, float3& wi) {
+VK_NOINLINE bool sampleClearcoat(float3 wo, const ClearcoatParams& p, uint& rng, float3& wi) {
     float u1 = rand(rng);
     float u2 = rand(rng);
     float alpha2 = p.alpha * p.alpha;
@@ -825,13 +834,13 @@ VK_D float sheenDistributionValue(float3 localWi, const SheenParams& p) {
     float scale = p.transformA / lenSqr;
     return INV_PI * z * scale * scale;
 }
-VK_D float sheenDirectionalAlbedo(float cosT, float sheenRoughness) {
+VK_NOINLINE float sheenDirectionalAlbedo(float cosT, float sheenRoughness) {
     return sheenLtcLookup(cosT, clamp(sheenRoughness, 1e-3f, 1.0f), 2u);
 }
 VK_D float sheenLayerAttenuation(float sheenWeight, float cosT, float sheenRoughness) {
     return saturate(1.0f - sheenWeight * sheenDirectionalAlbedo(cosT, sheenRoughness));
 }
-VK_D BSDFEval evalSheen(float3 sheenColor, float sheenRoughness, float3 wo, float3 wi) {
+VK_NOINLINE BSDFEval evalSheen(float3 sheenColor, float sheenRoughness, float3 wo, float3 wi) {
     BSDFEval e;
     if (cosTheta(wo) <= 0.0f || cosTheta(wi) <= 0.0f) return e;
     SheenParams p = makeSheenParams(wo, sheenRoughness);
@@ -841,7 +850,7 @@ VK_D BSDFEval evalSheen(float3 sheenColor, float sheenRoughness, float3 wo, floa
     e.pdf = value;
     return e;
 }
-VK_D bool sampleSheen(float3 wo, float sheenRoughness, uint& rng, float3& wi) {
+VK_NOINLINE bool sampleSheen(float3 wo, float sheenRoughness, uint& rng, float3& wi) {
     SheenParams p = makeSheenParams(wo, sheenRoughness);
     if (abs(p.transformA) < 1e-5f || p.albedo < 1e-5f) {
         wi = float3(0.0f);
@@ -918,7 +927,7 @@ VK_D BSDFEval evalDielectricReflection(const SpectralTables& t, const BSDFMateri
     e.pdf = reflectionProbability * ggxReflectionPdf(wo, wm, p);
     return e;
 }
-VK_D BSDFEval evalDielectricTransmission(const SpectralTables& t, const BSDFMaterial& mat, float3 wo, float3 wi, uint frontFace,
+VK_NOINLINE BSDFEval evalDielectricTransmission(const SpectralTables& t, const BSDFMaterial& mat, float3 wo, float3 wi, uint frontFace,
                                            const GGXParams& p, float coatAttenuation, float lambdaNm, uint spectralMode) {
     BSDFEval e;
     if (mat.transmission <= 0.0f || cosTheta(wo) <= 0.0f || cosTheta(wi) >= 0.0f) return e;
@@ -994,7 +1003,7 @@ VK_D float evalSpectralDielectricTransmissionLane(const BSDFMaterial& mat, float
     pdf = tp * ggxVisibleNormalPdf(wo, wm, p) * dwmDwi;
     return coatAttenuation * transmissionColor * ((1.0f - fresnel) * Dm * G * transmissionTerm * transportScale);
 }
-VK_D float4 evalSpectralDielectricTransmission(const SpectralTables& t, const BSDFMaterial& mat, float3 wo, float3 wi,
+VK_NOINLINE float4 evalSpectralDielectricTransmission(const SpectralTables& t, const BSDFMaterial& mat, float3 wo, float3 wi,
                                                  uint frontFace, const GGXParams& p, float coatAttenuation, float4 wl,
                                                  float4& techniquePdf) {
     float4 value(0.0f);
@@ -1206,7 +1215,7 @@ VK_D BSDFEval evalScalarReflectionStack(const SpectralTables& t, const BSDFState
     e.value = sheenValue + vs * baseValue;
     return e;
 }
-VK_D BSDFEval evalBSDFMode(const SpectralTables& t, const BSDFState& s, float3 wi, uint spectralMode) {
+VK_NOINLINE BSDFEval evalBSDFMode(const SpectralTables& t, const BSDFState& s, float3 wi, uint spectralMode) {
     if (cosTheta(wi) > 0.0f) return evalScalarReflectionStack(t, s, wi, spectralMode);
     BSDFEval tr = evalDielectricTransmission(
         t, s.material, s.wo, wi, s.frontFace, s.ggx,
@@ -1274,7 +1283,7 @@ VK_D float4 evalSpectralReflectionStack(const SpectralTables& t, const BSDFState
     float4 baseValue = float4(coatValue) + ra * (m.metallic * metalValue + nonMetal * (dielectricValue + vd * substrateValue));
     return sheenValue + vs * baseValue;
 }
-VK_D float4 evalSpectralBSDF(const SpectralTables& t, const BSDFState& s, float3 wi, float4 wl, float4& techniquePdf) {
+VK_NOINLINE float4 evalSpectralBSDF(const SpectralTables& t, const BSDFState& s, float3 wi, float4 wl, float4& techniquePdf) {
     if (cosTheta(wi) > 0.0f) return evalSpectralReflectionStack(t, s, wi, wl, techniquePdf);
     float coatAtt = useInteriorDielectricInterface(s) ? 1.0f : materialTransmissionStackAttenuation(s.material, s.wo);
     float4 v = evalSpectralDielectricTransmission(t, s.material, s.wo, wi, s.frontFace, s.ggx, coatAtt, wl, techniquePdf);
@@ -1287,7 +1296,7 @@ struct BSDFDirectionSample {
     float3 wi = float3(0.0f);
     uint isTransmission = 0u;
 };
-VK_D bool sampleBSDFDirection(const BSDFState& s, uint& rng, BSDFDirectionSample& out) {
+VK_NOINLINE bool sampleBSDFDirection(const BSDFState& s, uint& rng, BSDFDirectionSample& out) {
     out = BSDFDirectionSample();
     float selector = rand(rng);
     if (selector < s.sampleWeights.sheen) return sampleSheen(s.wo, s.material.sheenRoughness, rng, out.wi);
@@ -1419,21 +1428,25 @@ VK_D float4 unpackOctTangent(uint packed) {
 // ---- geometry/surface/transform.slang:6-55 ------------------------------------------------------------------------
 static constexpr float SURFACE_DEG_TO_RAD = 0.01745329251994329577f;
 static constexpr float SURFACE_SCALE_EPSILON = 1e-6f;
-VK_D float3 rotateX(float3 v, float a) {
-    float s = sinf(a), c = cosf(a);
-    return float3(v.x, c * v.y - s * v.z, s * v.y + c * v.z);
-}
-VK_D float3 rotateY(float3 v, float a) {
-    float s = sinf(a), c = cosf(a);
-    return float3(c * v.x + s * v.z, v.y, -s * v.x + c * v.z);
-}
-VK_D float3 rotateZ(float3 v, float a) {
-    float s = sinf(a), c = cosf(a);
-    return float3(c * v.x - s * v.y, s * v.x + c * v.y, v.z);
-}
-VK_D float3 rotateMeshVector(float3 v, float3 rotationDegrees) {
+// sin/cos of a mesh's Euler rotation. The reference's shader re-evaluates these six transcendentals in every
+// rotateMeshVector call (three calls per hit, surface/transform.slang:9-29); they depend on MeshInfo only, so they are
+// evaluated once per mesh by k_mesh_trig (same device sinf/cosf, same bits) and fetched per hit.
+struct MeshTrig {
+    float sx, cx, sy, cy, sz, cz, pad0, pad1;
+};
+VK_D MeshTrig makeMeshTrig(float3 rotationDegrees) {
     float3 r = rotationDegrees * SURFACE_DEG_TO_RAD;
-    return rotateZ(rotateY(rotateX(v, r.x), r.y), r.z);
+    MeshTrig t;
+    t.sx = sinf(r.x); t.cx = cosf(r.x);
+    t.sy = sinf(r.y); t.cy = cosf(r.y);
+    t.sz = sinf(r.z); t.cz = cosf(r.z);
+    t.pad0 = t.pad1 = 0.0f;
+    return t;
+}
+VK_D float3 rotateMeshVector(float3 v, const MeshTrig& t) {
+    float3 a(v.x, t.cx * v.y - t.sx * v.z, t.sx * v.y + t.cx * v.z);          // rotateX
+    float3 b(t.cy * a.x + t.sy * a.z, a.y, -t.sy * a.x + t.cy * a.z);         // rotateY
+    return float3(t.cz * b.x - t.sz * b.y, t.sz * b.x + t.cz * b.y, b.z);     // rotateZ
 }
 VK_D float safeSignedReciprocal(float v) {
     if (abs(v) > SURFACE_SCALE_EPSILON) return 1.0f / v;
@@ -1441,10 +1454,10 @@ VK_D float safeSignedReciprocal(float v) {
 }
 VK_D float3 meshScale(const MeshInfo& m) { return float3(m.scale[0], m.scale[1], m.scale[2]); }
 VK_D float3 meshRotation(const MeshInfo& m) { return float3(m.rotation[0], m.rotation[1], m.rotation[2]); }
-VK_D float3 meshTransformVector(const MeshInfo& m, float3 v) { return rotateMeshVector(v * meshScale(m), meshRotation(m)); }
-VK_D float3 meshTransformNormal(const MeshInfo& m, float3 n) {
+VK_D float3 meshTransformVector(const MeshInfo& m, const MeshTrig& t, float3 v) { return rotateMeshVector(v * meshScale(m), t); }
+VK_D float3 meshTransformNormal(const MeshInfo& m, const MeshTrig& t, float3 n) {
     float3 inv(safeSignedReciprocal(m.scale[0]), safeSignedReciprocal(m.scale[1]), safeSignedReciprocal(m.scale[2]));
-    return safeNormalize(rotateMeshVector(n * inv, meshRotation(m)));
+    return safeNormalize(rotateMeshVector(n * inv, t));
 }
 VK_D float surfaceTransformSign(const MeshInfo& m) { return m.scale[0] * m.scale[1] * m.scale[2] < 0.0f ? -1.0f : 1.0f; }
 

@@ -124,8 +124,8 @@ struct SurfaceShadingData {
     SurfaceTextureData textureData;
 };
 
-__device__ __forceinline__ SurfaceShadingData reconstructSurfaceShading(const SceneView& sc, const MeshInfo& mesh, uint32_t prim, float2 bary,
-                                                                        float3 worldRayDir) {
+__device__ __forceinline__ SurfaceShadingData reconstructSurfaceShading(const SceneView& sc, const MeshInfo& mesh, const MeshTrig& trig, uint32_t prim,
+                                                                        float2 bary, float3 worldRayDir) {
     TriangleVertices tv;
     loadTriangleVertices(sc, mesh, prim, tv);
     float3 objectNormal = safeNormalize(interp3(unpackOctNormal(tv.v0.packedNormal), unpackOctNormal(tv.v1.packedNormal),
@@ -133,13 +133,13 @@ __device__ __forceinline__ SurfaceShadingData reconstructSurfaceShading(const Sc
     float4 objectTangent = interp4(unpackOctTangent(tv.v0.packedTangent), unpackOctTangent(tv.v1.packedTangent),
                                    unpackOctTangent(tv.v2.packedTangent), bary);
     float handedness = objectTangent.w < 0.0f ? -1.0f : 1.0f;
-    float3 shadingNormalUnoriented = meshTransformNormal(mesh, objectNormal);
+    float3 shadingNormalUnoriented = meshTransformNormal(mesh, trig, objectNormal);
     float facing = dot(shadingNormalUnoriented, worldRayDir) > 0.0f ? -1.0f : 1.0f;
     float3 p0(tv.v0.position[0], tv.v0.position[1], tv.v0.position[2]);
     float3 p1(tv.v1.position[0], tv.v1.position[1], tv.v1.position[2]);
     float3 p2(tv.v2.position[0], tv.v2.position[1], tv.v2.position[2]);
-    float3 worldEdge1 = meshTransformVector(mesh, p1 - p0);
-    float3 worldEdge2 = meshTransformVector(mesh, p2 - p0);
+    float3 worldEdge1 = meshTransformVector(mesh, trig, p1 - p0);
+    float3 worldEdge2 = meshTransformVector(mesh, trig, p2 - p0);
     float3 geometricNormal = safeNormalize(cross(worldEdge1, worldEdge2));
     if (surfaceTransformSign(mesh) < 0.0f) geometricNormal = -geometricNormal;
     SurfaceShadingData hit;
@@ -147,7 +147,7 @@ __device__ __forceinline__ SurfaceShadingData reconstructSurfaceShading(const Sc
     hit.frontFace = dot(geometricNormal, worldRayDir) < 0.0f ? 1u : 0u;
     hit.shadingNormal = shadingNormalUnoriented * facing;
     hit.geometricNormal = hit.frontFace != 0u ? geometricNormal : -geometricNormal;
-    hit.tangent = float4(safeNormalize(meshTransformVector(mesh, objectTangent.xyz())) * facing, handedness);
+    hit.tangent = float4(safeNormalize(meshTransformVector(mesh, trig, objectTangent.xyz())) * facing, handedness);
     hit.textureData = evaluateSurfaceTextureData(tv, bary);
     return hit;
 }
@@ -372,7 +372,13 @@ __global__ void __launch_bounds__(128) k_shade(const FrameParams fp, const uint3
         // ---- surface (PathSurfaceState.__init) -----------------------------------------------------------------------
         const MeshInfo mesh = loadMeshInfo(sc.meshInfos + hitInst);
         const float3 hitPoint = ray.origin + ray.direction * hitT;
-        SurfaceShadingData surface = reconstructSurfaceShading(sc, mesh, hitPrim, float2(__uint_as_float(ha.w), fp.hitB[i]), ray.direction);
+        MeshTrig trig;
+        {
+            const ::float4* tq = reinterpret_cast<const ::float4*>(sc.meshTrig + hitInst);
+            const ::float4 t0 = __ldg(tq), t1 = __ldg(tq + 1);
+            trig.sx = t0.x; trig.cx = t0.y; trig.sy = t0.z; trig.cy = t0.w; trig.sz = t1.x; trig.cz = t1.y; trig.pad0 = trig.pad1 = 0.0f;
+        }
+        SurfaceShadingData surface = reconstructSurfaceShading(sc, mesh, trig, hitPrim, float2(__uint_as_float(ha.w), fp.hitB[i]), ray.direction);
         Material material = loadMaterial(sc.materials + surface.materialIndex);
         {
             const ShadingBasis unperturbed = makeShadingBasis(surface.shadingNormal, surface.tangent);
@@ -803,6 +809,16 @@ __global__ void __launch_bounds__(256) k_untile(const uint32_t* __restrict__ src
         (void)srcStridePixels;
         for (uint32_t k = 0; k < words; k++) dst[d + k] = src[s + k];
     }
+}
+
+// One thread per mesh: the rotation trig the shade kernel would otherwise re-evaluate per hit (see MeshTrig).
+__global__ void __launch_bounds__(128) k_mesh_trig(const MeshInfo* __restrict__ infos, MeshTrig* __restrict__ out, uint32_t count) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    out[i] = makeMeshTrig(float3(infos[i].rotation[0], infos[i].rotation[1], infos[i].rotation[2]));
+}
+void launchMeshTrig(const MeshInfo* infos, MeshTrig* out, uint32_t count, cudaStream_t st) {
+    if (count) k_mesh_trig<<<(count + 127) / 128, 128, 0, st>>>(infos, out, count);
 }
 
 int traceBlocksPerSm(bool count) {
