@@ -292,8 +292,10 @@ def imported_node_transform(gltf_local):
 # ---------------------------------------------------------------------------------------------------------------
 def _norm3(v):
     v = np.asarray(v, dtype=np.float32)
-    n = f32(math.sqrt(float(f32(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]))))
-    return (v / n).astype(np.float32) if n > 0 else v
+    n = f32(math.sqrt(float(f32(f32(v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]))))
+    if n < f32(1.1920929e-07):  # cglm glm_vec3_normalize: zero vector below FLT_EPSILON, else scale by 1/norm
+        return np.zeros(3, dtype=np.float32)
+    return (v * f32(f32(1.0) / n)).astype(np.float32)
 
 
 def camera_matrices(pos, target, up, vfov_deg, width, height, near=0.001, far=10000.0):
@@ -533,15 +535,22 @@ class HostMesh:
     gltf_material: dict | None = None
 
 
+def _dot3(a, b):
+    """fp32 dot product summed left to right (np.dot may go through BLAS with a different accumulation)."""
+    a = np.asarray(a, dtype=np.float32)
+    b = np.asarray(b, dtype=np.float32)
+    return f32(f32(f32(a[0] * b[0]) + f32(a[1] * b[1])) + f32(a[2] * b[2]))
+
+
 def _fallback_tangent(n):
     n = np.asarray(n, dtype=np.float32)
-    if float(np.dot(n, n)) <= 1e-12:
+    if float(_dot3(n, n)) <= 1e-12:
         n = np.array([0, 0, 1], dtype=np.float32)
     else:
         n = _norm3(n)
     up = np.array([1, 0, 0], dtype=np.float32) if abs(float(n[2])) > 0.999 else np.array([0, 0, 1], dtype=np.float32)
     t = np.cross(up, n).astype(np.float32)
-    if float(np.dot(t, t)) <= 1e-12:
+    if float(_dot3(t, t)) <= 1e-12:
         t = np.array([1, 0, 0], dtype=np.float32)
     else:
         t = _norm3(t)
@@ -551,11 +560,11 @@ def _fallback_tangent(n):
 def _orthonormalize_tangent(n, t, handed):
     n = np.asarray(n, dtype=np.float32)
     t = np.asarray(t, dtype=np.float32)
-    if float(np.dot(n, n)) <= 1e-12 or float(np.dot(t, t)) <= 1e-12:
+    if float(_dot3(n, n)) <= 1e-12 or float(_dot3(t, t)) <= 1e-12:
         return None
     n = _norm3(n)
-    t = (t - n * f32(np.dot(t, n))).astype(np.float32)
-    if float(np.dot(t, t)) <= 1e-12:
+    t = (t - n * _dot3(t, n)).astype(np.float32)
+    if float(_dot3(t, t)) <= 1e-12:
         return None
     t = _norm3(t)
     return np.array([t[0], t[1], t[2], -1.0 if handed < 0 else 1.0], dtype=np.float32)
@@ -583,11 +592,11 @@ def _generate_tangents(verts, indices, uv):
             t2[i] += tdir
     for i in range(n):
         nrm = verts["normal"][i, :3]
-        if float(np.dot(nrm, nrm)) <= 1e-12 or float(np.dot(t1[i], t1[i])) <= 1e-12:
+        if float(_dot3(nrm, nrm)) <= 1e-12 or float(_dot3(t1[i], t1[i])) <= 1e-12:
             verts["tangent"][i] = _fallback_tangent(nrm)
             continue
         nn = _norm3(nrm)
-        handed = -1.0 if float(np.dot(np.cross(nn, t1[i]), t2[i])) < 0 else 1.0
+        handed = -1.0 if float(_dot3(np.cross(nn, t1[i]).astype(np.float32), t2[i])) < 0 else 1.0
         r = _orthonormalize_tangent(nrm, t1[i], handed)
         verts["tangent"][i] = r if r is not None else _fallback_tangent(nrm)
 

@@ -1,0 +1,173 @@
+"""The C host library (libvkrt_host.so: VKRT_* API, vkrt.scene + .glb ingest, scene preparation) against the oracle-side numpy
+restatement of the same reference code (oracle/host_ref.py), array for array. Runs without a GPU (hostOnly handles).
+
+Integer / byte work (packed normals, tangents, colours, indices, bases, dedup, alias indices, flags) must match bit for bit.
+fp32 results that pass through libm transcendentals (sin/cos of Euler angles, tan of the field of view, atan2/asin in the
+transform decomposition) are compared with a few-ulp tolerance, stated per test."""
+import os
+
+import numpy as np
+import pytest
+
+import harness as H
+
+hr = H.hr
+ASSETS = os.path.join(H.ROOT, "assets")
+
+
+def _host(**kw):
+    from vkrt_b200 import host
+    return host.Host(host_only=True, **kw)
+
+
+def _ulp_close(a, b, ulps=4, floor=1e-6):
+    a, b = np.asarray(a, np.float32), np.asarray(b, np.float32)
+    tol = np.maximum(np.abs(a), np.abs(b)) * np.float32(ulps * 1.2e-7) + np.float32(floor)
+    return bool(np.all(np.abs(a.astype(np.float64) - b.astype(np.float64)) <= tol))
+
+
+@pytest.mark.parametrize("scene", ["cornell", "prism", "caustics"])
+def test_scene_file_matches_reference_restatement(scene):
+    path = os.path.join(ASSETS, "scenes", scene + ".json")
+    w, h = 320, 180
+    hs = _host(width=w, height=h)
+    hs.load_scene(path)
+    hs.start_render(w, h, 64)
+    got = hs.prepare_scene()
+    ref = hr.load_scene_json(path).prepare(w, h)
+
+    # geometry: byte-exact (positions/uvs are copied, normals/tangents/colours are quantised integers)
+    assert got["vertices"].tobytes() == ref["vertices"].tobytes()
+    assert np.array_equal(got["indices"], ref["indices"])
+    assert np.array_equal(got["geometrySource"], ref["geometrySource"])
+    assert np.array_equal(got["alphaTested"], ref["alphaTested"])
+    gi, ri = got["meshInfos"], ref["meshInfos"]
+    for key in ("vertexBase", "vertexCount", "indexBase", "indexCount", "materialIndex", "renderBackfaces"):
+        assert np.array_equal(gi[key], ri[key]), key
+    assert np.array_equal(gi["opacity"], ri["opacity"])
+    # transforms: composed from Euler angles with sinf/cosf -> a few ulp; decomposed Euler angles in degrees -> 1e-3 degrees
+    assert _ulp_close(got["world3x4"], ref["world3x4"], ulps=8)
+    assert np.allclose(gi["position"], ri["position"], rtol=0, atol=1e-6)
+    assert np.allclose(gi["scale"], ri["scale"], rtol=1e-5, atol=1e-6)
+    d = np.abs(((gi["rotation"] - ri["rotation"]) + 180.0) % 360.0 - 180.0)
+    assert float(d.max()) < 2e-3
+    # materials: sanitised copies of the JSON values -> byte-exact
+    assert got["materials"].tobytes() == np.ascontiguousarray(ref["materials"]).tobytes()
+    # lights
+    L = ref["lights"]
+    assert len(got["emissiveMeshes"]) == L["meshCount"] and len(got["emissiveTriangles"]) == L["triangleCount"]
+    if L["meshCount"]:
+        for key in ("triOffset", "triCount"):
+            assert np.array_equal(got["emissiveMeshes"][key], L["meshes"][key][:L["meshCount"]])
+        assert _ulp_close(got["emissiveMeshes"]["pmfMesh"], L["meshes"]["pmfMesh"][:L["meshCount"]], ulps=64)
+        assert _ulp_close(got["emissiveMeshes"]["invTotalArea"], L["meshes"]["invTotalArea"][:L["meshCount"]], ulps=64)
+        assert np.array_equal(got["emissiveMeshes"]["emission"], L["meshes"]["emission"][:L["meshCount"]])
+        for key in ("v0Area", "e1Pad", "e2Pad"):
+            assert np.allclose(got["emissiveTriangles"][key], L["triangles"][key][:L["triangleCount"]], rtol=2e-5, atol=2e-6), key
+        assert np.allclose(gi["lightPdfArea"], ri["lightPdfArea"], rtol=1e-4, atol=0)
+        # alias tables: same structure whenever the pmf inputs agree to rounding; compare the distributions they encode
+        for q, idx, rq, ridx, n in ((got["triAliasQ"], got["triAliasIdx"], L["triAliasQ"], L["triAliasIdx"], L["triangleCount"]),):
+            em = got["emissiveMeshes"][0]
+            cnt = int(em["triCount"])
+
+            def pmf(qq, ii):
+                p = np.zeros(cnt)
+                np.add.at(p, np.arange(cnt), qq[:cnt].astype(np.float64) / cnt)
+                np.add.at(p, ii[:cnt].astype(np.int64), (1.0 - qq[:cnt].astype(np.float64)) / cnt)
+                return p
+            assert np.allclose(pmf(q, idx), pmf(rq, ridx), rtol=0, atol=1e-6)
+    # SceneData: integers exact, camera matrices to a few ulp (tanf, normalisation)
+    gsd = np.frombuffer(got["sceneData"].tobytes(), dtype=hr.SCENE_DATA)[0]
+    rsd = ref["sceneData"]
+    for key in ("rrMaxDepth", "rrMinDepth", "packedRenderSettings", "environmentTextureIndex", "debugMode", "misNeeEnabled", "emissiveMeshCount",
+                "emissiveTriangleCount"):
+        assert int(gsd[key]) == int(rsd[key]), key
+    assert np.array_equal(gsd["viewportRect"], rsd["viewportRect"])
+    assert np.allclose(gsd["environmentLight"], rsd["environmentLight"], rtol=1e-6)
+    assert np.allclose(gsd["viewInverse"], rsd["viewInverse"], rtol=2e-5, atol=2e-6)
+    assert np.allclose(gsd["projInverse"], rsd["projInverse"], rtol=2e-5, atol=1e-4)
+    hs.close()
+
+
+def test_dedup_shares_geometry_across_imports():
+    hs = _host()
+    hs.load_scene(os.path.join(ASSETS, "scenes", "cornell.json"))
+    got = hs.prepare_scene()
+    gs = got["geometrySource"]
+    # cornell: plane.glb x5 -> one owner, sphere.glb x2 -> one owner, bunny -> its own
+    assert len(gs) == 8 and len(set(gs.tolist())) == 3
+    assert len(got["vertices"]) == 4 + 559 + 34834
+    hs.close()
+
+
+def test_setters_clamp_like_the_reference():
+    from vkrt_b200 import VkrtError
+    hs = _host()
+    hs.set_path_depth(9, 200)           # settings.c:41-57: max clamped to 64, min <= max
+    s = hs.scene_settings()
+    assert (s.rrMinDepth, s.rrMaxDepth) == (9, 64)
+    hs.set_path_depth(100, 0)
+    s = hs.scene_settings()
+    assert (s.rrMinDepth, s.rrMaxDepth) == (1, 1)
+    hs.set_samples_per_pixel(0)
+    assert hs.scene_settings().samplesPerPixel == 1
+    with pytest.raises(VkrtError):
+        hs.set_render_mode(7)
+    with pytest.raises(VkrtError):
+        hs.set_debug_mode(99)
+    hs.set_environment_light((float("nan"), -1.0, 2.0), float("inf"))
+    s = hs.scene_settings()
+    assert list(s.environmentColor) == [1.0, 0.0, 2.0] and s.environmentStrength == 0.0  # non-finite -> fallback (numeric.h:5-17)
+    hs.close()
+
+
+def test_render_session_protocol_without_device():
+    """startRender resets the accumulation state; tracing needs a device and fails loudly on a hostOnly handle."""
+    from vkrt_b200 import VkrtError
+    hs = _host()
+    hs.generate_soup(300)
+    hs.start_render(64, 48, 8)
+    st = hs.render_status()
+    assert st.renderPhase == 1 and st.totalSamples == 0 and st.renderTargetSamples == 8
+    hs.update_scene()
+    with pytest.raises(VkrtError):
+        hs.draw()
+    hs.close()
+
+
+def test_procedural_scenes_are_deterministic_and_well_formed():
+    a, b = _host(), _host()
+    for hs in (a, b):
+        hs.generate_soup(1000)
+    pa, pb = a.prepare_scene(), b.prepare_scene()
+    assert pa["vertices"].tobytes() == pb["vertices"].tobytes()
+    assert len(pa["indices"]) == 3000 + 6 and len(pa["meshInfos"]) == 17
+    assert int(pa["meshInfos"]["indexCount"][:16].sum()) == 3000
+    assert len(pa["emissiveTriangles"]) == 2
+    a.close(); b.close()
+    hs = _host()
+    hs.generate_instanced(os.path.join(ASSETS, "models", "suzanne.glb"), 27)
+    p = hs.prepare_scene()
+    assert len(p["meshInfos"]) == 27 + 2
+    assert len(set(p["geometrySource"][:27].tolist())) == 1   # one BLAS shared by every instance
+    assert len(p["indices"]) == 62976 * 3 + 12
+    hs.close()
+
+
+def test_alias_table_reconstructs_pmf():
+    """buildAliasTable exactness (SURVEY §8c iii): the table encodes exactly the input distribution."""
+    import ctypes as C
+    from vkrt_b200 import host
+    lib = host.load_host_library()
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 7, 960, 4099):
+        pmf = rng.uniform(0.01, 1.0, n).astype(np.float32)
+        pmf /= pmf.sum(dtype=np.float32)
+        q, idx = hr.build_alias_table(pmf)
+        cq, cidx = np.zeros(n, np.float32), np.zeros(n, np.uint32)
+        assert lib.VKRT_hostBuildAliasTable(pmf.ctypes.data_as(C.c_void_p), C.c_uint32(n), cq.ctypes.data_as(C.c_void_p), cidx.ctypes.data_as(C.c_void_p)) == 1
+        assert np.array_equal(cq.view(np.uint32), q.view(np.uint32)) and np.array_equal(cidx, idx)   # C host == restatement, bit for bit
+        rec = np.zeros(n)
+        np.add.at(rec, np.arange(n), q.astype(np.float64) / n)
+        np.add.at(rec, idx.astype(np.int64), (1.0 - q.astype(np.float64)) / n)
+        assert np.allclose(rec, pmf, atol=2e-6)

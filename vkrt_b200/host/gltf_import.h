@@ -1,0 +1,29 @@
+/* gltf_import.h — result of importing one .glb (see gltf_import.c). */
+#ifndef VKRT_HOST_GLTF_IMPORT_H
+#define VKRT_HOST_GLTF_IMPORT_H
+
+#include "../../include/vkrt_host.h"
+
+typedef struct GltfMesh {
+    Vertex* vertices;     /* engine space (Z-up), 16-byte aligned */
+    size_t vertexCount;
+    uint32_t* indices;
+    size_t indexCount;
+    float world[4][4];    /* engine-space world matrix of the owning node (column-major) */
+    int materialIndex;    /* into GltfImport.materials, -1 = none */
+    int doubleSided;
+    char name[VKRT_NAME_LEN];
+} GltfMesh;
+
+typedef struct GltfImport {
+    GltfMesh* meshes;
+    uint32_t meshCount;
+    Material* materials;
+    char (*materialNames)[VKRT_NAME_LEN];
+    uint32_t materialCount;
+} GltfImport;
+
+int gltfImportFile(const char* path, GltfImport* out, char* error, size_t errorSize); /* 1 = ok */
+void gltfImportFree(GltfImport* imp);
+
+#endif
