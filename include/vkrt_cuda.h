@@ -163,6 +163,11 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_render_frame(vkrt_cuda_ctx* ctx, const Scene
 /* Same work, but only enqueued on the context's stream (no host sync, no stats); pair with vkrt_cuda_sync. */
 VKRT_CUDA_API VKRT_Result vkrt_cuda_render_frame_async(vkrt_cuda_ctx* ctx, const SceneData* sceneData);
 VKRT_CUDA_API VKRT_Result vkrt_cuda_sync(vkrt_cuda_ctx* ctx);
+/* Device-side stopwatch on the context's own stream (the stream every kernel of this library is launched on): begin records a CUDA
+ * event, end records a second one, waits for it and returns the elapsed device time between the two. Replaces the reference's GPU
+ * timestamp pair around the frame (record.c:274-280,795-800) for multi-frame measurements. */
+VKRT_CUDA_API VKRT_Result vkrt_cuda_timer_begin(vkrt_cuda_ctx* ctx);
+VKRT_CUDA_API VKRT_Result vkrt_cuda_timer_end(vkrt_cuda_ctx* ctx, float* outMs);
 
 /* Multi-GPU (no reference equivalent). The library talks to NCCL through dlopen("libnccl.so.2"),
  * so a single-GPU host needs no NCCL. uniqueId is the 128-byte ncclUniqueId obtained from

@@ -85,7 +85,7 @@ struct vkrt_cuda_ctx {
     uint32_t rank = 0, worldSize = 1, tileW = 32, tileH = 32;
     uint32_t requestedCapacity = 0, flags = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t evA = nullptr, evB = nullptr;
+    cudaEvent_t evA = nullptr, evB = nullptr, evT0 = nullptr, evT1 = nullptr;
     std::string error;
 
     // scene
@@ -476,6 +476,8 @@ VKRT_CUDA_API void vkrt_cuda_destroy(vkrt_cuda_ctx* ctx) {
     for (auto* t : ctx->texturePixels) delete t;
     for (cudaEvent_t e : ctx->stageEvents) cudaEventDestroy(e);
     if (ctx->evA) cudaEventDestroy(ctx->evA);
+    if (ctx->evT0) cudaEventDestroy(ctx->evT0);
+    if (ctx->evT1) cudaEventDestroy(ctx->evT1);
     if (ctx->evB) cudaEventDestroy(ctx->evB);
     cudaStream_t st = ctx->stream;
     delete ctx;
@@ -756,6 +758,23 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_sync(vkrt_cuda_ctx* ctx) {
     if (!ctx) return VKRT_ERROR_INVALID_ARGUMENT;
     cudaSetDevice(ctx->device);
     CU(cudaStreamSynchronize(ctx->stream));
+    return VKRT_SUCCESS;
+}
+
+VKRT_CUDA_API VKRT_Result vkrt_cuda_timer_begin(vkrt_cuda_ctx* ctx) {
+    if (!ctx) return VKRT_ERROR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    if (!ctx->evT0) { CU(cudaEventCreate(&ctx->evT0)); CU(cudaEventCreate(&ctx->evT1)); }
+    CU(cudaEventRecord(ctx->evT0, ctx->stream));
+    return VKRT_SUCCESS;
+}
+VKRT_CUDA_API VKRT_Result vkrt_cuda_timer_end(vkrt_cuda_ctx* ctx, float* outMs) {
+    if (!ctx || !outMs) return VKRT_ERROR_INVALID_ARGUMENT;
+    if (!ctx->evT0) return fail(ctx, VKRT_ERROR_OPERATION_FAILED, "timer_end without timer_begin");
+    cudaSetDevice(ctx->device);
+    CU(cudaEventRecord(ctx->evT1, ctx->stream));
+    CU(cudaEventSynchronize(ctx->evT1));
+    CU(cudaEventElapsedTime(outMs, ctx->evT0, ctx->evT1));
     return VKRT_SUCCESS;
 }
 
