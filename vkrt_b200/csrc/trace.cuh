@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_trace(const TraceParams P) {
     int blasBase = 0;
     uint32_t curInst = 0, curFlags = 0;
     RayShear shear;
-    uint2 G = make_uint2(0u, 0u);
+    uint2 G = make_uint2(0u, 0u), Gt = make_uint2(0u, 0u);  // pending node group / pending primitive group of this lane
     bool exhausted = false;
     unsigned long long nNodes = 0, nTris = 0, nInst = 0;
 
@@ -158,6 +158,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_trace(const TraceParams P) {
                         inBlas = false;
                         sp = 0;
                         G = make_uint2(A.tlasRoot, 0x80000000u);
+                        Gt = make_uint2(0u, 0u);
                         if (A.instanceCount == 0u) G = make_uint2(0u, 0u);
                     }
                 }
@@ -167,25 +168,31 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_trace(const TraceParams P) {
         if (__ballot_sync(0xffffffffu, R.active) == 0u) break;
 
         // ---- traverse until this lane finishes or the warp wants a refill ------------------------------------------
+        // Each trip of this loop is three short, warp-convergent sections (profiles/r01_notes.md: the previous
+        // "test a node, then loop over all of its primitives" shape ran at 10.5 of 32 lanes):
+        //   1. lanes without a pending primitive test ONE node (or unpack a popped primitive group),
+        //   2. lanes with a pending primitive process ONE primitive (triangle test, or instance entry in the TLAS),
+        //   3. lanes with nothing pending pop the stack / leave the BLAS / retire the ray.
         while (R.active) {
-            uint2 Gt = make_uint2(0u, 0u);
-            if (G.y & 0xff000000u) {
-                const int bit = 31 - __clz(G.y & 0xff000000u);
-                const uint32_t slot = (uint32_t)(bit - 24) ^ octinv;
-                G.y &= ~(1u << bit);
-                if (G.y & 0xff000000u) { if (sp < TRACE_STACK) stack[sp++] = G; }
-                const uint32_t nodeIndex = G.x + __popc(G.y & 0xffu & ((1u << slot) - 1u));
-                uint32_t childBase, primBase, imask;
-                const uint32_t hits = intersectNode8(A.nodes + nodeIndex, o, idir, octinv, R.tMin, R.tBest, childBase, primBase, imask);
-                if (COUNT) nNodes++;
-                G = make_uint2(childBase, (hits & 0xff000000u) | imask);
-                Gt = make_uint2(primBase, hits & 0x00ffffffu);
-            } else {
-                Gt = G;
-                G = make_uint2(0u, 0u);
+            if (Gt.y == 0u) {
+                if (G.y & 0xff000000u) {
+                    const int bit = 31 - __clz(G.y & 0xff000000u);
+                    const uint32_t slot = (uint32_t)(bit - 24) ^ octinv;
+                    G.y &= ~(1u << bit);
+                    if (G.y & 0xff000000u) { if (sp < TRACE_STACK) stack[sp++] = G; }
+                    const uint32_t nodeIndex = G.x + __popc(G.y & 0xffu & ((1u << slot) - 1u));
+                    uint32_t childBase, primBase, imask;
+                    const uint32_t hits = intersectNode8(A.nodes + nodeIndex, o, idir, octinv, R.tMin, R.tBest, childBase, primBase, imask);
+                    if (COUNT) nNodes++;
+                    G = make_uint2(childBase, (hits & 0xff000000u) | imask);
+                    Gt = make_uint2(primBase, hits & 0x00ffffffu);
+                } else if (G.y) {  // a primitive group that was parked on the stack
+                    Gt = G;
+                    G = make_uint2(0u, 0u);
+                }
             }
 
-            while (Gt.y) {
+            if (Gt.y) {
                 const int i = __ffs(Gt.y) - 1;
                 Gt.y &= Gt.y - 1u;
                 const uint32_t primIndex = Gt.x + (uint32_t)i;
@@ -217,48 +224,48 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_trace(const TraceParams P) {
                             if (COUNT) nInst++;
                         }
                     }
-                    break;
-                }
-                // triangle
-                const ::float4* tri = A.triangles + (size_t)primIndex * 3;
-                const ::float4 a = __ldg(tri), b = __ldg(tri + 1), c = __ldg(tri + 2);
-                if (COUNT) nTris++;
-                float t, u, v;
-                if (!watertightTriangle(o, shear, float3(a.x, a.y, a.z), float3(b.x, b.y, b.z), float3(c.x, c.y, c.z), t, u, v)) continue;
-                if (!(t > R.tMin)) continue;
-                const uint32_t prim = __float_as_uint(a.w);
-                bool closer = t < R.tBest;
-                if (!closer && t == R.tBest && R.hitInst != VKRT_INVALID_INDEX)
-                    closer = curInst < R.hitInst || (curInst == R.hitInst && prim < R.hitPrim);
-                if (!closer) continue;
-                if (curFlags & INSTANCE_FLAG_ALPHA_TESTED) {
-                    const uint32_t seed = R.anyHit ? __ldg(P.shSeed + (R.index - extCount)) : (P.raySeed ? __ldg(P.raySeed + R.index) : 0u);
-                    if (!alphaHitAccepted(P.scene, curInst, prim, float2(u, v), seed)) continue;
-                }
-                if (R.anyHit) {
-                    if (curFlags & INSTANCE_FLAG_TRANSMISSIVE) {
-                        R.sawTransmissive = true;   // keep looking for an opaque occluder, but not in this instance
-                        sp = blasBase;
-                        G = make_uint2(0u, 0u);
-                        Gt.y = 0u;
-                    } else {
-                        R.hitInst = curInst;        // occluded: done
-                        R.hitPrim = prim;
-                        sp = 0;
-                        inBlas = false;
-                        G = make_uint2(0u, 0u);
-                        Gt.y = 0u;
+                } else {
+                    const ::float4* tri = A.triangles + (size_t)primIndex * 3;
+                    const ::float4 a = __ldg(tri), b = __ldg(tri + 1), c = __ldg(tri + 2);
+                    if (COUNT) nTris++;
+                    float t, u, v;
+                    bool accept = watertightTriangle(o, shear, float3(a.x, a.y, a.z), float3(b.x, b.y, b.z), float3(c.x, c.y, c.z), t, u, v) && t > R.tMin;
+                    const uint32_t prim = __float_as_uint(a.w);
+                    if (accept) {
+                        bool closer = t < R.tBest;
+                        if (!closer && t == R.tBest && R.hitInst != VKRT_INVALID_INDEX)
+                            closer = curInst < R.hitInst || (curInst == R.hitInst && prim < R.hitPrim);
+                        accept = closer;
                     }
-                    break;
+                    if (accept && (curFlags & INSTANCE_FLAG_ALPHA_TESTED)) {
+                        const uint32_t seed = R.anyHit ? __ldg(P.shSeed + (R.index - extCount)) : (P.raySeed ? __ldg(P.raySeed + R.index) : 0u);
+                        accept = alphaHitAccepted(P.scene, curInst, prim, float2(u, v), seed);
+                    }
+                    if (accept) {
+                        if (!R.anyHit) {
+                            R.hitInst = curInst;
+                            R.hitPrim = prim;
+                            R.tBest = t;
+                            R.hitU = u;
+                            R.hitV = v;
+                        } else if (curFlags & INSTANCE_FLAG_TRANSMISSIVE) {
+                            R.sawTransmissive = true;   // keep looking for an opaque occluder, but not in this instance
+                            sp = blasBase;
+                            G = make_uint2(0u, 0u);
+                            Gt.y = 0u;
+                        } else {
+                            R.hitInst = curInst;        // occluded: done
+                            R.hitPrim = prim;
+                            sp = 0;
+                            inBlas = false;
+                            G = make_uint2(0u, 0u);
+                            Gt.y = 0u;
+                        }
+                    }
                 }
-                R.hitInst = curInst;
-                R.hitPrim = prim;
-                R.tBest = t;
-                R.hitU = u;
-                R.hitV = v;
             }
 
-            if ((G.y & 0xff000000u) == 0u) {
+            if (Gt.y == 0u && (G.y & 0xff000000u) == 0u) {
                 if (inBlas && sp == blasBase) {  // BLAS exhausted: back to the world-space ray
                     inBlas = false;
                     o = R.o; d = R.d;

@@ -275,7 +275,10 @@ __device__ __forceinline__ float computeSpectralMISWeight(float4 sampled, float4
 // shade: one path vertex (the body of the reference's depth loop between two TraceRay calls)
 // ----------------------------------------------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(128) k_shade(const FrameParams fp, const uint32_t depth) {
+#ifndef SHADE_MIN_BLOCKS
+#define SHADE_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade(const FrameParams fp, const uint32_t depth) {
     const uint32_t count = fp.extCount[depth];
     const PathState& S = fp.st[depth & 1u];
     const PathState& N = fp.st[(depth & 1u) ^ 1u];
