@@ -1145,6 +1145,7 @@ struct BSDFState {
     float wavelengthNm = 0.0f;
     uint spectralMode = 0u;
     BSDFBranchWeights sampleWeights;
+    __device__ BSDFState() {}
     __device__ BSDFState(const BSDFMaterial& m, float3 wo_, uint ff, float wl, uint sm)
         : material(m), wo(wo_), frontFace(ff), wavelengthNm(wl), spectralMode(sm) {
         ggx = makeGGXParams(m, wo_);

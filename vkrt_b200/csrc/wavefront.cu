@@ -274,11 +274,28 @@ __device__ __forceinline__ float computeSpectralMISWeight(float4 sampled, float4
 // ----------------------------------------------------------------------------------------------------------------------
 // shade: one path vertex (the body of the reference's depth loop between two TraceRay calls)
 // ----------------------------------------------------------------------------------------------------------------------
-template <int MODE>
 #ifndef SHADE_MIN_BLOCKS
-#define SHADE_MIN_BLOCKS 2
+#define SHADE_MIN_BLOCKS 1
 #endif
-__global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade(const FrameParams fp, const uint32_t depth) {
+#ifndef SHADE_BLOCK
+#define SHADE_BLOCK 512
+#endif
+// The body is cut into four phases separated by block barriers. k_shade is bound by instruction fetch, not by ALU or memory
+// (profiles/r01_notes.md: "no instruction" is the top stall with ~200 KB of SASS live); keeping the warps of a block inside the same
+// phase makes them share the instruction lines they fetch. Every thread of a block runs the same number of loop trips and reaches
+// every barrier; a thread whose vertex is finished (miss, absorbed, debug view, out of range) just carries live = false through.
+#ifdef SHADE_NO_BARRIER
+#define SHADE_PHASE_BARRIER()
+#else
+#define SHADE_PHASE_BARRIER() __syncthreads()
+#endif
+#ifdef SHADE_FINE_BARRIERS
+#define SHADE_SUBPHASE_BARRIER() __syncthreads()
+#else
+#define SHADE_SUBPHASE_BARRIER()
+#endif
+template <int MODE>
+__global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const FrameParams fp, const uint32_t depth) {
     const uint32_t count = fp.extCount[depth];
     const PathState& S = fp.st[depth & 1u];
     const PathState& N = fp.st[(depth & 1u) ^ 1u];
@@ -289,130 +306,153 @@ __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade(const FramePara
     const bool neeEnabled = (fp.modeFlags & MODE_NEE_ENABLED) && !(fp.modeFlags & MODE_BSDF_ONLY);
     const bool neeOnly = (fp.modeFlags & MODE_NEE_ONLY) != 0u;
 
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-        const ::float4 ro = S.rayO[i], rd = S.rayD[i];
-        const ::uint4 ha = fp.hitA[i];
-        const uint32_t rec = S.record[i];
-        uint32_t rng = S.rng[i];
-        uint32_t flags = S.flags[i];
-        const ::float4 thrRaw = S.thr[i];
-        Ray ray;
-        ray.origin = float3(ro.x, ro.y, ro.z);
-        ray.direction = float3(rd.x, rd.y, rd.z);
-        const uint32_t hitInst = ha.x, hitPrim = ha.y;
-        const float hitT = __uint_as_float(ha.z);
-        const uint32_t sampleInChunk = rec / lpc;
-        const uint32_t lp = rec - sampleInChunk * lpc;
-        const uint32_t sampleIndex = fp.chunkFirstSample + sampleInChunk;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < count; base += gridDim.x * blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        bool live = i < count;
 
-        // ---- unpack mode state ---------------------------------------------------------------------------------
+        // ================================ phase 1: unpack, miss, surface, material, closure state ================================
+        Ray ray;
+        uint32_t rec = 0u, rng = 0u, flags = 0u, hitInst = VKRT_INVALID_INDEX, hitPrim = 0u, lp = 0u, sampleIndex = 0u;
+        float hitT = 0.0f, hitU = 0.0f;
         float3 thrRgb(0.0f);
         float thrScalar = 0.0f, prevBsdfPdf = 0.0f, lambdaScalar = 0.0f, unit = 0.0f;
         float4 thr4(0.0f), wl4(0.0f), techPdf(0.0f);
         bool heroActive = false;
-        if (MODE == MODE_RGB) {
-            thrRgb = float3(thrRaw.x, thrRaw.y, thrRaw.z);
-            prevBsdfPdf = thrRaw.w;
-        } else if (MODE == MODE_SINGLE) {
-            thrScalar = thrRaw.x;
-            lambdaScalar = thrRaw.y;
-            prevBsdfPdf = thrRaw.z;
-        } else {
-            thr4 = fromF4(thrRaw);
-            const ::float4 misc = S.heroMisc[i];
-            unit = misc.x;
-            thrScalar = misc.y;
-            prevBsdfPdf = misc.z;
-            wl4 = heroWavelengths(unit);
-            lambdaScalar = wl4.x;
-            heroActive = (flags & PF_HERO_ACTIVE) != 0u;
-            techPdf = fromF4(S.techPdf[i]);
-        }
         MediumState medium;
-        medium.flags = (flags >> 1) & 3u;
-        if (medium.absorptionActive()) {
-            const ::float4 sg = S.sigma[i];
-            medium.absorptionSigma = float3(sg.x, sg.y, sg.z);
-            medium.spectralAbsorptionSigma = fromF4(sg);
-            if (MODE == MODE_SINGLE || (MODE == MODE_HERO && !heroActive)) medium.spectralAbsorptionSigma = float4(sg.x);
+        MeshInfo mesh;
+        float3 hitPoint(0.0f);
+        SurfaceShadingData surface;
+        Material material;
+        ShadingBasis basis;
+        BSDFMaterial bm;
+        BSDFState state;
+        bool currentVertexNeeAllowed = false;
+
+        if (live) {
+            const ::float4 ro = S.rayO[i], rd = S.rayD[i];
+            const ::uint4 ha = fp.hitA[i];
+            rec = S.record[i];
+            rng = S.rng[i];
+            flags = S.flags[i];
+            const ::float4 thrRaw = S.thr[i];
+            ray.origin = float3(ro.x, ro.y, ro.z);
+            ray.direction = float3(rd.x, rd.y, rd.z);
+            hitInst = ha.x;
+            hitPrim = ha.y;
+            hitT = __uint_as_float(ha.z);
+            hitU = __uint_as_float(ha.w);
+            const uint32_t sampleInChunk = rec / lpc;
+            lp = rec - sampleInChunk * lpc;
+            sampleIndex = fp.chunkFirstSample + sampleInChunk;
+
+            // ---- unpack mode state ---------------------------------------------------------------------------------
+            if (MODE == MODE_RGB) {
+                thrRgb = float3(thrRaw.x, thrRaw.y, thrRaw.z);
+                prevBsdfPdf = thrRaw.w;
+            } else if (MODE == MODE_SINGLE) {
+                thrScalar = thrRaw.x;
+                lambdaScalar = thrRaw.y;
+                prevBsdfPdf = thrRaw.z;
+            } else {
+                thr4 = fromF4(thrRaw);
+                const ::float4 misc = S.heroMisc[i];
+                unit = misc.x;
+                thrScalar = misc.y;
+                prevBsdfPdf = misc.z;
+                wl4 = heroWavelengths(unit);
+                lambdaScalar = wl4.x;
+                heroActive = (flags & PF_HERO_ACTIVE) != 0u;
+                techPdf = fromF4(S.techPdf[i]);
+            }
+            medium.flags = (flags >> 1) & 3u;
+            if (medium.absorptionActive()) {
+                const ::float4 sg = S.sigma[i];
+                medium.absorptionSigma = float3(sg.x, sg.y, sg.z);
+                medium.spectralAbsorptionSigma = fromF4(sg);
+                if (MODE == MODE_SINGLE || (MODE == MODE_HERO && !heroActive)) medium.spectralAbsorptionSigma = float4(sg.x);
+            }
+
+            // ---- miss: environment (loop.slang:4-6, */transport.slang accumulate*Environment) -------------------------
+            if (hitInst == VKRT_INVALID_INDEX) {
+                if (!neeOnly && !mediumHasActiveBoundary(medium)) {
+                    const float3 env = sampleEnvironmentRadiance(sc, scene, ray.direction);
+                    if (MODE == MODE_RGB) {
+                        ::float4 r = fp.rec.radiance[rec];
+                        const float3 c = thrRgb * env;
+                        r.x += c.x; r.y += c.y; r.z += c.z;
+                        fp.rec.radiance[rec] = r;
+                    } else if (MODE == MODE_SINGLE) {
+                        fp.rec.radiance[rec].x += thrScalar * spectralScalarFromLinearSrgb(T, env, lambdaScalar);
+                    } else if (heroActive) {
+                        const float4 c = thr4 * heroWavelengthBalanceWeight(techPdf) * spectralScalarFromLinearSrgb4(T, env, wl4);
+                        ::float4 r = fp.rec.radiance[rec];
+                        r.x += c.x; r.y += c.y; r.z += c.z; r.w += c.w;
+                        fp.rec.radiance[rec] = r;
+                    } else {
+                        fp.rec.radianceScalar[rec] += thrScalar * spectralScalarFromLinearSrgb(T, env, lambdaScalar);
+                    }
+                }
+                live = false;
+            }
         }
 
-        // ---- miss: environment (loop.slang:4-6, */transport.slang accumulate*Environment) -------------------------
-        if (hitInst == VKRT_INVALID_INDEX) {
-            if (!neeOnly && !mediumHasActiveBoundary(medium)) {
-                const float3 env = sampleEnvironmentRadiance(sc, scene, ray.direction);
-                if (MODE == MODE_RGB) {
-                    ::float4 r = fp.rec.radiance[rec];
-                    const float3 c = thrRgb * env;
-                    r.x += c.x; r.y += c.y; r.z += c.z;
-                    fp.rec.radiance[rec] = r;
-                } else if (MODE == MODE_SINGLE) {
-                    fp.rec.radiance[rec].x += thrScalar * spectralScalarFromLinearSrgb(T, env, lambdaScalar);
-                } else if (heroActive) {
-                    const float4 c = thr4 * heroWavelengthBalanceWeight(techPdf) * spectralScalarFromLinearSrgb4(T, env, wl4);
-                    ::float4 r = fp.rec.radiance[rec];
-                    r.x += c.x; r.y += c.y; r.z += c.z; r.w += c.w;
-                    fp.rec.radiance[rec] = r;
-                } else {
-                    fp.rec.radianceScalar[rec] += thrScalar * spectralScalarFromLinearSrgb(T, env, lambdaScalar);
-                }
-            }
-            continue;
-        }
+        SHADE_SUBPHASE_BARRIER();
 
         // ---- medium transmittance along the segment (apply*MediumTransmittance) ------------------------------------
-        if (medium.absorptionActive()) {
-            if (MODE == MODE_RGB) thrRgb *= mediumTransmittance(medium, hitT);
-            else if (MODE == MODE_HERO && heroActive) thr4 *= mediumSpectralTransmittance(medium, hitT);
-            else thrScalar *= mediumTransmittance(medium, hitT).x;
-        }
-        {
+        if (live) {
+            if (medium.absorptionActive()) {
+                if (MODE == MODE_RGB) thrRgb *= mediumTransmittance(medium, hitT);
+                else if (MODE == MODE_HERO && heroActive) thr4 *= mediumSpectralTransmittance(medium, hitT);
+                else thrScalar *= mediumTransmittance(medium, hitT).x;
+            }
             const bool alive = MODE == MODE_RGB ? anyGreater(thrRgb, 0.0f)
                                                 : ((MODE == MODE_HERO && heroActive) ? anyGreater(thr4, 0.0f) : thrScalar > 0.0f);
-            if (!alive) continue;
+            if (!alive) live = false;
         }
 
         // ---- surface (PathSurfaceState.__init) -----------------------------------------------------------------------
-        const MeshInfo mesh = loadMeshInfo(sc.meshInfos + hitInst);
-        const float3 hitPoint = ray.origin + ray.direction * hitT;
-        MeshTrig trig;
-        {
-            const ::float4* tq = reinterpret_cast<const ::float4*>(sc.meshTrig + hitInst);
-            const ::float4 t0 = __ldg(tq), t1 = __ldg(tq + 1);
-            trig.sx = t0.x; trig.cx = t0.y; trig.sy = t0.z; trig.cy = t0.w; trig.sz = t1.x; trig.cz = t1.y; trig.pad0 = trig.pad1 = 0.0f;
-        }
-        SurfaceShadingData surface = reconstructSurfaceShading(sc, mesh, trig, hitPrim, float2(__uint_as_float(ha.w), fp.hitB[i]), ray.direction);
-        Material material = loadMaterial(sc.materials + surface.materialIndex);
-        {
-            const ShadingBasis unperturbed = makeShadingBasis(surface.shadingNormal, surface.tangent);
-            surface.shadingNormal = applyNormalTexture(sc, material, surface.textureData, unperturbed);
-        }
-        surface.shadingNormal = sanitizeShadingNormal(surface.shadingNormal, surface.geometricNormal, -ray.direction);
-        const ShadingBasis basis = makeShadingBasis(surface.shadingNormal, surface.tangent);
-        applySurfaceTextures(sc, material, surface.textureData);
-        const BSDFMaterial bm(material);
+        if (live) {
+            mesh = loadMeshInfo(sc.meshInfos + hitInst);
+            hitPoint = ray.origin + ray.direction * hitT;
+            MeshTrig trig;
+            {
+                const ::float4* tq = reinterpret_cast<const ::float4*>(sc.meshTrig + hitInst);
+                const ::float4 t0 = __ldg(tq), t1 = __ldg(tq + 1);
+                trig.sx = t0.x; trig.cx = t0.y; trig.sy = t0.z; trig.cy = t0.w; trig.sz = t1.x; trig.cz = t1.y; trig.pad0 = trig.pad1 = 0.0f;
+            }
+            surface = reconstructSurfaceShading(sc, mesh, trig, hitPrim, float2(hitU, fp.hitB[i]), ray.direction);
+            material = loadMaterial(sc.materials + surface.materialIndex);
+            {
+                const ShadingBasis unperturbed = makeShadingBasis(surface.shadingNormal, surface.tangent);
+                surface.shadingNormal = applyNormalTexture(sc, material, surface.textureData, unperturbed);
+            }
+            surface.shadingNormal = sanitizeShadingNormal(surface.shadingNormal, surface.geometricNormal, -ray.direction);
+            basis = makeShadingBasis(surface.shadingNormal, surface.tangent);
+            applySurfaceTextures(sc, material, surface.textureData);
+            bm = BSDFMaterial(material);
 
-        // ---- primary-surface debug views (integrator/path/debug.slang:31-64) -----------------------------------------
-        if (sampleIndex == 0u && depth == 0u && scene.debugMode != VKRT_DEBUG_MODE_NONE) {
-            const uint32_t dm = scene.debugMode;
-            bool handled = true;
-            float3 c(0.0f);
-            if (dm == VKRT_DEBUG_MODE_NORMALS) c = surface.shadingNormal * 0.5f + 0.5f;
-            else if (dm == VKRT_DEBUG_MODE_DEPTH) c = float3(1.0f / (1.0f + hitT));
-            else if (dm == VKRT_DEBUG_MODE_BASE_COLOR_MAP) c = sampleBaseColorTexture(sc, material, surface.textureData).xyz();
-            else if (dm == VKRT_DEBUG_MODE_METALLIC_MAP) c = float3(sampleMetallicRoughnessTexture(sc, material, surface.textureData).z);
-            else if (dm == VKRT_DEBUG_MODE_ROUGHNESS_MAP) c = float3(sampleMetallicRoughnessTexture(sc, material, surface.textureData).y);
-            else if (dm == VKRT_DEBUG_MODE_NORMAL_MAP) c = sampleNormalTexture(sc, material, surface.textureData).xyz();
-            else if (dm == VKRT_DEBUG_MODE_EMISSIVE_MAP) c = sampleEmissiveTexture(sc, material, surface.textureData).xyz();
-            else handled = false;
-            if (handled) {
-                fp.film.debugColor[lp] = toF4(c, 1.0f);
-                continue;
+            // ---- primary-surface debug views (integrator/path/debug.slang:31-64) -----------------------------------------
+            if (sampleIndex == 0u && depth == 0u && scene.debugMode != VKRT_DEBUG_MODE_NONE) {
+                const uint32_t dm = scene.debugMode;
+                bool handled = true;
+                float3 c(0.0f);
+                if (dm == VKRT_DEBUG_MODE_NORMALS) c = surface.shadingNormal * 0.5f + 0.5f;
+                else if (dm == VKRT_DEBUG_MODE_DEPTH) c = float3(1.0f / (1.0f + hitT));
+                else if (dm == VKRT_DEBUG_MODE_BASE_COLOR_MAP) c = sampleBaseColorTexture(sc, material, surface.textureData).xyz();
+                else if (dm == VKRT_DEBUG_MODE_METALLIC_MAP) c = float3(sampleMetallicRoughnessTexture(sc, material, surface.textureData).z);
+                else if (dm == VKRT_DEBUG_MODE_ROUGHNESS_MAP) c = float3(sampleMetallicRoughnessTexture(sc, material, surface.textureData).y);
+                else if (dm == VKRT_DEBUG_MODE_NORMAL_MAP) c = sampleNormalTexture(sc, material, surface.textureData).xyz();
+                else if (dm == VKRT_DEBUG_MODE_EMISSIVE_MAP) c = sampleEmissiveTexture(sc, material, surface.textureData).xyz();
+                else handled = false;
+                if (handled) {
+                    fp.film.debugColor[lp] = toF4(c, 1.0f);
+                    live = false;
+                }
             }
         }
-
-        // ---- denoiser features (loop.slang:83-103) ----------------------------------------------------------------
-        {
+        SHADE_SUBPHASE_BARRIER();
+        if (live) {
+            // ---- denoiser features (loop.slang:83-103) ----------------------------------------------------------------
             const bool follow = materialDenoiserShouldFollowSpecularHit(bm, surface.frontFace);
             if (depth == 0u) fp.rec.follow[rec] = follow ? 1.0f : 0.0f;
             if (!(flags & PF_FEATURES_RESOLVED) && !follow) {
@@ -420,18 +460,19 @@ __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade(const FramePara
                 fp.rec.featB[rec] = toF4(surface.shadingNormal, float(depth + 1u));
                 flags |= PF_FEATURES_RESOLVED;
             }
+            const float stateWavelength = MODE == MODE_RGB ? 0.0f : lambdaScalar;
+            state = BSDFState(bm, worldToLocal(-ray.direction, basis), surface.frontFace, stateWavelength, MODE == MODE_RGB ? 0u : 1u);
+            currentVertexNeeAllowed = !medium.refractiveActive();
         }
+        SHADE_PHASE_BARRIER();
 
-        const float stateWavelength = MODE == MODE_RGB ? 0.0f : lambdaScalar;
-        const BSDFState state(bm, worldToLocal(-ray.direction, basis), surface.frontFace, stateWavelength, MODE == MODE_RGB ? 0u : 1u);
-        const bool currentVertexNeeAllowed = !medium.refractiveActive();
-
-        // ---- next-event estimation (light/direct/*.slang); the shadow ray is traced by the next k_trace launch ---------
+        // ================================ phase 2: next-event estimation (light/direct/*.slang) ================================
+        // The shadow ray is traced by the next k_trace launch.
         bool shadowPending = false;
-        ::float4 shadowO, shadowD, shadowC;
+        ::float4 shadowO = make_float4(0.f, 0.f, 0.f, 0.f), shadowD = shadowO, shadowC = shadowO;
         uint32_t shadowSeed = 0u;
         bool shadowScalarLane = false;
-        if (neeEnabled && currentVertexNeeAllowed && cosTheta(state.wo) > 0.0f) {
+        if (live && neeEnabled && currentVertexNeeAllowed && cosTheta(state.wo) > 0.0f) {
             const DirectLightSurfaceSample ls = sampleDirectLightSurface(sc, scene, hitPoint, rng);
             if (ls.valid) {
                 const float3 shadowOffset = dot(ls.wi, surface.geometricNormal) >= 0.0f ? surface.geometricNormal : -surface.geometricNormal;
@@ -477,150 +518,160 @@ __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade(const FramePara
                 shadowSeed = rng;
             }
         }
+        SHADE_PHASE_BARRIER();
 
-        // ---- emission seen by BSDF sampling (integrator.slang:79-85; hero: integrator.slang:98-126) -------------------
-        if (!neeOnly) {
-            const float3 emission = float3(material.emissionColor[0], material.emissionColor[1], material.emissionColor[2]) * material.emissionLuminance;
-            if (anyGreater(emission, 0.0f)) {
-                const bool misActive = (fp.modeFlags & MODE_NEE_ENABLED) && (flags & PF_PREV_VERTEX_NEE_ALLOWED) && depth > 0u;
-                if (MODE == MODE_HERO && heroActive) {
-                    float misWeight = heroWavelengthBalanceWeight(techPdf);
-                    if (misActive) {
-                        const float lp2 = lightPdfAreaToSolidAngle(mesh.lightPdfArea, surface.geometricNormal, ray.direction, hitT);
-                        const float4 pv = fromF4(S.prevVertexTechPdf[i]), pb = fromF4(S.prevBsdfTechPdf[i]);
-                        misWeight = computeSpectralMISWeight(pv * pb, pv * lp2);
-                    }
-                    const float4 c = thr4 * (spectralScalarFromLinearSrgb4(T, emission, wl4) * misWeight);
-                    ::float4 r = fp.rec.radiance[rec];
-                    r.x += c.x; r.y += c.y; r.z += c.z; r.w += c.w;
-                    fp.rec.radiance[rec] = r;
-                } else {
-                    float misWeight = 1.0f;
-                    if (misActive && prevBsdfPdf > 0.0f) {
-                        const float lp2 = lightPdfAreaToSolidAngle(mesh.lightPdfArea, surface.geometricNormal, ray.direction, hitT);
-                        misWeight = lp2 <= 0.0f ? 1.0f : powerHeuristic(prevBsdfPdf, lp2);
-                    }
-                    if (MODE == MODE_RGB) {
-                        const float3 c = thrRgb * (emission * misWeight);
-                        ::float4 r = fp.rec.radiance[rec];
-                        r.x += c.x; r.y += c.y; r.z += c.z;
-                        fp.rec.radiance[rec] = r;
-                    } else {
-                        const float c = thrScalar * (spectralScalarFromLinearSrgb(T, emission, lambdaScalar) * misWeight);
-                        if (MODE == MODE_SINGLE) fp.rec.radiance[rec].x += c;
-                        else fp.rec.radianceScalar[rec] += c;
-                    }
-                }
-            }
-        }
-        if ((fp.modeFlags & MODE_BOUNCE_COUNT) && sampleIndex == 0u) fp.film.bounceCount[lp] = depth + 1u;
-
-        // ---- sample the next direction (sample*NextDirection) -------------------------------------------------------
-        bool pathContinues = true;
+        // ================================ phase 3: emission, BSDF sampling ================================
+        bool pathContinues = live;
         uint32_t isTransmission = 0u;
         float3 wi(0.0f);
         float4 newPrevVertexTechPdf(0.0f), newPrevBsdfTechPdf(0.0f);
-        if (MODE == MODE_HERO && heroActive) {
-            const SpectralBSDFSample smp = sampleSpectralBSDF(T, state, basis, wl4, rng);
-            if (!smp.isUsable()) pathContinues = false;
-            if (pathContinues) {
-                newPrevVertexTechPdf = techPdf;
-                newPrevBsdfTechPdf = smp.techniquePdf;
-                techPdf *= smp.techniquePdf;
-                thr4 *= smp.weight;
-                if (!anyGreater(thr4, 0.0f)) pathContinues = false;
-            }
-            if (pathContinues) {
-                if (smp.isTransmission != 0u && materialMediumIsRefractive(bm) && bm.abbeNumber > 0.0f) {
-                    // dispersive collapse (spectral_hero/transport.slang:77-87). The 4-lane radiance stays in the record and
-                    // is converted to XYZ by the film kernel together with the scalar lane.
-                    thrScalar = thr4.x;
-                    thr4 = float4(0.0f);
-                    prevBsdfPdf = smp.techniquePdf.x;
-                    heroActive = false;
-                    flags &= ~PF_HERO_ACTIVE;
+        if (live) {
+            // ---- emission seen by BSDF sampling (integrator.slang:79-85; hero: integrator.slang:98-126) -------------------
+            if (!neeOnly) {
+                const float3 emission = float3(material.emissionColor[0], material.emissionColor[1], material.emissionColor[2]) * material.emissionLuminance;
+                if (anyGreater(emission, 0.0f)) {
+                    const bool misActive = (fp.modeFlags & MODE_NEE_ENABLED) && (flags & PF_PREV_VERTEX_NEE_ALLOWED) && depth > 0u;
+                    if (MODE == MODE_HERO && heroActive) {
+                        float misWeight = heroWavelengthBalanceWeight(techPdf);
+                        if (misActive) {
+                            const float lp2 = lightPdfAreaToSolidAngle(mesh.lightPdfArea, surface.geometricNormal, ray.direction, hitT);
+                            const float4 pv = fromF4(S.prevVertexTechPdf[i]), pb = fromF4(S.prevBsdfTechPdf[i]);
+                            misWeight = computeSpectralMISWeight(pv * pb, pv * lp2);
+                        }
+                        const float4 c = thr4 * (spectralScalarFromLinearSrgb4(T, emission, wl4) * misWeight);
+                        ::float4 r = fp.rec.radiance[rec];
+                        r.x += c.x; r.y += c.y; r.z += c.z; r.w += c.w;
+                        fp.rec.radiance[rec] = r;
+                    } else {
+                        float misWeight = 1.0f;
+                        if (misActive && prevBsdfPdf > 0.0f) {
+                            const float lp2 = lightPdfAreaToSolidAngle(mesh.lightPdfArea, surface.geometricNormal, ray.direction, hitT);
+                            misWeight = lp2 <= 0.0f ? 1.0f : powerHeuristic(prevBsdfPdf, lp2);
+                        }
+                        if (MODE == MODE_RGB) {
+                            const float3 c = thrRgb * (emission * misWeight);
+                            ::float4 r = fp.rec.radiance[rec];
+                            r.x += c.x; r.y += c.y; r.z += c.z;
+                            fp.rec.radiance[rec] = r;
+                        } else {
+                            const float c = thrScalar * (spectralScalarFromLinearSrgb(T, emission, lambdaScalar) * misWeight);
+                            if (MODE == MODE_SINGLE) fp.rec.radiance[rec].x += c;
+                            else fp.rec.radianceScalar[rec] += c;
+                        }
+                    }
                 }
-                isTransmission = smp.isTransmission;
-                wi = smp.wi;
             }
-        } else {
-            const BSDFSample smp = sampleBSDF(T, state, basis, rng);
-            if (!smp.isUsable()) pathContinues = false;
-            if (pathContinues) {
-                if (MODE == MODE_RGB) {
-                    thrRgb *= smp.weight;
-                    if (!anyGreater(thrRgb, 0.0f)) pathContinues = false;
-                } else {
-                    thrScalar *= smp.weight.x;
-                    if (thrScalar <= 0.0f) pathContinues = false;
-                }
-                prevBsdfPdf = smp.pdf;
-                isTransmission = smp.isTransmission;
-                wi = smp.wi;
-            }
+            if ((fp.modeFlags & MODE_BOUNCE_COUNT) && sampleIndex == 0u) fp.film.bounceCount[lp] = depth + 1u;
         }
-
-        if (pathContinues) {
-            // medium update + NEE bookkeeping (integrator.slang:96-98)
-            if (MODE == MODE_RGB) updateMediumStateFromTransmission(T, bm, surface.frontFace, isTransmission, 0.0f, 0u, medium);
-            else if (MODE == MODE_HERO && heroActive) updateMediumStateFromTransmissionSpectral(T, bm, surface.frontFace, isTransmission, wl4, medium);
-            else updateMediumStateFromTransmission(T, bm, surface.frontFace, isTransmission, lambdaScalar, 1u, medium);
-            const bool sampledPathNeeAllowed = currentVertexNeeAllowed && isTransmission == 0u;  // shadow kernel clears it on "unsupported"
-            flags = (flags & ~(PF_PREV_VERTEX_NEE_ALLOWED | PF_MEDIUM_REFRACTIVE | PF_MEDIUM_ABSORPTION)) |
-                    (sampledPathNeeAllowed ? PF_PREV_VERTEX_NEE_ALLOWED : 0u) | (medium.flags << 1);
-            // Russian roulette (integrator.slang:100-106)
-            if (depth + 1u >= scene.rrMinDepth) {
-                float cp;
-                if (MODE == MODE_RGB) cp = clamp(maxComponent(thrRgb), RR_MIN_CONTINUE_PROB, RR_MAX_CONTINUE_PROB);
-                else if (MODE == MODE_HERO && heroActive) cp = clamp(maxComponent4(thr4), RR_MIN_CONTINUE_PROB, RR_MAX_CONTINUE_PROB);
-                else cp = clamp(thrScalar, RR_MIN_CONTINUE_PROB, RR_MAX_CONTINUE_PROB);
-                if (rand(rng) > cp) {
-                    pathContinues = false;
-                } else if (MODE == MODE_RGB) {
-                    thrRgb /= cp;
-                } else if (MODE == MODE_HERO && heroActive) {
-                    techPdf *= float4(cp);
-                    thr4 /= cp;
-                } else {
-                    thrScalar /= cp;
+        SHADE_SUBPHASE_BARRIER();
+        if (live) {
+            // ---- sample the next direction (sample*NextDirection) -------------------------------------------------------
+            if (MODE == MODE_HERO && heroActive) {
+                const SpectralBSDFSample smp = sampleSpectralBSDF(T, state, basis, wl4, rng);
+                if (!smp.isUsable()) pathContinues = false;
+                if (pathContinues) {
+                    newPrevVertexTechPdf = techPdf;
+                    newPrevBsdfTechPdf = smp.techniquePdf;
+                    techPdf *= smp.techniquePdf;
+                    thr4 *= smp.weight;
+                    if (!anyGreater(thr4, 0.0f)) pathContinues = false;
                 }
-            }
-        }
-        if (depth + 1u >= scene.rrMaxDepth) pathContinues = false;
-
-        // ---- write the continuing path at its new (compacted) position ------------------------------------------------
-        uint32_t newPos = 0x7fffffffu;
-        if (pathContinues) {
-            newPos = allocSlots(fp.extCount + depth + 1u);
-            const float3 off = isTransmission != 0u ? -surface.geometricNormal : surface.geometricNormal;
-            N.rayO[newPos] = toF4(hitPoint + off * SHADOW_ORIGIN_OFFSET, RAY_T_MIN);
-            N.rayD[newPos] = toF4(wi, RAY_T_MAX);
-            N.record[newPos] = rec;
-            N.rng[newPos] = rng;
-            N.flags[newPos] = flags;
-            if (MODE == MODE_RGB) {
-                N.thr[newPos] = toF4(thrRgb, prevBsdfPdf);
-                if (medium.absorptionActive()) N.sigma[newPos] = toF4(medium.absorptionSigma, 0.0f);
-            } else if (MODE == MODE_SINGLE) {
-                N.thr[newPos] = make_float4(thrScalar, lambdaScalar, prevBsdfPdf, 0.0f);
-                if (medium.absorptionActive()) N.sigma[newPos] = toF4(medium.absorptionSigma, 0.0f);
+                if (pathContinues) {
+                    if (smp.isTransmission != 0u && materialMediumIsRefractive(bm) && bm.abbeNumber > 0.0f) {
+                        // dispersive collapse (spectral_hero/transport.slang:77-87). The 4-lane radiance stays in the record and
+                        // is converted to XYZ by the film kernel together with the scalar lane.
+                        thrScalar = thr4.x;
+                        thr4 = float4(0.0f);
+                        prevBsdfPdf = smp.techniquePdf.x;
+                        heroActive = false;
+                        flags &= ~PF_HERO_ACTIVE;
+                    }
+                    isTransmission = smp.isTransmission;
+                    wi = smp.wi;
+                }
             } else {
-                N.thr[newPos] = toF4(thr4);
-                N.heroMisc[newPos] = make_float4(unit, thrScalar, prevBsdfPdf, 0.0f);
-                N.techPdf[newPos] = toF4(techPdf);
-                N.prevVertexTechPdf[newPos] = toF4(newPrevVertexTechPdf);
-                N.prevBsdfTechPdf[newPos] = toF4(newPrevBsdfTechPdf);
-                if (medium.absorptionActive())
-                    N.sigma[newPos] = heroActive ? toF4(medium.spectralAbsorptionSigma) : toF4(medium.absorptionSigma, 0.0f);
+                const BSDFSample smp = sampleBSDF(T, state, basis, rng);
+                if (!smp.isUsable()) pathContinues = false;
+                if (pathContinues) {
+                    if (MODE == MODE_RGB) {
+                        thrRgb *= smp.weight;
+                        if (!anyGreater(thrRgb, 0.0f)) pathContinues = false;
+                    } else {
+                        thrScalar *= smp.weight.x;
+                        if (thrScalar <= 0.0f) pathContinues = false;
+                    }
+                    prevBsdfPdf = smp.pdf;
+                    isTransmission = smp.isTransmission;
+                    wi = smp.wi;
+                }
             }
         }
-        if (shadowPending) {
-            const uint32_t k = allocSlots(fp.shCount + depth);
-            fp.shO[k] = shadowO;
-            fp.shD[k] = shadowD;
-            fp.shContribution[k] = shadowC;
-            fp.shTarget[k] = make_uint2(rec, newPos | (shadowScalarLane ? SHADOW_KIND_SCALAR : 0u));
-            fp.shSeed[k] = shadowSeed;
+        SHADE_PHASE_BARRIER();
+
+        // ================================ phase 4: medium update, Russian roulette, queue writes ================================
+        if (live) {
+            if (pathContinues) {
+                // medium update + NEE bookkeeping (integrator.slang:96-98)
+                if (MODE == MODE_RGB) updateMediumStateFromTransmission(T, bm, surface.frontFace, isTransmission, 0.0f, 0u, medium);
+                else if (MODE == MODE_HERO && heroActive) updateMediumStateFromTransmissionSpectral(T, bm, surface.frontFace, isTransmission, wl4, medium);
+                else updateMediumStateFromTransmission(T, bm, surface.frontFace, isTransmission, lambdaScalar, 1u, medium);
+                const bool sampledPathNeeAllowed = currentVertexNeeAllowed && isTransmission == 0u;  // shadow kernel clears it on "unsupported"
+                flags = (flags & ~(PF_PREV_VERTEX_NEE_ALLOWED | PF_MEDIUM_REFRACTIVE | PF_MEDIUM_ABSORPTION)) |
+                        (sampledPathNeeAllowed ? PF_PREV_VERTEX_NEE_ALLOWED : 0u) | (medium.flags << 1);
+                // Russian roulette (integrator.slang:100-106)
+                if (depth + 1u >= scene.rrMinDepth) {
+                    float cp;
+                    if (MODE == MODE_RGB) cp = clamp(maxComponent(thrRgb), RR_MIN_CONTINUE_PROB, RR_MAX_CONTINUE_PROB);
+                    else if (MODE == MODE_HERO && heroActive) cp = clamp(maxComponent4(thr4), RR_MIN_CONTINUE_PROB, RR_MAX_CONTINUE_PROB);
+                    else cp = clamp(thrScalar, RR_MIN_CONTINUE_PROB, RR_MAX_CONTINUE_PROB);
+                    if (rand(rng) > cp) {
+                        pathContinues = false;
+                    } else if (MODE == MODE_RGB) {
+                        thrRgb /= cp;
+                    } else if (MODE == MODE_HERO && heroActive) {
+                        techPdf *= float4(cp);
+                        thr4 /= cp;
+                    } else {
+                        thrScalar /= cp;
+                    }
+                }
+            }
+            if (depth + 1u >= scene.rrMaxDepth) pathContinues = false;
+
+            // ---- write the continuing path at its new (compacted) position ------------------------------------------------
+            uint32_t newPos = 0x7fffffffu;
+            if (pathContinues) {
+                newPos = allocSlots(fp.extCount + depth + 1u);
+                const float3 off = isTransmission != 0u ? -surface.geometricNormal : surface.geometricNormal;
+                N.rayO[newPos] = toF4(hitPoint + off * SHADOW_ORIGIN_OFFSET, RAY_T_MIN);
+                N.rayD[newPos] = toF4(wi, RAY_T_MAX);
+                N.record[newPos] = rec;
+                N.rng[newPos] = rng;
+                N.flags[newPos] = flags;
+                if (MODE == MODE_RGB) {
+                    N.thr[newPos] = toF4(thrRgb, prevBsdfPdf);
+                    if (medium.absorptionActive()) N.sigma[newPos] = toF4(medium.absorptionSigma, 0.0f);
+                } else if (MODE == MODE_SINGLE) {
+                    N.thr[newPos] = make_float4(thrScalar, lambdaScalar, prevBsdfPdf, 0.0f);
+                    if (medium.absorptionActive()) N.sigma[newPos] = toF4(medium.absorptionSigma, 0.0f);
+                } else {
+                    N.thr[newPos] = toF4(thr4);
+                    N.heroMisc[newPos] = make_float4(unit, thrScalar, prevBsdfPdf, 0.0f);
+                    N.techPdf[newPos] = toF4(techPdf);
+                    N.prevVertexTechPdf[newPos] = toF4(newPrevVertexTechPdf);
+                    N.prevBsdfTechPdf[newPos] = toF4(newPrevBsdfTechPdf);
+                    if (medium.absorptionActive())
+                        N.sigma[newPos] = heroActive ? toF4(medium.spectralAbsorptionSigma) : toF4(medium.absorptionSigma, 0.0f);
+                }
+            }
+            if (shadowPending) {
+                const uint32_t k = allocSlots(fp.shCount + depth);
+                fp.shO[k] = shadowO;
+                fp.shD[k] = shadowD;
+                fp.shContribution[k] = shadowC;
+                fp.shTarget[k] = make_uint2(rec, newPos | (shadowScalarLane ? SHADOW_KIND_SCALAR : 0u));
+                fp.shSeed[k] = shadowSeed;
+            }
         }
     }
 }
@@ -832,9 +883,9 @@ int traceBlocksPerSm(bool count) {
 }
 int shadeBlocksPerSm(int mode) {
     int n = 0;
-    if (mode == MODE_RGB) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shade<MODE_RGB>, 128, 0);
-    else if (mode == MODE_SINGLE) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shade<MODE_SINGLE>, 128, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shade<MODE_HERO>, 128, 0);
+    if (mode == MODE_RGB) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shade<MODE_RGB>, SHADE_BLOCK, 0);
+    else if (mode == MODE_SINGLE) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shade<MODE_SINGLE>, SHADE_BLOCK, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shade<MODE_HERO>, SHADE_BLOCK, 0);
     return n > 0 ? n : 1;
 }
 
@@ -845,9 +896,9 @@ void launchRaygen(int mode, const FrameParams& fp, int grid, cudaStream_t st) {
     else k_raygen<MODE_HERO><<<grid, 256, 0, st>>>(fp);
 }
 void launchShade(int mode, const FrameParams& fp, uint32_t depth, int grid, cudaStream_t st) {
-    if (mode == MODE_RGB) k_shade<MODE_RGB><<<grid, 128, 0, st>>>(fp, depth);
-    else if (mode == MODE_SINGLE) k_shade<MODE_SINGLE><<<grid, 128, 0, st>>>(fp, depth);
-    else k_shade<MODE_HERO><<<grid, 128, 0, st>>>(fp, depth);
+    if (mode == MODE_RGB) k_shade<MODE_RGB><<<grid, SHADE_BLOCK, 0, st>>>(fp, depth);
+    else if (mode == MODE_SINGLE) k_shade<MODE_SINGLE><<<grid, SHADE_BLOCK, 0, st>>>(fp, depth);
+    else k_shade<MODE_HERO><<<grid, SHADE_BLOCK, 0, st>>>(fp, depth);
 }
 void launchFilm(int mode, const FrameParams& fp, int firstChunk, int lastChunk, int grid, cudaStream_t st) {
     if (mode == MODE_RGB) k_film<MODE_RGB><<<grid, 256, 0, st>>>(fp, firstChunk, lastChunk);
