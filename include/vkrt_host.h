@@ -273,6 +273,11 @@ VKRT_HOST_API vkrt_cuda_ctx* VKRT_cudaContext(VKRT* vkrt);
 VKRT_HOST_API VKRT_Result VKRT_getLastFrameStats(const VKRT* vkrt, vkrt_cuda_frame_stats* outStats);
 VKRT_HOST_API VKRT_Result VKRT_getBuildStats(const VKRT* vkrt, vkrt_cuda_build_stats* outStats);
 VKRT_HOST_API const char* VKRT_lastError(const VKRT* vkrt);
+/* Interleaved-tile partition of a width x height image over worldSize ranks (vkrt_b200/csrc/tiles.h; tile size 0 = 32): the ascending
+ * global tile ids owned by `rank`. A rank's tile-compact film stores its tiles back to back, tileWidth*tileHeight pixels each. */
+VKRT_HOST_API VKRT_Result VKRT_tilePartition(uint32_t width, uint32_t height, uint32_t tileWidth, uint32_t tileHeight, uint32_t rank, uint32_t worldSize,
+                                             uint32_t* outLocalTileCount, uint32_t* outLocalToGlobalTile, uint32_t capacity, uint32_t* outTilesX,
+                                             uint32_t* outTilesY);
 
 #ifdef __cplusplus
 }

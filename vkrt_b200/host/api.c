@@ -2,6 +2,7 @@
 #include <time.h>
 
 #include "host_state.h"
+#include "../csrc/tiles.h"
 
 static double nowSeconds(void) {
     struct timespec ts;
@@ -935,6 +936,22 @@ VKRT_Result VKRT_appOfflineRender(VKRT* v, uint32_t width, uint32_t height, uint
         out->mpathsPerSecond = out->samplesPerSecond * (double)width * (double)height / 1e6;
         out->extensionRays = v->totalExtensionRays;
         out->shadowRays = v->totalShadowRays;
+    }
+    return VKRT_SUCCESS;
+}
+
+/* ---- tile partition (shared definition with the CUDA library: csrc/tiles.h) ------------------------------------------------ */
+VKRT_Result VKRT_tilePartition(uint32_t width, uint32_t height, uint32_t tileWidth, uint32_t tileHeight, uint32_t rank, uint32_t worldSize,
+                               uint32_t* outLocalTileCount, uint32_t* outLocalToGlobalTile, uint32_t capacity, uint32_t* outTilesX, uint32_t* outTilesY) {
+    if (width == 0 || height == 0 || worldSize == 0 || rank >= worldSize) return VKRT_ERROR_INVALID_ARGUMENT;
+    vkrt_tile_layout lay;
+    vkrt_tile_layout_init(&lay, width, height, tileWidth, tileHeight, rank, worldSize);
+    if (outLocalTileCount) *outLocalTileCount = lay.localTileCount;
+    if (outTilesX) *outTilesX = lay.tilesX;
+    if (outTilesY) *outTilesY = lay.tilesY;
+    if (outLocalToGlobalTile) {
+        if (capacity < lay.localTileCount) return VKRT_ERROR_INVALID_ARGUMENT;
+        vkrt_tile_layout_local_tiles(&lay, outLocalToGlobalTile);
     }
     return VKRT_SUCCESS;
 }
