@@ -59,7 +59,9 @@ enum {
     VKRT_CUDA_FLAG_NONE = 0u,
     VKRT_CUDA_FLAG_COUNT_RAYS = 1u << 0,    /* per-frame ray/node/triangle counters (instrumented build of the same kernels) */
     VKRT_CUDA_FLAG_NO_MATERIAL_SORT = 1u << 1, /* shade in queue order instead of material-sorted order */
-    VKRT_CUDA_FLAG_STAGE_TIMING = 1u << 2     /* vkrt_cuda_render_frame records a CUDA event after every launch and fills traceMs / shadeMs */
+    VKRT_CUDA_FLAG_STAGE_TIMING = 1u << 2,    /* vkrt_cuda_render_frame records a CUDA event after every launch and fills traceMs / shadeMs */
+    VKRT_CUDA_FLAG_FORCE_TWO_LEVEL = 1u << 3, /* always build BLAS per unique geometry + TLAS (default: chosen from the instancing ratio) */
+    VKRT_CUDA_FLAG_FORCE_FLAT = 1u << 4       /* always build one BVH over all instanced triangles */
 };
 
 typedef struct vkrt_cuda_build_stats {
@@ -72,6 +74,8 @@ typedef struct vkrt_cuda_build_stats {
     uint64_t instancedTriangleCount;
     uint64_t bvh8NodeCount;
     uint64_t accelBytes;       /* nodes + repacked triangles + instance records */
+    uint32_t flat;             /* 1 = single-level BVH over instanced triangles was built, 0 = BLAS per geometry + TLAS */
+    uint32_t reserved;
 } vkrt_cuda_build_stats;
 
 typedef struct vkrt_cuda_frame_stats {

@@ -41,6 +41,7 @@ def main():
     ap.add_argument("--count", action="store_true")
     ap.add_argument("--max-paths", type=int, default=0)
     ap.add_argument("--png", default="")
+    ap.add_argument("--flags", type=int, default=0, help="extra VKRT_CUDA_FLAG_* bits (2 = no material sort, 8 = two-level, 16 = flat)")
     a = ap.parse_args()
 
     t0 = time.time()
@@ -54,7 +55,7 @@ def main():
     prep["sceneData"]["samplesPerPixel"] = a.spp
     print("scene prep %.2fs: %d verts %d indices %d instances %d emissive tris" % (
         time.time() - t0, len(prep["vertices"]), len(prep["indices"]), len(prep["meshInfos"]), prep["lights"]["triangleCount"]), flush=True)
-    g = H.CudaBackend(flags=(1 if a.count else 0) | 4, max_paths=a.max_paths or a.w * a.h * a.spp)
+    g = H.CudaBackend(flags=(1 if a.count else 0) | 4 | a.flags, max_paths=a.max_paths or a.w * a.h * a.spp)
     g.upload(prep, rgb2spec=scenes.rgb2spec() if a.mode != "rgb" else None)
     bs = g.build_stats
     print("build: %.3f ms (blas %.3f tlas %.3f) geometries %d instances %d tris %d nodes %d bytes %d" % (

@@ -15,6 +15,9 @@ import scenes
 
 pytestmark = pytest.mark.gpu
 
+# both acceleration-structure variants must give the same bits: BLAS per geometry + TLAS (flag 8), one flat BVH (flag 16)
+ACCEL = pytest.mark.parametrize("accel", [8, 16], ids=["two_level", "flat"])
+
 
 def _check_ids(o, g, sd):
     o.trace_primary(sd)
@@ -40,32 +43,36 @@ def _check_images(o, g, frac=0.995, rel_rmse=0.02):
     assert (np.abs(oa - ob) > 64).mean() < 0.01  # 16-bit display values
 
 
-def test_cornell_rgb_ids_and_images():
+@ACCEL
+def test_cornell_rgb_ids_and_images(accel):
     w = h = 128
     prep = scenes.cornell(w, h, spp=4)
-    o, g = scenes.both_backends(prep, w, h)
+    o, g = scenes.both_backends(prep, w, h, flags=accel)
+    assert g.build_stats.flat == (1 if accel == 16 else 0)
     _check_ids(o, g, prep["sceneData"])
     o.render(prep["sceneData"], frames=3)
     g.render(prep["sceneData"], frames=3)
     _check_images(o, g)
 
 
-def test_cornell_glass_medium_and_unsupported_transmission():
+@ACCEL
+def test_cornell_glass_medium_and_unsupported_transmission(accel):
     w = h = 96
     prep = scenes.cornell(w, h, spp=4, glass=True)
     prep["materials"][7]["absorptionCoefficient"] = 2.0
     prep["materials"][7]["attenuationColor"] = (0.4, 0.8, 0.9)
-    o, g = scenes.both_backends(prep, w, h)
+    o, g = scenes.both_backends(prep, w, h, flags=accel)
     _check_ids(o, g, prep["sceneData"])
     o.render(prep["sceneData"], frames=2)
     g.render(prep["sceneData"], frames=2)
     _check_images(o, g, frac=0.99, rel_rmse=0.05)
 
 
-def test_instanced_two_level_bvh():
+@ACCEL
+def test_instanced_two_level_bvh(accel):
     w, h = 160, 96
     prep = scenes.instanced(w, h, count=64, spp=2)
-    o, g = scenes.both_backends(prep, w, h)
+    o, g = scenes.both_backends(prep, w, h, flags=accel)
     assert g.build_stats.uniqueGeometries == 3 and g.build_stats.instanceCount == 66
     _check_ids(o, g, prep["sceneData"])
     o.render(prep["sceneData"], frames=2)
@@ -73,10 +80,11 @@ def test_instanced_two_level_bvh():
     _check_images(o, g, frac=0.99, rel_rmse=0.05)
 
 
-def test_soup_ids_and_random_rays():
+@ACCEL
+def test_soup_ids_and_random_rays(accel):
     w, h = 128, 96
     prep = scenes.soup(60000, w, h, spp=1)
-    o, g = scenes.both_backends(prep, w, h)
+    o, g = scenes.both_backends(prep, w, h, flags=accel)
     _check_ids(o, g, prep["sceneData"])
     rng = np.random.default_rng(9)
     n = 50000
@@ -164,6 +172,19 @@ def test_cornell_spectral(sampling):
     o.render(prep["sceneData"], frames=2)
     g.render(prep["sceneData"], frames=2)
     _check_images(o, g, frac=0.99, rel_rmse=0.05)
+
+
+def test_default_accel_choice():
+    """Stacked, non-shared meshes (the 16-mesh soup: overlap depth 16) -> one flat BVH; separated instances (cornell) keep
+    BLAS per geometry + TLAS (vkrt_cuda_build_accel heuristic)."""
+    g = H.CudaBackend()
+    g.upload(scenes.cornell(32, 32))
+    assert g.build_stats.flat == 0
+    g.close()
+    g = H.CudaBackend()
+    g.upload(scenes.soup(20000, 32, 32))
+    assert g.build_stats.flat == 1
+    g.close()
 
 
 def test_dispersive_glass_hero_collapse():

@@ -19,6 +19,8 @@ AOV_ACCUM, AOV_ALBEDO, AOV_NORMAL, AOV_OUTPUT, AOV_HITID_CENTER, AOV_HITID_S0, A
 FLAG_COUNT_RAYS = 1
 FLAG_NO_MATERIAL_SORT = 2
 FLAG_STAGE_TIMING = 4
+FLAG_FORCE_TWO_LEVEL = 8
+FLAG_FORCE_FLAT = 16
 
 VKRT_SUCCESS = 0
 _ERRORS = {0: "SUCCESS", -1: "INVALID_ARGUMENT", -2: "OPERATION_FAILED", -3: "OUT_OF_MEMORY", -4: "DEVICE_LOST",
@@ -39,7 +41,7 @@ class CreateInfo(C.Structure):
 class BuildStats(C.Structure):
     _fields_ = [("buildMs", C.c_float), ("blasMs", C.c_float), ("tlasMs", C.c_float), ("uniqueGeometries", C.c_uint32),
                 ("instanceCount", C.c_uint32), ("triangleCount", C.c_uint64), ("instancedTriangleCount", C.c_uint64),
-                ("bvh8NodeCount", C.c_uint64), ("accelBytes", C.c_uint64)]
+                ("bvh8NodeCount", C.c_uint64), ("accelBytes", C.c_uint64), ("flat", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class FrameStats(C.Structure):

@@ -8,6 +8,9 @@
 //   bvh8Nodes   : compressed 8-wide nodes, 80 B each (Ylitie, Karras, Laine 2017), BLASes first, TLAS last
 //   triangles   : 3 x ::float4 per triangle in leaf order: v0.xyz|prim, v1.xyz|-, v2.xyz|-   (48 B, object space)
 //   instances   : 64 B per TLAS leaf: inverse 3x4 (row-major, 3 x ::float4) + {blasRoot, triBase, flags, instanceIndex}
+// Flat variant (vkrt_cuda_build_accel picks it when instancing does not pay): ONE BVH over the world-space boxes of all
+// instanced triangles; leaves index `flatPrims` {triangle record, instance}; triangles stay in object space and the ray is taken into
+// the instance's space at the triangle test, so hits are bit-identical to the two-level structure.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -52,10 +55,13 @@ struct Lbvh {
 
 struct AccelView {
     const Bvh8Node* nodes;
-    const ::float4* triangles;
-    const InstanceRecord* instances;
-    uint32_t tlasRoot;      // node index of the TLAS root
-    uint32_t instanceCount;
+    const ::float4* triangles;          // two-level: BLAS leaf order; flat: primitive order per unique geometry
+    const InstanceRecord* instances;    // two-level: TLAS leaf order; flat: instance order
+    const ::uint2* flatPrims;           // flat only, leaf order: x = triangle record, y = instance
+    uint32_t tlasRoot;      // node index of the TLAS root (flat: of the single BVH)
+    uint32_t instanceCount; // 0 = nothing to hit
+    uint32_t flat;          // 1 = single-level BVH over instanced triangles
+    uint32_t pad;
 };
 
 } // namespace vk

@@ -24,8 +24,9 @@
 namespace vk {
 void launchRaygen(int mode, const FrameParams& fp, int grid, cudaStream_t st);
 void launchShade(int mode, const FrameParams& fp, uint32_t depth, int grid, cudaStream_t st);
+void launchShadeSort(const FrameParams& fp, uint32_t depth, int smCount, cudaStream_t st);
 void launchFilm(int mode, const FrameParams& fp, int firstChunk, int lastChunk, int grid, cudaStream_t st);
-void launchTrace(const TraceParams& tp, bool count, int grid, cudaStream_t st);
+void launchTrace(const TraceParams& tp, bool count, int grid, cudaStream_t st);  // picks the flat / two-level kernel from tp.scene.accel.flat
 void launchPrimaryRaygen(const FrameParams& fp, int jittered, int grid, cudaStream_t st);
 void launchPrimaryStore(const FrameParams& fp, int grid, cudaStream_t st);
 void launchUntile(const void* src, void* dst, const TileMap& tm, const uint32_t* l2g, uint32_t words, int grid, cudaStream_t st);
@@ -115,6 +116,8 @@ struct vkrt_cuda_ctx {
     DevBuf<Bvh8Node> nodes;
     DevBuf<::float4> triangles;
     DevBuf<InstanceRecord> instanceRecords, instancesLeafOrder;
+    DevBuf<::uint2> flatPrims;
+    bool accelFlat = false;
     DevBuf<::float4> blasBounds;
     DevBuf<uint32_t> instanceBlas;
     uint32_t tlasRoot = 0;
@@ -133,6 +136,7 @@ struct vkrt_cuda_ctx {
     DevBuf<::uint4> hitA;
     DevBuf<::uint2> u2pool[8];
     DevBuf<uint32_t> counters;  // extCount | shCount | traceWork, MAX_DEPTH_SLOTS each
+    DevBuf<uint32_t> shadeOrder, sortBins;
     DevBuf<unsigned long long> stats;
     FrameParams fp = {};
     int readIndex = 0;
@@ -234,6 +238,9 @@ SceneView makeSceneView(vkrt_cuda_ctx* c) {
     v.accel.instances = c->instancesLeafOrder.p;
     v.accel.tlasRoot = c->tlasRoot;
     v.accel.instanceCount = (uint32_t)c->hostMeshInfos.size();
+    v.accel.flatPrims = c->flatPrims.p;
+    v.accel.flat = c->accelFlat ? 1u : 0u;
+    v.accel.pad = 0u;
     return v;
 }
 
@@ -270,6 +277,10 @@ VKRT_Result allocateWavefront(vkrt_cuda_ctx* ctx) {
     if (!ok) return fail(ctx, VKRT_ERROR_OUT_OF_MEMORY, "wavefront allocation failed (capacity %u paths, %u local pixels)", cap, lpc);
     if (ctx->counters.alloc(MAX_DEPTH_SLOTS * 3) != cudaSuccess || ctx->stats.alloc(4) != cudaSuccess)
         return fail(ctx, VKRT_ERROR_OUT_OF_MEMORY, "counter allocation failed");
+    if (ctx->shadeOrder.alloc(cap) != cudaSuccess || ctx->sortBins.alloc(512) != cudaSuccess)
+        return fail(ctx, VKRT_ERROR_OUT_OF_MEMORY, "sort buffer allocation failed");
+    fp.shadeOrder = (ctx->flags & VKRT_CUDA_FLAG_NO_MATERIAL_SORT) ? nullptr : ctx->shadeOrder.p;
+    fp.sortBins = ctx->sortBins.p;
     fp.extCount = ctx->counters.p;
     fp.shCount = ctx->counters.p + MAX_DEPTH_SLOTS;
     fp.traceWork = ctx->counters.p + 2 * MAX_DEPTH_SLOTS;
@@ -378,6 +389,7 @@ VKRT_Result enqueueFrame(vkrt_cuda_ctx* ctx, const SceneData* sceneData, uint32_
         for (uint32_t d = 0; d < sd.rrMaxDepth; d++) {
             launchTrace(makeTraceParams(ctx, d, true, d > 0), count, ctx->traceGrid, st);
             mark(1);
+            if (fp.shadeOrder) { launchShadeSort(fp, d, ctx->smCount, st); nl += 3; }
             launchShade(mode, fp, d, ctx->shadeGrid[mode], st);
             mark(0);
             nl += 2;
@@ -616,6 +628,128 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_build_accel(vkrt_cuda_ctx* ctx, vkrt_cuda_bu
         instancedTris += mi.indexCount / 3u;
     }
     if (totalTris > 0xFFFFFFF0ull) return fail(ctx, VKRT_ERROR_INVALID_ARGUMENT, "too many triangles");
+    // ---- single-level variant: one BVH over all instanced triangles in world space ------------------------------------------------
+    // Instancing (shared BLASes under a TLAS) pays when geometry is reused many times; when it is not — a handful of instances, or many
+    // overlapping meshes like the 16-mesh triangle soup, where a ray enters 9 BLASes — a flat BVH traverses far fewer nodes.
+    // Decision: average overlap depth of the instances' world boxes = sum of box volumes / volume of their union box. Separated
+    // instances (cornell: depth < 1) keep their own well-fitting BLASes — mixing ten wall-sized triangles into one Morton-ordered
+    // tree with 70 k small ones costs 1.7x the node visits; stacked instances (soup: depth 16) are flattened. Flattening is also
+    // limited to scenes where it does not multiply memory (instanced <= 2 x unique triangles, or <= 4 Mi triangles in total).
+    bool flat = false;
+    if (instancedTris > 0 && instancedTris < 0x7FFFFFF0ull && instancedTris <= std::max<uint64_t>(4ull << 20, 2 * totalTris) &&
+        !(ctx->flags & (VKRT_CUDA_FLAG_FORCE_TWO_LEVEL | VKRT_CUDA_FLAG_FORCE_FLAT))) {
+        DevBuf<int> gb;
+        CU(gb.alloc(8 * std::max<size_t>(blas.size(), 1)));
+        for (size_t b = 0; b < blas.size(); b++)
+            launchGeometryBounds(ctx->vertices.p, ctx->indices.p, blas[b].vertexBase, blas[b].indexBase, blas[b].triCount, gb.p + 8 * b, ctx->stream);
+        std::vector<int> hb(8 * blas.size());
+        CU(cudaMemcpyAsync(hb.data(), gb.p, sizeof(int) * hb.size(), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        double ulo[3] = {1e300, 1e300, 1e300}, uhi[3] = {-1e300, -1e300, -1e300};
+        std::vector<double> boxes((size_t)n * 6);
+        for (uint32_t i = 0; i < n; i++) {
+            const int* g = &hb[8 * instanceBlas[i]];
+            float lo[3] = {orderedIntToFloatHost(g[0]), orderedIntToFloatHost(g[1]), orderedIntToFloatHost(g[2])};
+            float hi[3] = {orderedIntToFloatHost(g[3]), orderedIntToFloatHost(g[4]), orderedIntToFloatHost(g[5])};
+            double* bx = &boxes[(size_t)i * 6];
+            for (int a = 0; a < 3; a++) { bx[a] = 1e300; bx[3 + a] = -1e300; }
+            if (lo[0] > hi[0]) continue;
+            const float* m = &ctx->hostWorld[(size_t)i * 12];
+            for (int k = 0; k < 8; k++) {
+                double p[3] = {(k & 1) ? hi[0] : lo[0], (k & 2) ? hi[1] : lo[1], (k & 4) ? hi[2] : lo[2]};
+                for (int a = 0; a < 3; a++) {
+                    double w = m[a * 4] * p[0] + m[a * 4 + 1] * p[1] + m[a * 4 + 2] * p[2] + m[a * 4 + 3];
+                    bx[a] = std::min(bx[a], w);
+                    bx[3 + a] = std::max(bx[3 + a], w);
+                }
+            }
+            for (int a = 0; a < 3; a++) { ulo[a] = std::min(ulo[a], bx[a]); uhi[a] = std::max(uhi[a], bx[3 + a]); }
+        }
+        double diag = 0.0;
+        for (int a = 0; a < 3; a++) diag = std::max(diag, uhi[a] - ulo[a]);
+        const double pad = 1e-3 * diag;  // planes get a sliver of volume, not zero
+        double unionVol = 1.0, sumVol = 0.0;
+        for (int a = 0; a < 3; a++) unionVol *= (uhi[a] - ulo[a]) + 2 * pad;
+        for (uint32_t i = 0; i < n; i++) {
+            const double* bx = &boxes[(size_t)i * 6];
+            if (bx[0] > bx[3]) continue;
+            double v = 1.0;
+            for (int a = 0; a < 3; a++) v *= (bx[3 + a] - bx[a]) + 2 * pad;
+            sumVol += v;
+        }
+        flat = unionVol > 0.0 && sumVol / unionVol > 2.0;
+    }
+    if (ctx->flags & VKRT_CUDA_FLAG_FORCE_TWO_LEVEL) flat = false;
+    if ((ctx->flags & VKRT_CUDA_FLAG_FORCE_FLAT) && instancedTris > 0 && instancedTris < 0x7FFFFFF0ull) flat = true;
+    ctx->accelFlat = flat;
+    if (flat) {
+        cudaStream_t st = ctx->stream;
+        uint32_t pb = 0;
+        for (auto& b : blas) { b.primBase = pb; pb += b.triCount; }
+        std::vector<::uint4> instTable(n);
+        std::vector<uint32_t> triOffsets(n + 1, 0u);
+        std::vector<InstanceRecord> records(n);
+        for (uint32_t i = 0; i < n; i++) {
+            const BlasDesc& d = blas[instanceBlas[i]];
+            instTable[i] = make_uint4(d.vertexBase, d.indexBase, d.primBase, d.triCount);
+            triOffsets[i + 1] = triOffsets[i] + d.triCount;
+            float inv[12];
+            invertAffine3x4(&ctx->hostWorld[(size_t)i * 12], inv);
+            InstanceRecord& r = records[i];
+            r.inv0 = make_float4(inv[0], inv[1], inv[2], inv[3]);
+            r.inv1 = make_float4(inv[4], inv[5], inv[6], inv[7]);
+            r.inv2 = make_float4(inv[8], inv[9], inv[10], inv[11]);
+            r.blasRoot = 0;
+            r.flags = 0;
+            if (ctx->hostAlpha[i]) r.flags |= INSTANCE_FLAG_ALPHA_TESTED;
+            if (ctx->hostMaterials[ctx->hostMeshInfos[i].materialIndex].transmission > 0.0f) r.flags |= INSTANCE_FLAG_TRANSMISSIVE;
+            if (d.triCount == 0) r.flags |= INSTANCE_FLAG_EMPTY;
+            r.instanceIndex = i;
+            r.pad = 0;
+        }
+        const uint32_t total = (uint32_t)instancedTris;
+        DevBuf<::uint4> dInstTable;
+        DevBuf<uint32_t> dTriOffsets;
+        DevBuf<::uint2> flatScratch;
+        DevBuf<Bvh8Node> scratchNodes;
+        CU(dInstTable.upload(instTable.data(), n, st));
+        CU(dTriOffsets.upload(triOffsets.data(), n + 1, st));
+        CU(flatScratch.alloc(total));
+        CU(scratchNodes.alloc(total));
+        CU(ctx->triangles.alloc((size_t)std::max<uint64_t>(totalTris, 1) * 3));
+        CU(ctx->flatPrims.alloc(total));
+        CU(ctx->instanceRecords.upload(records.data(), records.size(), st));
+        CU(ctx->instancesLeafOrder.upload(records.data(), records.size(), st));  // instance order in the flat variant
+        CU(cudaEventRecord(ctx->evA, st));
+        for (const BlasDesc& d : blas) launchPackTriangles(ctx->vertices.p, ctx->indices.p, d.vertexBase, d.indexBase, d.triCount, ctx->triangles.p, d.primBase, st);
+        uint32_t nodeCount = 0, primCount = 0;
+        if (!ctx->builder.buildFlat(st, ctx->vertices.p, ctx->indices.p, dInstTable.p, dTriOffsets.p, n, ctx->world3x4.p, total, flatScratch.p, scratchNodes.p, 0u,
+                                    ctx->flatPrims.p, &nodeCount, &primCount))
+            return fail(ctx, VKRT_ERROR_OPERATION_FAILED, "flat BVH build failed: %s", ctx->builder.err);
+        if (primCount != total) return fail(ctx, VKRT_ERROR_OPERATION_FAILED, "flat BVH emitted %u of %u triangles", primCount, total);
+        CU(ctx->nodes.alloc(std::max(nodeCount, 1u)));
+        launchRelocateNodes(scratchNodes.p, ctx->nodes.p, nodeCount, 0u, 0u, st);
+        CU(cudaEventRecord(ctx->evB, st));
+        CU(cudaStreamSynchronize(st));
+        CU(cudaGetLastError());
+        ctx->tlasRoot = 0;
+        ctx->accelValid = true;
+        vkrt_cuda_build_stats& s = ctx->buildStats;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->evA, ctx->evB);
+        s.blasMs = ms;
+        s.tlasMs = 0.0f;
+        s.buildMs = ms;
+        s.uniqueGeometries = (uint32_t)blas.size();
+        s.instanceCount = n;
+        s.triangleCount = totalTris;
+        s.instancedTriangleCount = instancedTris;
+        s.bvh8NodeCount = nodeCount;
+        s.accelBytes = (uint64_t)nodeCount * sizeof(Bvh8Node) + totalTris * 48ull + instancedTris * 8ull + (uint64_t)n * sizeof(InstanceRecord);
+        s.flat = 1;
+        if (outStats) *outStats = s;
+        return VKRT_SUCCESS;
+    }
     // worst-case node budget: one 8-wide node per binary internal node; trimmed after the build
     uint64_t nodeBudget = 0;
     for (auto& b : blas) { b.nodeBase = (uint32_t)nodeBudget; nodeBudget += std::max(b.triCount, 1u); }
@@ -709,6 +843,7 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_build_accel(vkrt_cuda_ctx* ctx, vkrt_cuda_bu
     s.instancedTriangleCount = instancedTris;
     s.bvh8NodeCount = finalNodes + tlasNodes;
     s.accelBytes = s.bvh8NodeCount * sizeof(Bvh8Node) + totalTris * 48ull + (uint64_t)n * sizeof(InstanceRecord);
+    s.flat = 0;
     if (outStats) *outStats = s;
     return VKRT_SUCCESS;
 }

@@ -18,8 +18,16 @@ struct BuildTarget {
     uint32_t primBase = 0;
     const InstanceRecord* instanceRecords = nullptr;
     InstanceRecord* instancesOut = nullptr;
+    const uint2* flatIn = nullptr;
+    const uint4* flatInstances = nullptr;
+    uint2* flatOut = nullptr;
 };
 
+void launchPackTriangles(const ShaderVertex* vertices, const uint32_t* indices, uint32_t vertexBase, uint32_t indexBase, uint32_t triCount,
+                         ::float4* trianglesOut, uint32_t primBase, cudaStream_t st);
+void launchGeometryBounds(const ShaderVertex* vertices, const uint32_t* indices, uint32_t vertexBase, uint32_t indexBase, uint32_t triCount, int* bounds6,
+                          cudaStream_t st);
+float orderedIntToFloatHost(int i);
 void launchRelocateNodes(const Bvh8Node* src, Bvh8Node* dst, uint32_t count, uint32_t oldBase, uint32_t newBase, cudaStream_t st);
 
 // Scratch memory + launch sequence for one BVH build at a time (reused across BLASes and the TLAS).
@@ -35,6 +43,9 @@ public:
     bool buildTlas(cudaStream_t st, const ::float4* blasBounds, const uint32_t* instanceBlas, const float* world3x4,
                    const InstanceRecord* records, uint32_t instanceCount, Bvh8Node* nodesOut, uint32_t nodeBase,
                    InstanceRecord* instancesOut, uint32_t* outNodeCount, uint32_t* outPrimCount);
+    bool buildFlat(cudaStream_t st, const ShaderVertex* vertices, const uint32_t* indices, const uint4* flatInstances, const uint32_t* triOffsets,
+                   uint32_t instanceCount, const float* world3x4, uint32_t totalPrims, uint2* flatScratch, Bvh8Node* nodesOut, uint32_t nodeBase,
+                   uint2* flatOut, uint32_t* outNodeCount, uint32_t* outPrimCount);
     char err[512] = {0};
 
 private:

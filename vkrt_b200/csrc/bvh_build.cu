@@ -13,6 +13,7 @@
 // (DESIGN.md "Build" gives the algorithmic bytes per triangle).
 #include <cfloat>
 #include <cstdio>
+#include <cstring>
 #include <vector>
 
 #include "accel.cuh"
@@ -121,6 +122,94 @@ __global__ void k_instance_bounds(const ::float4* __restrict__ blasBounds, const
         primHi[i] = make_float4(hi.x, hi.y, hi.z, 0.0f);
     }
     reduceBounds(lo, hi, valid, bounds);
+}
+
+// Object-space AABB of one geometry (ordered-int atomics into bounds6), for the flat / two-level decision.
+__global__ void k_geometry_bounds(const ShaderVertex* __restrict__ vertices, const uint32_t* __restrict__ indices, uint32_t vertexBase, uint32_t indexBase,
+                                  uint32_t triCount, int* bounds6) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = t < triCount;
+    float3 lo(FLT_MAX), hi(-FLT_MAX);
+    if (valid) {
+        for (int k = 0; k < 3; k++) {
+            uint32_t vi = indices[indexBase + t * 3u + k] + vertexBase;
+            ::float4 p = *reinterpret_cast<const ::float4*>(vertices[vi].position);
+            float3 v(p.x, p.y, p.z);
+            lo = min(lo, v);
+            hi = max(hi, v);
+        }
+    }
+    reduceBounds(lo, hi, valid, bounds6);
+}
+void launchGeometryBounds(const ShaderVertex* vertices, const uint32_t* indices, uint32_t vertexBase, uint32_t indexBase, uint32_t triCount, int* bounds6,
+                          cudaStream_t st) {
+    k_init_bounds<<<1, 32, 0, st>>>(bounds6);
+    if (triCount) k_geometry_bounds<<<(triCount + 255) / 256, 256, 0, st>>>(vertices, indices, vertexBase, indexBase, triCount, bounds6);
+}
+float orderedIntToFloatHost(int i) {
+    int b = i >= 0 ? i : i ^ 0x7fffffff;
+    float f;
+    memcpy(&f, &b, 4);
+    return f;
+}
+
+// ---- flat (single-level) build inputs ----------------------------------------------------------------------------------
+// Enumerates every (instance, local triangle) pair: triOffsets is the exclusive prefix sum of the instances' triangle counts.
+__global__ void k_flat_enumerate(const uint32_t* __restrict__ triOffsets, uint32_t instanceCount, uint32_t total, uint2* __restrict__ out) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= total) return;
+    uint32_t lo = 0, hi = instanceCount;  // last instance whose offset <= p
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (triOffsets[mid] <= p) lo = mid; else hi = mid;
+    }
+    out[p] = make_uint2(lo, p - triOffsets[lo]);
+}
+// World-space AABB of an instanced triangle: the three vertices through the instance's 3x4 world transform, padded twice (once for
+// the watertight test's own rounding, once for the rounding of these transforms; the hit itself is computed in object space).
+__global__ void k_flat_bounds(const ShaderVertex* __restrict__ vertices, const uint32_t* __restrict__ indices, const uint2* __restrict__ flatIn,
+                              const uint4* __restrict__ flatInstances, const float* __restrict__ world3x4, uint32_t total,
+                              ::float4* __restrict__ primLo, ::float4* __restrict__ primHi, int* bounds) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = p < total;
+    float3 lo(FLT_MAX), hi(-FLT_MAX);
+    if (valid) {
+        const uint2 fp = flatIn[p];
+        const uint4 inst = flatInstances[fp.x];
+        const float* m = world3x4 + (size_t)fp.x * 12;
+        for (int k = 0; k < 3; k++) {
+            uint32_t vi = indices[inst.y + fp.y * 3u + k] + inst.x;
+            ::float4 q = *reinterpret_cast<const ::float4*>(vertices[vi].position);
+            float3 w(m[0] * q.x + m[1] * q.y + m[2] * q.z + m[3], m[4] * q.x + m[5] * q.y + m[6] * q.z + m[7], m[8] * q.x + m[9] * q.y + m[10] * q.z + m[11]);
+            lo = min(lo, w);
+            hi = max(hi, w);
+        }
+        padBox(lo, hi);
+        padBox(lo, hi);
+        primLo[p] = make_float4(lo.x, lo.y, lo.z, 0.0f);
+        primHi[p] = make_float4(hi.x, hi.y, hi.z, 0.0f);
+    }
+    reduceBounds(lo, hi, valid, bounds);
+}
+// Object-space triangle records of one unique geometry in primitive order (a.w = primitive index), shared by all of its instances.
+__global__ void k_pack_triangles(const ShaderVertex* __restrict__ vertices, const uint32_t* __restrict__ indices, uint32_t vertexBase, uint32_t indexBase,
+                                 uint32_t triCount, ::float4* __restrict__ trianglesOut, uint32_t primBase) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= triCount) return;
+    ::float4 v[3];
+    for (int k = 0; k < 3; k++) {
+        uint32_t vi = indices[indexBase + t * 3u + k] + vertexBase;
+        v[k] = *reinterpret_cast<const ::float4*>(vertices[vi].position);
+    }
+    v[0].w = __uint_as_float(t);
+    v[1].w = 0.0f;
+    v[2].w = 0.0f;
+    const size_t o = (size_t)(primBase + t) * 3;
+    trianglesOut[o] = v[0]; trianglesOut[o + 1] = v[1]; trianglesOut[o + 2] = v[2];
+}
+void launchPackTriangles(const ShaderVertex* vertices, const uint32_t* indices, uint32_t vertexBase, uint32_t indexBase, uint32_t triCount,
+                         ::float4* trianglesOut, uint32_t primBase, cudaStream_t st) {
+    if (triCount) k_pack_triangles<<<(triCount + 255) / 256, 256, 0, st>>>(vertices, indices, vertexBase, indexBase, triCount, trianglesOut, primBase);
 }
 
 // ---- Morton codes ----------------------------------------------------------------------------------------------------
@@ -392,6 +481,10 @@ struct CollapseParams {
     // instance emission
     const InstanceRecord* instanceRecords;  // by instance index
     InstanceRecord* instancesOut;           // in TLAS leaf order
+    // flat (single-level) emission: primitive p = (instance, local triangle) -> {object-space triangle record, instance}
+    const uint2* flatIn;
+    const uint4* flatInstances;             // per instance: vertexBase, indexBase, first triangle record, triangle count
+    uint2* flatOut;                         // in leaf order
 };
 
 __device__ __forceinline__ float boxHalfArea(::float4 lo, ::float4 hi) {
@@ -537,7 +630,10 @@ __global__ void __launch_bounds__(64) k_collapse(CollapseParams P, const uint2* 
             for (uint32_t q = 0; q < cnt; q++) {
                 uint32_t prim = P.sortedVals[first + q];
                 uint32_t outIndex = P.primBase + primBaseLocal + primOffset + q;
-                if (P.trianglesOut) {
+                if (P.flatOut) {
+                    const uint2 fp = P.flatIn[prim];  // x = instance, y = local triangle
+                    P.flatOut[outIndex] = make_uint2(P.flatInstances[fp.x].z + fp.y, fp.x);
+                } else if (P.trianglesOut) {
                     ::float4 v[3];
                     for (int kk = 0; kk < 3; kk++) {
                         uint32_t vi = P.indices[P.indexBase + prim * 3u + kk] + P.vertexBase;
@@ -653,6 +749,7 @@ bool AccelBuilder::buildFromBoxes(cudaStream_t st, uint32_t n, const BuildTarget
     P.vertices = tgt.vertices; P.indices = tgt.indices; P.vertexBase = tgt.vertexBase; P.indexBase = tgt.indexBase;
     P.trianglesOut = tgt.trianglesOut; P.primBase = tgt.primBase;
     P.instanceRecords = tgt.instanceRecords; P.instancesOut = tgt.instancesOut;
+    P.flatIn = tgt.flatIn; P.flatInstances = tgt.flatInstances; P.flatOut = tgt.flatOut;
     uint32_t initCounters[4] = {0u, 1u, 0u, 0u};  // node 0 (root) is pre-allocated
     CK(cudaMemcpyAsync(counters, initCounters, sizeof(initCounters), cudaMemcpyHostToDevice, st));
     uint2 rootWork = make_uint2(0u, 0u);  // bvh2 node 0 (for n == 1 that is the single leaf) -> local bvh8 node 0
@@ -700,6 +797,22 @@ bool AccelBuilder::buildTlas(cudaStream_t st, const ::float4* blasBounds, const 
     BuildTarget tgt = {};
     tgt.nodesOut = nodesOut; tgt.nodeBase = nodeBase; tgt.instanceRecords = records; tgt.instancesOut = instancesOut;
     return buildFromBoxes(st, instanceCount, tgt, outNodeCount, outPrimCount);
+}
+
+// Single-level BVH over every instanced triangle in world space (used when instancing does not pay: few or heavily overlapping
+// instances). flatScratch must hold totalPrims uint2 entries.
+bool AccelBuilder::buildFlat(cudaStream_t st, const ShaderVertex* vertices, const uint32_t* indices, const uint4* flatInstances,
+                             const uint32_t* triOffsets, uint32_t instanceCount, const float* world3x4, uint32_t totalPrims, uint2* flatScratch,
+                             Bvh8Node* nodesOut, uint32_t nodeBase, uint2* flatOut, uint32_t* outNodeCount, uint32_t* outPrimCount) {
+    if (!reserve(totalPrims)) return false;
+    const uint32_t grid = (totalPrims + 255) / 256;
+    k_flat_enumerate<<<grid, 256, 0, st>>>(triOffsets, instanceCount, totalPrims, flatScratch);
+    k_init_bounds<<<1, 32, 0, st>>>(bounds);
+    k_flat_bounds<<<grid, 256, 0, st>>>(vertices, indices, flatScratch, flatInstances, world3x4, totalPrims, primLo, primHi, bounds);
+    BuildTarget tgt = {};
+    tgt.nodesOut = nodesOut; tgt.nodeBase = nodeBase;
+    tgt.flatIn = flatScratch; tgt.flatInstances = flatInstances; tgt.flatOut = flatOut;
+    return buildFromBoxes(st, totalPrims, tgt, outNodeCount, outPrimCount);
 }
 
 } // namespace vk

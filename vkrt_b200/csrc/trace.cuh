@@ -103,7 +103,7 @@ struct LaneRay {
     bool anyHit, sawTransmissive, active;
 };
 
-template <bool COUNT>
+template <bool COUNT, bool FLAT>
 __global__ void __launch_bounds__(TRACE_BLOCK) k_trace(const TraceParams P) {
     const int lane = threadIdx.x & 31;
     const uint32_t extCount = P.extCount ? *P.extCount : 0u;
@@ -122,6 +122,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_trace(const TraceParams P) {
     int blasBase = 0;
     uint32_t curInst = 0, curFlags = 0;
     RayShear shear;
+    float3 objO(0.0f);  // flat variant: ray origin in the cached instance's object space
     uint2 G = make_uint2(0u, 0u), Gt = make_uint2(0u, 0u);  // pending node group / pending primitive group of this lane
     bool exhausted = false;
     unsigned long long nNodes = 0, nTris = 0, nInst = 0;
@@ -156,6 +157,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_trace(const TraceParams P) {
                         idir = safeInvDir(d);
                         octinv = 7u ^ ((d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u));
                         inBlas = false;
+                        if (FLAT) curInst = VKRT_INVALID_INDEX;  // no object-space ray cached yet
                         sp = 0;
                         G = make_uint2(A.tlasRoot, 0x80000000u);
                         Gt = make_uint2(0u, 0u);
@@ -196,7 +198,67 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_trace(const TraceParams P) {
                 const int i = __ffs(Gt.y) - 1;
                 Gt.y &= Gt.y - 1u;
                 const uint32_t primIndex = Gt.x + (uint32_t)i;
-                if (!inBlas) {
+                if (FLAT) {
+                    // ---- single-level BVH: the leaf entry names {triangle record, instance}; the triangle stays in object space and the
+                    // ray is taken into the instance's space (cached per lane until the instance changes) -> same arithmetic, same bits
+                    // as the two-level structure.
+                    const ::uint2 fp = __ldg(A.flatPrims + primIndex);
+                    bool testable = true;
+                    if (fp.y != curInst) {
+                        const InstanceRecord* rec = A.instances + fp.y;
+                        const ::uint4 meta = __ldg(reinterpret_cast<const ::uint4*>(rec) + 3);
+                        const ::float4 r0 = __ldg(reinterpret_cast<const ::float4*>(rec));
+                        const ::float4 r1 = __ldg(reinterpret_cast<const ::float4*>(rec) + 1);
+                        const ::float4 r2 = __ldg(reinterpret_cast<const ::float4*>(rec) + 2);
+                        const float4 i0(r0.x, r0.y, r0.z, r0.w), i1(r1.x, r1.y, r1.z, r1.w), i2(r2.x, r2.y, r2.z, r2.w);
+                        objO = xformPoint(i0, i1, i2, R.o);
+                        const float3 od = xformVector(i0, i1, i2, R.d);
+                        curFlags = meta.y;
+                        if (makeRayShear(od, shear)) {
+                            curInst = fp.y;
+                            if (COUNT) nInst++;
+                        } else {
+                            curInst = VKRT_INVALID_INDEX;
+                            testable = false;
+                        }
+                    }
+                    if (testable && R.anyHit && R.sawTransmissive && (curFlags & INSTANCE_FLAG_TRANSMISSIVE)) testable = false;
+                    if (testable) {
+                        const ::float4* tri = A.triangles + (size_t)fp.x * 3;
+                        const ::float4 a = __ldg(tri), b = __ldg(tri + 1), c = __ldg(tri + 2);
+                        if (COUNT) nTris++;
+                        float t, u, v;
+                        bool accept = watertightTriangle(objO, shear, float3(a.x, a.y, a.z), float3(b.x, b.y, b.z), float3(c.x, c.y, c.z), t, u, v) && t > R.tMin;
+                        const uint32_t prim = __float_as_uint(a.w);
+                        if (accept) {
+                            bool closer = t < R.tBest;
+                            if (!closer && t == R.tBest && R.hitInst != VKRT_INVALID_INDEX)
+                                closer = curInst < R.hitInst || (curInst == R.hitInst && prim < R.hitPrim);
+                            accept = closer;
+                        }
+                        if (accept && (curFlags & INSTANCE_FLAG_ALPHA_TESTED)) {
+                            const uint32_t seed = R.anyHit ? __ldg(P.shSeed + (R.index - extCount)) : (P.raySeed ? __ldg(P.raySeed + R.index) : 0u);
+                            accept = alphaHitAccepted(P.scene, curInst, prim, float2(u, v), seed);
+                        }
+                        if (accept) {
+                            if (!R.anyHit) {
+                                R.hitInst = curInst;
+                                R.hitPrim = prim;
+                                R.tBest = t;
+                                R.hitU = u;
+                                R.hitV = v;
+                            } else if (curFlags & INSTANCE_FLAG_TRANSMISSIVE) {
+                                R.sawTransmissive = true;   // keep looking for an opaque occluder; triangles of transmissive instances are skipped from now on
+                            } else {
+                                R.hitInst = curInst;        // occluded: done
+                                R.hitPrim = prim;
+                                sp = 0;
+                                G = make_uint2(0u, 0u);
+                                Gt.y = 0u;
+                            }
+                        }
+                    }
+                } else if (!inBlas) {
                     // TLAS leaf = instance: park the remaining TLAS work and descend into the BLAS
                     if (Gt.y) { if (sp < TRACE_STACK) stack[sp++] = Gt; }
                     if (G.y & 0xff000000u) { if (sp < TRACE_STACK) stack[sp++] = G; }

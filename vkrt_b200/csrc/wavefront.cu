@@ -306,9 +306,12 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const F
     const bool neeEnabled = (fp.modeFlags & MODE_NEE_ENABLED) && !(fp.modeFlags & MODE_BSDF_ONLY);
     const bool neeOnly = (fp.modeFlags & MODE_NEE_ONLY) != 0u;
 
+    const uint32_t* __restrict__ order = fp.shadeOrder;
+
     for (uint32_t base = blockIdx.x * blockDim.x; base < count; base += gridDim.x * blockDim.x) {
-        const uint32_t i = base + threadIdx.x;
-        bool live = i < count;
+        const uint32_t j = base + threadIdx.x;
+        bool live = j < count;
+        const uint32_t i = (live && order) ? __ldg(order + j) : j;   // material-sorted order: neighbouring lanes shade the same closure
 
         // ================================ phase 1: unpack, miss, surface, material, closure state ================================
         Ray ray;
@@ -322,10 +325,9 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const F
         MeshInfo mesh;
         float3 hitPoint(0.0f);
         SurfaceShadingData surface;
-        Material material;
         ShadingBasis basis;
-        BSDFMaterial bm;
-        BSDFState state;
+        BSDFState state;           // holds the only copy of the closure parameters that outlives phase 1 (state.material)
+        float3 emission(0.0f);     // textured, per-hit emission (integrator.slang:79-85)
         bool currentVertexNeeAllowed = false;
 
         if (live) {
@@ -421,7 +423,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const F
                 trig.sx = t0.x; trig.cx = t0.y; trig.sy = t0.z; trig.cy = t0.w; trig.sz = t1.x; trig.cz = t1.y; trig.pad0 = trig.pad1 = 0.0f;
             }
             surface = reconstructSurfaceShading(sc, mesh, trig, hitPrim, float2(hitU, fp.hitB[i]), ray.direction);
-            material = loadMaterial(sc.materials + surface.materialIndex);
+            Material material = loadMaterial(sc.materials + surface.materialIndex);
             {
                 const ShadingBasis unperturbed = makeShadingBasis(surface.shadingNormal, surface.tangent);
                 surface.shadingNormal = applyNormalTexture(sc, material, surface.textureData, unperturbed);
@@ -429,7 +431,8 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const F
             surface.shadingNormal = sanitizeShadingNormal(surface.shadingNormal, surface.geometricNormal, -ray.direction);
             basis = makeShadingBasis(surface.shadingNormal, surface.tangent);
             applySurfaceTextures(sc, material, surface.textureData);
-            bm = BSDFMaterial(material);
+            emission = float3(material.emissionColor[0], material.emissionColor[1], material.emissionColor[2]) * material.emissionLuminance;
+            state.material = BSDFMaterial(material);
 
             // ---- primary-surface debug views (integrator/path/debug.slang:31-64) -----------------------------------------
             if (sampleIndex == 0u && depth == 0u && scene.debugMode != VKRT_DEBUG_MODE_NONE) {
@@ -452,6 +455,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const F
         }
         SHADE_SUBPHASE_BARRIER();
         if (live) {
+            const BSDFMaterial bm = state.material;
             // ---- denoiser features (loop.slang:83-103) ----------------------------------------------------------------
             const bool follow = materialDenoiserShouldFollowSpecularHit(bm, surface.frontFace);
             if (depth == 0u) fp.rec.follow[rec] = follow ? 1.0f : 0.0f;
@@ -528,7 +532,6 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const F
         if (live) {
             // ---- emission seen by BSDF sampling (integrator.slang:79-85; hero: integrator.slang:98-126) -------------------
             if (!neeOnly) {
-                const float3 emission = float3(material.emissionColor[0], material.emissionColor[1], material.emissionColor[2]) * material.emissionLuminance;
                 if (anyGreater(emission, 0.0f)) {
                     const bool misActive = (fp.modeFlags & MODE_NEE_ENABLED) && (flags & PF_PREV_VERTEX_NEE_ALLOWED) && depth > 0u;
                     if (MODE == MODE_HERO && heroActive) {
@@ -577,7 +580,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const F
                     if (!anyGreater(thr4, 0.0f)) pathContinues = false;
                 }
                 if (pathContinues) {
-                    if (smp.isTransmission != 0u && materialMediumIsRefractive(bm) && bm.abbeNumber > 0.0f) {
+                    if (smp.isTransmission != 0u && materialMediumIsRefractive(state.material) && state.material.abbeNumber > 0.0f) {
                         // dispersive collapse (spectral_hero/transport.slang:77-87). The 4-lane radiance stays in the record and
                         // is converted to XYZ by the film kernel together with the scalar lane.
                         thrScalar = thr4.x;
@@ -612,9 +615,9 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const F
         if (live) {
             if (pathContinues) {
                 // medium update + NEE bookkeeping (integrator.slang:96-98)
-                if (MODE == MODE_RGB) updateMediumStateFromTransmission(T, bm, surface.frontFace, isTransmission, 0.0f, 0u, medium);
-                else if (MODE == MODE_HERO && heroActive) updateMediumStateFromTransmissionSpectral(T, bm, surface.frontFace, isTransmission, wl4, medium);
-                else updateMediumStateFromTransmission(T, bm, surface.frontFace, isTransmission, lambdaScalar, 1u, medium);
+                if (MODE == MODE_RGB) updateMediumStateFromTransmission(T, state.material, surface.frontFace, isTransmission, 0.0f, 0u, medium);
+                else if (MODE == MODE_HERO && heroActive) updateMediumStateFromTransmissionSpectral(T, state.material, surface.frontFace, isTransmission, wl4, medium);
+                else updateMediumStateFromTransmission(T, state.material, surface.frontFace, isTransmission, lambdaScalar, 1u, medium);
                 const bool sampledPathNeeAllowed = currentVertexNeeAllowed && isTransmission == 0u;  // shadow kernel clears it on "unsupported"
                 flags = (flags & ~(PF_PREV_VERTEX_NEE_ALLOWED | PF_MEDIUM_REFRACTIVE | PF_MEDIUM_ABSORPTION)) |
                         (sampledPathNeeAllowed ? PF_PREV_VERTEX_NEE_ALLOWED : 0u) | (medium.flags << 1);
@@ -674,6 +677,72 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const F
             }
         }
     }
+}
+
+// ----------------------------------------------------------------------------------------------------------------------
+// Material sort of one depth's queue: a 256-bin counting sort on key = 0 (miss) | 1 + materialIndex. Three small kernels
+// (count, scan, scatter); block-local histograms in shared memory keep the global atomics to one per bin per block.
+// ----------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t shadeSortKey(const FrameParams& fp, uint32_t i) {
+    const uint32_t inst = fp.hitA[i].x;
+    if (inst == VKRT_INVALID_INDEX) return 0u;
+    const uint32_t m = __ldg(&fp.scene.meshInfos[inst].materialIndex) + 1u;
+    return m > 255u ? 255u : m;
+}
+__global__ void __launch_bounds__(256) k_sort_count(const FrameParams fp, const uint32_t depth) {
+    __shared__ uint32_t hist[256];
+    hist[threadIdx.x] = 0u;
+    __syncthreads();
+    const uint32_t count = fp.extCount[depth];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) atomicAdd(&hist[shadeSortKey(fp, i)], 1u);
+    __syncthreads();
+    if (hist[threadIdx.x]) atomicAdd(&fp.sortBins[threadIdx.x], hist[threadIdx.x]);
+}
+__global__ void __launch_bounds__(256) k_sort_scan(const FrameParams fp) {
+    __shared__ uint32_t s[256];
+    const uint32_t c = fp.sortBins[threadIdx.x];
+    s[threadIdx.x] = c;
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {
+        uint32_t v = threadIdx.x >= (uint32_t)o ? s[threadIdx.x - o] : 0u;
+        __syncthreads();
+        s[threadIdx.x] += v;
+        __syncthreads();
+    }
+    fp.sortBins[threadIdx.x] = s[threadIdx.x] - c;  // exclusive start
+    fp.sortBins[256 + threadIdx.x] = 0u;            // cursor
+}
+__global__ void __launch_bounds__(256) k_sort_scatter(const FrameParams fp, const uint32_t depth) {
+    __shared__ uint32_t hist[256], base[256];
+    const uint32_t count = fp.extCount[depth];
+    // every block handles contiguous chunks of 256 * ITEMS entries so that one reservation per bin covers a whole chunk
+    constexpr uint32_t ITEMS = 8;
+    for (uint32_t chunk = blockIdx.x * 256u * ITEMS; chunk < count; chunk += gridDim.x * 256u * ITEMS) {
+        hist[threadIdx.x] = 0u;
+        __syncthreads();
+        uint32_t key[ITEMS], rank[ITEMS];
+#pragma unroll
+        for (uint32_t k = 0; k < ITEMS; k++) {
+            const uint32_t i = chunk + k * 256u + threadIdx.x;
+            key[k] = i < count ? shadeSortKey(fp, i) : 0xffffffffu;
+            if (i < count) rank[k] = atomicAdd(&hist[key[k]], 1u);
+        }
+        __syncthreads();
+        if (hist[threadIdx.x]) base[threadIdx.x] = fp.sortBins[threadIdx.x] + atomicAdd(&fp.sortBins[256 + threadIdx.x], hist[threadIdx.x]);
+        __syncthreads();
+#pragma unroll
+        for (uint32_t k = 0; k < ITEMS; k++) {
+            const uint32_t i = chunk + k * 256u + threadIdx.x;
+            if (i < count) fp.shadeOrder[base[key[k]] + rank[k]] = i;
+        }
+        __syncthreads();
+    }
+}
+void launchShadeSort(const FrameParams& fp, uint32_t depth, int smCount, cudaStream_t st) {
+    cudaMemsetAsync(fp.sortBins, 0, sizeof(uint32_t) * 512, st);
+    k_sort_count<<<smCount * 8, 256, 0, st>>>(fp, depth);
+    k_sort_scan<<<1, 256, 0, st>>>(fp);
+    k_sort_scatter<<<smCount * 8, 256, 0, st>>>(fp, depth);
 }
 
 // ----------------------------------------------------------------------------------------------------------------------
@@ -877,8 +946,9 @@ void launchMeshTrig(const MeshInfo* infos, MeshTrig* out, uint32_t count, cudaSt
 
 int traceBlocksPerSm(bool count) {
     int n = 0;
-    if (count) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace<true>, TRACE_BLOCK, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace<false>, TRACE_BLOCK, 0);
+    // the two-level variant has the larger register footprint; one grid size serves both
+    if (count) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace<true, false>, TRACE_BLOCK, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace<false, false>, TRACE_BLOCK, 0);
     return n > 0 ? n : 1;
 }
 int shadeBlocksPerSm(int mode) {
@@ -906,8 +976,9 @@ void launchFilm(int mode, const FrameParams& fp, int firstChunk, int lastChunk, 
     else k_film<MODE_HERO><<<grid, 256, 0, st>>>(fp, firstChunk, lastChunk);
 }
 void launchTrace(const TraceParams& tp, bool count, int grid, cudaStream_t st) {
-    if (count) k_trace<true><<<grid, TRACE_BLOCK, 0, st>>>(tp);
-    else k_trace<false><<<grid, TRACE_BLOCK, 0, st>>>(tp);
+    const bool flat = tp.scene.accel.flat != 0u;
+    if (count) { if (flat) k_trace<true, true><<<grid, TRACE_BLOCK, 0, st>>>(tp); else k_trace<true, false><<<grid, TRACE_BLOCK, 0, st>>>(tp); }
+    else { if (flat) k_trace<false, true><<<grid, TRACE_BLOCK, 0, st>>>(tp); else k_trace<false, false><<<grid, TRACE_BLOCK, 0, st>>>(tp); }
 }
 void launchPrimaryRaygen(const FrameParams& fp, int jittered, int grid, cudaStream_t st) { k_primary_raygen<<<grid, 256, 0, st>>>(fp, jittered); }
 void launchPrimaryStore(const FrameParams& fp, int grid, cudaStream_t st) { k_primary_store<<<grid, 256, 0, st>>>(fp); }

@@ -93,6 +93,10 @@ struct FrameParams {
     uint32_t* extCount;
     uint32_t* shCount;
     uint32_t* traceWork;
+    // material-sorted shading order (north_star: "sorted-by-material shading kernels"): order[j] = queue slot, grouped by
+    // key = 0 for a miss, 1 + materialIndex (clamped to 255) for a hit; nullptr = shade in queue order
+    uint32_t* shadeOrder;
+    uint32_t* sortBins;       // [0..255] counts -> starts, [256..511] cursors
     SampleRecords rec;
     Film film;
     int readIndex;            // accumulation read image
