@@ -48,10 +48,15 @@ struct TraceParams {
     unsigned long long* stats;   // optional: [0] nodes visited, [1] triangles tested, [2] instances entered
 };
 
-__device__ __forceinline__ uint32_t extractByte(uint32_t v, int i) { return (v >> (i * 8)) & 0xffu; }
+// byte j of v as an exact fp32 value without the conversion pipe: PRMT builds 0x4B0000bb = 2^23 + b, one FADD removes the 2^23
+__device__ __forceinline__ float byteToFloat(uint32_t v, uint32_t j) {
+    return __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7440u | j)) - 8388608.0f;
+}
 
 // Intersects the 8 children of one compressed node; returns the hit mask: bits 24..31 = internal children ordered by
-// (slot ^ octinv) (nearest = highest bit), bits 0..23 = primitives of the leaf children.
+// (slot ^ octinv) (nearest = highest bit), bits 0..23 = primitives of the leaf children. Branch-free: the meta byte of a child
+// encodes {count bits << 5 | bit position} for both kinds (internal children: 1 << 5 | 24 + slot), so one shift places the bits;
+// internal positions are re-ordered by XOR with octinv; empty slots (meta 0) contribute nothing.
 __device__ __forceinline__ uint32_t intersectNode8(const Bvh8Node* __restrict__ node, const float3& o, const float3& idir, uint32_t octinv,
                                                    float tMin, float tMax, uint32_t& childBase, uint32_t& primBase, uint32_t& imask) {
     const ::float4* q = reinterpret_cast<const ::float4*>(node);
@@ -65,6 +70,8 @@ __device__ __forceinline__ uint32_t intersectNode8(const Bvh8Node* __restrict__ 
     const float az = __uint_as_float(((ebits >> 16) & 0xffu) << 23) * idir.z;
     const float bx = (n0.x - o.x) * idir.x, by = (n0.y - o.y) * idir.y, bz = (n0.z - o.z) * idir.z;
     const bool negx = idir.x < 0.0f, negy = idir.y < 0.0f, negz = idir.z < 0.0f;
+    const float tMinS = tMin, tMaxS = tMax;
+    const uint32_t octinv4 = octinv * 0x01010101u;
     uint32_t hitmask = 0;
 #pragma unroll
     for (int half = 0; half < 2; half++) {
@@ -72,23 +79,24 @@ __device__ __forceinline__ uint32_t intersectNode8(const Bvh8Node* __restrict__ 
         const uint32_t lox4 = __float_as_uint(half ? n2.y : n2.x), loy4 = __float_as_uint(half ? n2.w : n2.z);
         const uint32_t loz4 = __float_as_uint(half ? n3.y : n3.x), hix4 = __float_as_uint(half ? n3.w : n3.z);
         const uint32_t hiy4 = __float_as_uint(half ? n4.y : n4.x), hiz4 = __float_as_uint(half ? n4.w : n4.z);
+        // four children at a time (Ylitie et al. 2017, listing 1): internal children have bits 3 and 4 of their position set
+        const uint32_t isInner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+        const uint32_t innerMask4 = (isInner4 >> 4) * 0xffu;  // 0x10 -> 0xff per byte (no carries between bytes)
+        const uint32_t bitIndex4 = (meta4 ^ (octinv4 & innerMask4)) & 0x1f1f1f1fu;
+        const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u;
         const uint32_t nx4 = negx ? hix4 : lox4, fx4 = negx ? lox4 : hix4;
         const uint32_t ny4 = negy ? hiy4 : loy4, fy4 = negy ? loy4 : hiy4;
         const uint32_t nz4 = negz ? hiz4 : loz4, fz4 = negz ? loz4 : hiz4;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            const uint32_t meta = extractByte(meta4, j);
-            if (meta == 0u) continue;
-            const float tnx = fmaf(float(extractByte(nx4, j)), ax, bx), tfx = fmaf(float(extractByte(fx4, j)), ax, bx);
-            const float tny = fmaf(float(extractByte(ny4, j)), ay, by), tfy = fmaf(float(extractByte(fy4, j)), ay, by);
-            const float tnz = fmaf(float(extractByte(nz4, j)), az, bz), tfz = fmaf(float(extractByte(fz4, j)), az, bz);
-            const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tMin));
-            const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tMax));
-            if (tn * 0.999999f <= tf * 1.000001f) {
-                const int slot = half * 4 + j;
-                if (imask & (1u << slot)) hitmask |= 1u << (24 + (slot ^ octinv));
-                else hitmask |= ((meta >> 5) & 7u) << (meta & 31u);
-            }
+            const float tnx = fmaf(byteToFloat(nx4, j), ax, bx), tfx = fmaf(byteToFloat(fx4, j), ax, bx);
+            const float tny = fmaf(byteToFloat(ny4, j), ay, by), tfy = fmaf(byteToFloat(fy4, j), ay, by);
+            const float tnz = fmaf(byteToFloat(nz4, j), az, bz), tfz = fmaf(byteToFloat(fz4, j), az, bz);
+            const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tMinS));
+            const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tMaxS));
+            const bool hit = tn * 0.999999f <= tf * 1.000001f;
+            const uint32_t bits = ((childBits4 >> (j * 8)) & 0xffu) << ((bitIndex4 >> (j * 8)) & 0xffu);
+            hitmask |= hit ? bits : 0u;
         }
     }
     return hitmask;
