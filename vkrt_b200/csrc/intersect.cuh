@@ -78,8 +78,10 @@ __device__ __forceinline__ float3 xformVector(const float4& r0, const float4& r1
                   __fadd_rn(__fadd_rn(__fmul_rn(r2.x, v.x), __fmul_rn(r2.y, v.y)), __fmul_rn(r2.z, v.z)));
 }
 
+// Reciprocal direction for the slab tests only (never for a hit): components below 1e-20 are replaced by +-1e-20, a displacement of
+// t * 1e-20 along that axis (far below fp32 resolution of any coordinate), so that 2^(e+15) * idir stays finite (trace.cuh).
 __device__ __forceinline__ float3 safeInvDir(const float3& d) {
-    const float eps = 1e-30f;
+    const float eps = 1e-20f;
     float x = fabsf(d.x) < eps ? (d.x < 0.0f ? -eps : eps) : d.x;
     float y = fabsf(d.y) < eps ? (d.y < 0.0f ? -eps : eps) : d.y;
     float z = fabsf(d.z) < eps ? (d.z < 0.0f ? -eps : eps) : d.z;

@@ -48,29 +48,40 @@ struct TraceParams {
     unsigned long long* stats;   // optional: [0] nodes visited, [1] triangles tested, [2] instances entered
 };
 
-// byte j of v as an exact fp32 value without the conversion pipe: PRMT builds 0x4B0000bb = 2^23 + b, one FADD removes the 2^23
-__device__ __forceinline__ float byteToFloat(uint32_t v, uint32_t j) {
-    return __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7440u | j)) - 8388608.0f;
+// Byte j of v dropped into the mantissa of 1.0f: PRMT builds 0x3F80bb00 = 1 + b * 2^-15 (no conversion pipe, no bias subtraction:
+// the "-1" is folded into the per-node plane constants below). `one` must live in a register so that the selector is the
+// immediate operand of PRMT (with a literal constant ptxas keeps the four selectors in uniform registers and copies one into a
+// vector register before every PRMT: 45 extra instructions per node, profiles/r01_notes.md).
+__device__ __forceinline__ float byteToUnitFloat(uint32_t v, uint32_t one, uint32_t j) {
+    return __uint_as_float(__byte_perm(one, v, 0x3240u + (j << 4)));
 }
 
 // Intersects the 8 children of one compressed node; returns the hit mask: bits 24..31 = internal children ordered by
 // (slot ^ octinv) (nearest = highest bit), bits 0..23 = primitives of the leaf children. Branch-free: the meta byte of a child
 // encodes {count bits << 5 | bit position} for both kinds (internal children: 1 << 5 | 24 + slot), so one shift places the bits;
 // internal positions are re-ordered by XOR with octinv; empty slots (meta 0) contribute nothing.
+//
+// Slab arithmetic: plane = p + q * 2^e, t = (plane - o) * idir = f * A + B with f = 1 + q * 2^-15 (byteToUnitFloat),
+// A = 2^(e+15) * idir, B = (p - o) * idir - A: ONE FMA per plane. B carries a rounding error of up to 2^-24 |A| = 2^-9 of a
+// quantisation step of ITS axis, so the near planes use B - 2^-22 |A| and the far planes B + 2^-22 |A| (1/128 step; a common margin
+// for the three axes would be a disaster: an axis the ray is almost parallel to has a huge |A|). The relative slack covers the
+// rounding of t itself. Culling never changes a result: the closest hit is independent of the traversal order (intersect.cuh).
 __device__ __forceinline__ uint32_t intersectNode8(const Bvh8Node* __restrict__ node, const float3& o, const float3& idir, uint32_t octinv,
-                                                   float tMin, float tMax, uint32_t& childBase, uint32_t& primBase, uint32_t& imask) {
+                                                   uint32_t one, float tMin, float tMax, uint32_t& childBase, uint32_t& primBase, uint32_t& imask) {
     const ::float4* q = reinterpret_cast<const ::float4*>(node);
     const ::float4 n0 = __ldg(q), n1 = __ldg(q + 1), n2 = __ldg(q + 2), n3 = __ldg(q + 3), n4 = __ldg(q + 4);
     const uint32_t ebits = __float_as_uint(n0.w);
     imask = ebits >> 24;
     childBase = __float_as_uint(n1.x);
     primBase = __float_as_uint(n1.y);
-    const float ax = __uint_as_float((ebits & 0xffu) << 23) * idir.x;
-    const float ay = __uint_as_float(((ebits >> 8) & 0xffu) << 23) * idir.y;
-    const float az = __uint_as_float(((ebits >> 16) & 0xffu) << 23) * idir.z;
-    const float bx = (n0.x - o.x) * idir.x, by = (n0.y - o.y) * idir.y, bz = (n0.z - o.z) * idir.z;
+    const float Ax = __uint_as_float(((ebits & 0xffu) + 15u) << 23) * idir.x;
+    const float Ay = __uint_as_float((((ebits >> 8) & 0xffu) + 15u) << 23) * idir.y;
+    const float Az = __uint_as_float((((ebits >> 16) & 0xffu) + 15u) << 23) * idir.z;
+    const float Bx = fmaf(n0.x - o.x, idir.x, -Ax), By = fmaf(n0.y - o.y, idir.y, -Ay), Bz = fmaf(n0.z - o.z, idir.z, -Az);
+    constexpr float M = 2.384185791015625e-07f;  // 2^-22
+    const float Bnx = fmaf(fabsf(Ax), -M, Bx), Bny = fmaf(fabsf(Ay), -M, By), Bnz = fmaf(fabsf(Az), -M, Bz);
+    const float Bfx = fmaf(fabsf(Ax), M, Bx), Bfy = fmaf(fabsf(Ay), M, By), Bfz = fmaf(fabsf(Az), M, Bz);
     const bool negx = idir.x < 0.0f, negy = idir.y < 0.0f, negz = idir.z < 0.0f;
-    const float tMinS = tMin, tMaxS = tMax;
     const uint32_t octinv4 = octinv * 0x01010101u;
     uint32_t hitmask = 0;
 #pragma unroll
@@ -89,12 +100,12 @@ __device__ __forceinline__ uint32_t intersectNode8(const Bvh8Node* __restrict__ 
         const uint32_t nz4 = negz ? hiz4 : loz4, fz4 = negz ? loz4 : hiz4;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            const float tnx = fmaf(byteToFloat(nx4, j), ax, bx), tfx = fmaf(byteToFloat(fx4, j), ax, bx);
-            const float tny = fmaf(byteToFloat(ny4, j), ay, by), tfy = fmaf(byteToFloat(fy4, j), ay, by);
-            const float tnz = fmaf(byteToFloat(nz4, j), az, bz), tfz = fmaf(byteToFloat(fz4, j), az, bz);
-            const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tMinS));
-            const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tMaxS));
-            const bool hit = tn * 0.999999f <= tf * 1.000001f;
+            const float tnx = fmaf(byteToUnitFloat(nx4, one, j), Ax, Bnx), tfx = fmaf(byteToUnitFloat(fx4, one, j), Ax, Bfx);
+            const float tny = fmaf(byteToUnitFloat(ny4, one, j), Ay, Bny), tfy = fmaf(byteToUnitFloat(fy4, one, j), Ay, Bfy);
+            const float tnz = fmaf(byteToUnitFloat(nz4, one, j), Az, Bnz), tfz = fmaf(byteToUnitFloat(fz4, one, j), Az, Bfz);
+            const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tMin));
+            const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tMax));
+            const bool hit = tn <= tf * 1.000002f;
             const uint32_t bits = ((childBits4 >> (j * 8)) & 0xffu) << ((bitIndex4 >> (j * 8)) & 0xffu);
             hitmask |= hit ? bits : 0u;
         }
@@ -133,6 +144,8 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_trace(const TraceParams P) {
     float3 objO(0.0f);  // flat variant: ray origin in the cached instance's object space
     uint2 G = make_uint2(0u, 0u), Gt = make_uint2(0u, 0u);  // pending node group / pending primitive group of this lane
     bool exhausted = false;
+    uint32_t one;  // 1.0f as an opaque register value (byteToUnitFloat)
+    asm volatile("mov.b32 %0, 0x3F800000;" : "=r"(one));
     unsigned long long nNodes = 0, nTris = 0, nInst = 0;
 
     while (true) {
@@ -192,7 +205,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_trace(const TraceParams P) {
                     if (G.y & 0xff000000u) { if (sp < TRACE_STACK) stack[sp++] = G; }
                     const uint32_t nodeIndex = G.x + __popc(G.y & 0xffu & ((1u << slot) - 1u));
                     uint32_t childBase, primBase, imask;
-                    const uint32_t hits = intersectNode8(A.nodes + nodeIndex, o, idir, octinv, R.tMin, R.tBest, childBase, primBase, imask);
+                    const uint32_t hits = intersectNode8(A.nodes + nodeIndex, o, idir, octinv, one, R.tMin, R.tBest, childBase, primBase, imask);
                     if (COUNT) nNodes++;
                     G = make_uint2(childBase, (hits & 0xff000000u) | imask);
                     Gt = make_uint2(primBase, hits & 0x00ffffffu);

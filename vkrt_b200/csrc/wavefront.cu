@@ -295,7 +295,7 @@ __device__ __forceinline__ float computeSpectralMISWeight(float4 sampled, float4
 #define SHADE_SUBPHASE_BARRIER()
 #endif
 template <int MODE>
-__global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const FrameParams fp, const uint32_t depth) {
+__global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ FrameParams fp, const uint32_t depth) {
     const uint32_t count = fp.extCount[depth];
     const PathState& S = fp.st[depth & 1u];
     const PathState& N = fp.st[(depth & 1u) ^ 1u];
