@@ -28,6 +28,7 @@ void launchShadeSort(const FrameParams& fp, uint32_t depth, int smCount, cudaStr
 void launchFilm(int mode, const FrameParams& fp, int firstChunk, int lastChunk, int grid, cudaStream_t st);
 void launchTrace(const TraceParams& tp, bool count, int grid, cudaStream_t st);  // picks the flat / two-level kernel from tp.scene.accel.flat
 void launchPrimaryRaygen(const FrameParams& fp, int jittered, int grid, cudaStream_t st);
+void launchPackRgb2spec(const float* table, uint32_t dataOffset, size_t cellCount, ::float4* cells, int grid, cudaStream_t st);
 void launchPrimaryStore(const FrameParams& fp, int grid, cudaStream_t st);
 void launchUntile(const void* src, void* dst, const TileMap& tm, const uint32_t* l2g, uint32_t words, int grid, cudaStream_t st);
 void launchMeshTrig(const MeshInfo* infos, MeshTrig* out, uint32_t count, cudaStream_t st);
@@ -104,6 +105,7 @@ struct vkrt_cuda_ctx {
     DevBuf<EmissiveMesh> emissiveMeshes;
     DevBuf<EmissiveTriangle> emissiveTriangles;
     DevBuf<float> meshAliasQ, triAliasQ, rgb2spec, srgbLut, world3x4;
+    DevBuf<::float4> rgb2specCells;   // the coefficient cells of rgb2spec re-packed as float4 (shading.cuh SpectralTables)
     DevBuf<uint32_t> meshAliasIdx, triAliasIdx;
     RGB2SpecTableInfo rgb2specInfo = {0, 0, 0};
     bool haveRgb2spec = false;
@@ -233,6 +235,8 @@ SceneView makeSceneView(vkrt_cuda_ctx* c) {
     v.srgbLut = c->srgbLut.p;
     v.spectral.info = c->rgb2specInfo;
     v.spectral.table = c->rgb2spec.p;
+    v.spectral.cells = c->rgb2specCells.p;
+    v.spectral.scale = c->rgb2spec.p + c->rgb2specInfo.scaleOffset;
     v.accel.nodes = c->nodes.p;
     v.accel.triangles = c->triangles.p;
     v.accel.instances = c->instancesLeafOrder.p;
@@ -474,7 +478,7 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_create(const vkrt_cuda_create_info* info, vk
     }
     // placeholders so that empty scenes still have valid pointers
     ctx->emissiveMeshes.alloc(1); ctx->emissiveTriangles.alloc(1); ctx->meshAliasQ.alloc(1); ctx->meshAliasIdx.alloc(1);
-    ctx->triAliasQ.alloc(1); ctx->triAliasIdx.alloc(1); ctx->textures.alloc(1); ctx->rgb2spec.alloc(1);
+    ctx->triAliasQ.alloc(1); ctx->triAliasIdx.alloc(1); ctx->textures.alloc(1); ctx->rgb2spec.alloc(1); ctx->rgb2specCells.alloc(1);
     cudaStreamSynchronize(ctx->stream);
     *outCtx = ctx;
     return VKRT_SUCCESS;
@@ -586,6 +590,10 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_set_rgb2spec(vkrt_cuda_ctx* ctx, const float
     if (need > floatCount || (uint64_t)info.scaleOffset + info.res > floatCount) return fail(ctx, VKRT_ERROR_INVALID_ARGUMENT, "rgb2spec payload too small");
     cudaSetDevice(ctx->device);
     CU(ctx->rgb2spec.upload(payload, floatCount, ctx->stream));
+    const size_t cellCount = 3ull * info.res * info.res * info.res;
+    CU(ctx->rgb2specCells.alloc(cellCount));
+    launchPackRgb2spec(ctx->rgb2spec.p, info.dataOffset, cellCount, ctx->rgb2specCells.p, ctx->smCount * 8, ctx->stream);
+    CU(cudaGetLastError());
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->rgb2specInfo = info;
     ctx->haveRgb2spec = true;

@@ -136,66 +136,81 @@ VK_D bool insideViewport(const SceneData& scene, int px, int py) {
 VK_D float linearSrgbLuminance(float3 rgb) { return dot(rgb, float3(0.2126f, 0.7152f, 0.0722f)); }
 
 // ---- utility/rgb2spec.slang:14-90 ---------------------------------------------------------------------------------
+// Device layout of the coefficient table (written once by vkrt_cuda_set_rgb2spec, k_pack_rgb2spec): `cells` holds one float4 per
+// grid cell {c0, c1, c2, 0} in the payload's cell order, so the 8 corners of a lookup are 8 aligned 128-bit loads (two neighbours along
+// x share a 32-byte sector) instead of 24 scalar loads; `scale` is the res-entry scale axis, which k_shade stages in shared memory.
 struct SpectralTables {
     RGB2SpecTableInfo info = {0, 0, 0};
-    const float* table = nullptr;
+    const float* table = nullptr;      // the payload as uploaded (rgb2spec.c:17-59)
+    const ::float4* cells = nullptr;   // 3 * res^3 packed coefficient cells
+    const float* scale = nullptr;      // table + scaleOffset, or its shared-memory copy
 };
 static constexpr float RGB2SPEC_EPSILON = 1e-8f;
+static constexpr uint RGB2SPEC_SMEM_RES = 64u;
 
-VK_D uint rgb2specFindInterval(const SpectralTables& t, float x) {
+// rgb2spec.slang:14-30: the largest index in [0, res-2] whose scale entry is <= x. The scale axis is non-decreasing, so that index is
+// the NUMBER of entries k in [1, res-2] with scale[k] <= x: for the standard res = 64 two rounds of independent loads (7 block pivots,
+// then 7 entries of the block) replace six dependent ones.
+VK_D uint rgb2specFindInterval(const float* __restrict__ scale, uint res, float x) {
+    if (res == 64u) {
+        uint block = 0u;
+#pragma unroll
+        for (int k = 8; k < 64; k += 8) block += scale[k] <= x ? 1u : 0u;
+        const float* s = scale + 8u * block;
+        uint left = 8u * block;
+#pragma unroll
+        for (int k = 1; k < 8; k++) left += s[k] <= x ? 1u : 0u;
+        return min(left, 62u);
+    }
     int left = 0;
-    int size = int(t.info.res) - 2;
+    int size = int(res) - 2;
     while (size > 0) {
         int half = size >> 1;
         int middle = left + half + 1;
-        if (t.table[t.info.scaleOffset + uint(middle)] <= x) {
+        if (scale[uint(middle)] <= x) {
             left = middle;
             size -= half + 1;
         } else {
             size = half;
         }
     }
-    return min(uint(left), t.info.res - 2u);
+    return min(uint(left), res - 2u);
 }
 
-VK_NOINLINE float3 rgb2specFetchTable(const float* __restrict__ table, uint tableRes, uint scaleOffset, uint dataOffset, float3 rgb) {
-    SpectralTables t;
-    t.info.res = tableRes; t.info.scaleOffset = scaleOffset; t.info.dataOffset = dataOffset;
-    t.table = table;
+VK_NOINLINE float3 rgb2specFetchTable(const ::float4* __restrict__ cells, const float* __restrict__ scale, uint res, float3 rgb) {
     float z = max(rgb.x, max(rgb.y, rgb.z));
     if (z <= RGB2SPEC_EPSILON) return float3(0.0f);
     uint dominantChannel = 0u;
     for (uint channel = 1u; channel < 3u; ++channel) {
         if (rgb[int(channel)] >= rgb[int(dominantChannel)]) dominantChannel = channel;
     }
-    const uint res = t.info.res;
     float xyScale = float(res - 1u) / z;
     float x = rgb[int((dominantChannel + 1u) % 3u)] * xyScale;
     float y = rgb[int((dominantChannel + 2u) % 3u)] * xyScale;
     uint xi = min(uint(x), res - 2u);
     uint yi = min(uint(y), res - 2u);
-    uint zi = rgb2specFindInterval(t, z);
-    uint offset = ((((dominantChannel * res + zi) * res + yi) * res + xi) * 3u);
-    uint dx = 3u, dy = dx * res, dz = dy * res;
+    uint zi = rgb2specFindInterval(scale, res, z);
+    const ::float4* c = cells + ((((size_t)dominantChannel * res + zi) * res + yi) * res + xi);
+    const uint dy = res, dz = res * res;
+    const ::float4 c000 = __ldg(c), c100 = __ldg(c + 1), c010 = __ldg(c + dy), c110 = __ldg(c + dy + 1);
+    const ::float4 c001 = __ldg(c + dz), c101 = __ldg(c + dz + 1), c011 = __ldg(c + dz + dy), c111 = __ldg(c + dz + dy + 1);
     float x1 = x - float(xi), y1 = y - float(yi);
     float x0 = 1.0f - x1, y0 = 1.0f - y1;
-    float scale0 = t.table[t.info.scaleOffset + zi];
-    float scale1 = t.table[t.info.scaleOffset + zi + 1u];
+    float scale0 = scale[zi];
+    float scale1 = scale[zi + 1u];
     float z1 = (z - scale0) / max(scale1 - scale0, RGB2SPEC_EPSILON);
     float z0 = 1.0f - z1;
-    float3 coeff(0.0f);
-    const float* tb = t.table;
-    for (uint j = 0; j < 3u; ++j) {
-        uint co = t.info.dataOffset + offset + j;
-        coeff[int(j)] = ((tb[co] * x0 + tb[co + dx] * x1) * y0 + (tb[co + dy] * x0 + tb[co + dy + dx] * x1) * y1) * z0 +
-                        ((tb[co + dz] * x0 + tb[co + dz + dx] * x1) * y0 +
-                         (tb[co + dz + dy] * x0 + tb[co + dz + dy + dx] * x1) * y1) *
-                            z1;
-    }
+    float3 coeff;
+    coeff.x = ((c000.x * x0 + c100.x * x1) * y0 + (c010.x * x0 + c110.x * x1) * y1) * z0 +
+              ((c001.x * x0 + c101.x * x1) * y0 + (c011.x * x0 + c111.x * x1) * y1) * z1;
+    coeff.y = ((c000.y * x0 + c100.y * x1) * y0 + (c010.y * x0 + c110.y * x1) * y1) * z0 +
+              ((c001.y * x0 + c101.y * x1) * y0 + (c011.y * x0 + c111.y * x1) * y1) * z1;
+    coeff.z = ((c000.z * x0 + c100.z * x1) * y0 + (c010.z * x0 + c110.z * x1) * y1) * z0 +
+              ((c001.z * x0 + c101.z * x1) * y0 + (c011.z * x0 + c111.z * x1) * y1) * z1;
     return coeff;
 }
 VK_D float3 rgb2specFetch(const SpectralTables& t, float3 rgb) {
-    return rgb2specFetchTable(t.table, t.info.res, t.info.scaleOffset, t.info.dataOffset, rgb);
+    return rgb2specFetchTable(t.cells, t.scale, t.info.res, rgb);
 }
 VK_D float rgb2specEvalCoeffs(float3 coeff, float lambdaNm) {
     float x = (coeff.x * lambdaNm + coeff.y) * lambdaNm + coeff.z;

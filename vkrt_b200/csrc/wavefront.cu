@@ -301,7 +301,14 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const _
     const PathState& N = fp.st[(depth & 1u) ^ 1u];
     const SceneView& sc = fp.scene;
     const SceneData& scene = fp.sd;
-    const SpectralTables& T = sc.spectral;
+    // spectral modes: the rgb2spec scale axis (res floats, searched several times per vertex) is staged in shared memory
+    __shared__ float sScale[RGB2SPEC_SMEM_RES];
+    SpectralTables T = sc.spectral;
+    if (MODE != MODE_RGB && T.info.res <= RGB2SPEC_SMEM_RES) {
+        if (threadIdx.x < T.info.res) sScale[threadIdx.x] = T.scale[threadIdx.x];
+        T.scale = sScale;
+        __syncthreads();
+    }
     const uint32_t lpc = fp.tiles.localPixelCount;
     const bool neeEnabled = (fp.modeFlags & MODE_NEE_ENABLED) && !(fp.modeFlags & MODE_BSDF_ONLY);
     const bool neeOnly = (fp.modeFlags & MODE_NEE_ONLY) != 0u;
@@ -939,6 +946,16 @@ __global__ void __launch_bounds__(128) k_mesh_trig(const MeshInfo* __restrict__ 
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     out[i] = makeMeshTrig(float3(infos[i].rotation[0], infos[i].rotation[1], infos[i].rotation[2]));
+}
+// rgb2spec payload -> float4 cells (shading.cuh SpectralTables)
+__global__ void __launch_bounds__(256) k_pack_rgb2spec(const float* __restrict__ table, uint32_t dataOffset, size_t cellCount, ::float4* __restrict__ cells) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cellCount; i += (size_t)gridDim.x * blockDim.x) {
+        const float* c = table + dataOffset + 3u * i;
+        cells[i] = make_float4(c[0], c[1], c[2], 0.0f);
+    }
+}
+void launchPackRgb2spec(const float* table, uint32_t dataOffset, size_t cellCount, ::float4* cells, int grid, cudaStream_t st) {
+    k_pack_rgb2spec<<<grid, 256, 0, st>>>(table, dataOffset, cellCount, cells);
 }
 void launchMeshTrig(const MeshInfo* infos, MeshTrig* out, uint32_t count, cudaStream_t st) {
     if (count) k_mesh_trig<<<(count + 127) / 128, 128, 0, st>>>(infos, out, count);
