@@ -51,6 +51,7 @@ rows = list(csv.DictReader(io.StringIO("\n".join(lines[start:]))))
 base = int(rows[0]["Address"], 16)
 by_in, by_out = collections.Counter(), collections.Counter()
 inst_in = collections.Counter()
+thr_in = collections.Counter()
 reasons = collections.defaultdict(collections.Counter)
 total = 0
 tot_inst = 0
@@ -63,15 +64,13 @@ for r in rows:
     k = inner.get(off, ("?", 0))
     by_in[k] += s
     inst_in[k] += n
+    thr_in[k] += int(r["Thread Instructions Executed"] or 0)
     by_out[outer.get(off, ("?", 0))] += s
     for key, v in r.items():
         if key.startswith("stall_") and "Not Issued" not in key and v and int(v):
             reasons[k][key[6:]] += int(v)
 print("kernel %s: %d samples, %d warp instructions" % (kern, total, tot_inst))
-print("-- innermost source line: samples %, warp-instructions %, top stall reasons")
+print("-- innermost source line: samples %, warp-instructions %, lanes per instruction, top stall reasons")
 for k, s in by_in.most_common(top):
     rs = ", ".join("%s %d" % kv for kv in reasons[k].most_common(3))
-    print("%-18s:%-5d %5.1f%% %5.1f%%  %s" % (k[0], k[1], 100.0 * s / total, 100.0 * inst_in[k] / max(tot_inst, 1), rs))
-print("-- kernel-body line (outermost inline frame)")
-for k, s in by_out.most_common(top // 2):
-    print("%-18s:%-5d %5.1f%%" % (k[0], k[1], 100.0 * s / total))
+    print("%-18s:%-5d %5.1f%% %5.1f%% %5.1f  %s" % (k[0], k[1], 100.0 * s / total, 100.0 * inst_in[k] / max(tot_inst, 1), thr_in[k] / max(inst_in[k], 1), rs))

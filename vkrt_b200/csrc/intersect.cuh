@@ -13,12 +13,17 @@
 
 namespace vk {
 
+// Shear constants of a ray (Woop et al. 2013). The permutation (kx, ky, kz) is stored as PRMT selectors: picking component k of a
+// vector is two byte-permutes, no compare / select chains or branches inside the per-triangle code (profiles/r01_notes.md).
 struct RayShear {
-    int kx, ky, kz;
+    uint32_t x1, x2, y1, y2, z1, z2;
     float Sx, Sy, Sz;
 };
 
 __device__ __forceinline__ float comp(const float3& v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
+__device__ __forceinline__ float pick(const float3& v, uint32_t s1, uint32_t s2) {
+    return __uint_as_float(__byte_perm(__byte_perm(__float_as_uint(v.x), __float_as_uint(v.y), s1), __float_as_uint(v.z), s2));
+}
 
 __device__ __forceinline__ bool makeRayShear(const float3& d, RayShear& s) {
     float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
@@ -30,9 +35,11 @@ __device__ __forceinline__ bool makeRayShear(const float3& d, RayShear& s) {
     int ky = kx == 2 ? 0 : kx + 1;
     float dz = comp(d, kz);
     if (dz < 0.0f) { int t = kx; kx = ky; ky = t; }
-    s.kx = kx; s.ky = ky; s.kz = kz;
-    s.Sx = __fdiv_rn(comp(d, kx), dz);
-    s.Sy = __fdiv_rn(comp(d, ky), dz);
+    s.x1 = kx == 1 ? 0x7654u : 0x3210u; s.x2 = kx == 2 ? 0x7654u : 0x3210u;
+    s.y1 = ky == 1 ? 0x7654u : 0x3210u; s.y2 = ky == 2 ? 0x7654u : 0x3210u;
+    s.z1 = kz == 1 ? 0x7654u : 0x3210u; s.z2 = kz == 2 ? 0x7654u : 0x3210u;
+    s.Sx = __fdiv_rn(pick(d, s.x1, s.x2), dz);
+    s.Sy = __fdiv_rn(pick(d, s.y1, s.y2), dz);
     s.Sz = __fdiv_rn(1.0f, dz);
     return m > 0.0f;
 }
@@ -42,10 +49,10 @@ __device__ __forceinline__ bool watertightTriangle(const float3& org, const RayS
     const float3 A = float3(__fsub_rn(v0.x, org.x), __fsub_rn(v0.y, org.y), __fsub_rn(v0.z, org.z));
     const float3 B = float3(__fsub_rn(v1.x, org.x), __fsub_rn(v1.y, org.y), __fsub_rn(v1.z, org.z));
     const float3 C = float3(__fsub_rn(v2.x, org.x), __fsub_rn(v2.y, org.y), __fsub_rn(v2.z, org.z));
-    const float Akz = comp(A, s.kz), Bkz = comp(B, s.kz), Ckz = comp(C, s.kz);
-    const float Ax = __fsub_rn(comp(A, s.kx), __fmul_rn(s.Sx, Akz)), Ay = __fsub_rn(comp(A, s.ky), __fmul_rn(s.Sy, Akz));
-    const float Bx = __fsub_rn(comp(B, s.kx), __fmul_rn(s.Sx, Bkz)), By = __fsub_rn(comp(B, s.ky), __fmul_rn(s.Sy, Bkz));
-    const float Cx = __fsub_rn(comp(C, s.kx), __fmul_rn(s.Sx, Ckz)), Cy = __fsub_rn(comp(C, s.ky), __fmul_rn(s.Sy, Ckz));
+    const float Akz = pick(A, s.z1, s.z2), Bkz = pick(B, s.z1, s.z2), Ckz = pick(C, s.z1, s.z2);
+    const float Ax = __fsub_rn(pick(A, s.x1, s.x2), __fmul_rn(s.Sx, Akz)), Ay = __fsub_rn(pick(A, s.y1, s.y2), __fmul_rn(s.Sy, Akz));
+    const float Bx = __fsub_rn(pick(B, s.x1, s.x2), __fmul_rn(s.Sx, Bkz)), By = __fsub_rn(pick(B, s.y1, s.y2), __fmul_rn(s.Sy, Bkz));
+    const float Cx = __fsub_rn(pick(C, s.x1, s.x2), __fmul_rn(s.Sx, Ckz)), Cy = __fsub_rn(pick(C, s.y1, s.y2), __fmul_rn(s.Sy, Ckz));
     float U = __fsub_rn(__fmul_rn(Cx, By), __fmul_rn(Cy, Bx));
     float V = __fsub_rn(__fmul_rn(Ax, Cy), __fmul_rn(Ay, Cx));
     float W = __fsub_rn(__fmul_rn(Bx, Ay), __fmul_rn(By, Ax));

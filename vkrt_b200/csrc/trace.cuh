@@ -21,6 +21,9 @@ namespace vk {
 constexpr int TRACE_STACK = 40;
 constexpr int TRACE_BLOCK = 128;
 constexpr int REFILL_THRESHOLD = 20;
+#ifndef TRACE_MIN_BLOCKS
+#define TRACE_MIN_BLOCKS 6   // 80 registers: 24 warps per SM (measured best, profiles/r01_notes.md)
+#endif
 constexpr uint32_t SHADOW_KIND_SCALAR = 1u << 31;  // in ShadowTarget.statePos: contribution goes to the scalar lane (hero fallback)
 
 struct TraceParams {
@@ -123,7 +126,7 @@ struct LaneRay {
 };
 
 template <bool COUNT, bool FLAT>
-__global__ void __launch_bounds__(TRACE_BLOCK) k_trace(const TraceParams P) {
+__global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS) k_trace(const TraceParams P) {
     const int lane = threadIdx.x & 31;
     const uint32_t extCount = P.extCount ? *P.extCount : 0u;
     const uint32_t shCount = P.shCount ? *P.shCount : 0u;
@@ -370,11 +373,10 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_trace(const TraceParams P) {
                             if (!occluded && !R.sawTransmissive) {
                                 const ::float4 c = __ldg(P.shContribution + k);
                                 if (target.y & SHADOW_KIND_SCALAR) {
-                                    P.radianceScalar[target.x] += c.x;
+                                    atomicAdd(P.radianceScalar + target.x, c.x);
                                 } else {
-                                    ::float4 r = P.radiance[target.x];
-                                    r.x += c.x; r.y += c.y; r.z += c.z; r.w += c.w;
-                                    P.radiance[target.x] = r;
+                                    // one shadow ray per record per launch: the reduction is race-free and fire-and-forget
+                                    atomicAdd(P.radiance + target.x, c);
                                 }
                             } else if (!occluded) {  // unsupported transmission: NEE is not trusted at this vertex
                                 const uint32_t pos = target.y & 0x7fffffffu;
