@@ -11,6 +11,7 @@
 //   6. greedy surface-area collapse to compressed 8-wide nodes (k_collapse), level by level
 // All stages stream their inputs with coalesced 8/16-byte accesses; the sort is the HBM-bound part
 // (DESIGN.md "Build" gives the algorithmic bytes per triangle).
+#include <algorithm>
 #include <cfloat>
 #include <cstdio>
 #include <cstring>
@@ -43,9 +44,11 @@ __global__ void k_init_bounds(int* bounds) {
     else if (threadIdx.x < 6) bounds[threadIdx.x] = floatToOrdered(-FLT_MAX);
 }
 
-__device__ __forceinline__ void reduceBounds(float3 lo, float3 hi, bool valid, int* bounds) {
-    // warp reduce then one atomic per warp per component
-    if (!valid) { lo = float3(FLT_MAX); hi = float3(-FLT_MAX); }
+// Block-level reduction of per-thread boxes, then ONE set of six ordered-int atomics per block. Every thread of the block must call
+// it (blockDim a multiple of 32, at most 1024). The kernels below accumulate over a grid-stride loop first, so a 10 M-triangle
+// geometry issues ~7 k atomics instead of 1.9 M on the same six words (profiles/r01_notes.md: 2.1 ms -> bandwidth-bound).
+__device__ __forceinline__ void reduceBounds(float3 lo, float3 hi, int* bounds) {
+    __shared__ float sBox[6][32];
     for (int o = 16; o > 0; o >>= 1) {
         lo.x = fminf(lo.x, __shfl_xor_sync(0xffffffffu, lo.x, o));
         lo.y = fminf(lo.y, __shfl_xor_sync(0xffffffffu, lo.y, o));
@@ -54,15 +57,27 @@ __device__ __forceinline__ void reduceBounds(float3 lo, float3 hi, bool valid, i
         hi.y = fmaxf(hi.y, __shfl_xor_sync(0xffffffffu, hi.y, o));
         hi.z = fmaxf(hi.z, __shfl_xor_sync(0xffffffffu, hi.z, o));
     }
-    if ((threadIdx.x & 31) == 0 && lo.x <= hi.x) {
-        atomicMin(&bounds[0], floatToOrdered(lo.x));
-        atomicMin(&bounds[1], floatToOrdered(lo.y));
-        atomicMin(&bounds[2], floatToOrdered(lo.z));
-        atomicMax(&bounds[3], floatToOrdered(hi.x));
-        atomicMax(&bounds[4], floatToOrdered(hi.y));
-        atomicMax(&bounds[5], floatToOrdered(hi.z));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = (blockDim.x + 31) >> 5;
+    if (lane == 0) {
+        sBox[0][warp] = lo.x; sBox[1][warp] = lo.y; sBox[2][warp] = lo.z;
+        sBox[3][warp] = hi.x; sBox[4][warp] = hi.y; sBox[5][warp] = hi.z;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        for (int c = 0; c < 6; c++) {
+            float v = lane < warps ? sBox[c][lane] : (c < 3 ? FLT_MAX : -FLT_MAX);
+            for (int o = 16; o > 0; o >>= 1) {
+                const float w = __shfl_xor_sync(0xffffffffu, v, o);
+                v = c < 3 ? fminf(v, w) : fmaxf(v, w);
+            }
+            if (lane == 0 && (c < 3 ? v < FLT_MAX : v > -FLT_MAX)) {
+                if (c < 3) atomicMin(&bounds[c], floatToOrdered(v)); else atomicMax(&bounds[c], floatToOrdered(v));
+            }
+        }
     }
 }
+constexpr int BOUNDS_MAX_BLOCKS = 148 * 8;
+static inline int boundsGrid(uint32_t n) { return (int)std::min<uint32_t>((n + 255u) / 256u, (uint32_t)BOUNDS_MAX_BLOCKS); }
 
 // Pads a box by 2^-20 of its largest absolute coordinate so that the (rounded) watertight test can never accept a
 // hit outside the boxes that cull for it.
@@ -76,10 +91,9 @@ __device__ __forceinline__ void padBox(float3& lo, float3& hi) {
 __global__ void k_triangle_bounds(const ShaderVertex* __restrict__ vertices, const uint32_t* __restrict__ indices, uint32_t vertexBase,
                                   uint32_t indexBase, uint32_t triCount, ::float4* __restrict__ primLo, ::float4* __restrict__ primHi,
                                   int* bounds) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    bool valid = t < triCount;
-    float3 lo(FLT_MAX), hi(-FLT_MAX);
-    if (valid) {
+    float3 accLo(FLT_MAX), accHi(-FLT_MAX);
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < triCount; t += gridDim.x * blockDim.x) {
+        float3 lo(FLT_MAX), hi(-FLT_MAX);
         for (int k = 0; k < 3; k++) {
             uint32_t vi = indices[indexBase + t * 3u + k] + vertexBase;
             ::float4 p = *reinterpret_cast<const ::float4*>(vertices[vi].position);
@@ -90,8 +104,10 @@ __global__ void k_triangle_bounds(const ShaderVertex* __restrict__ vertices, con
         padBox(lo, hi);
         primLo[t] = make_float4(lo.x, lo.y, lo.z, 0.0f);
         primHi[t] = make_float4(hi.x, hi.y, hi.z, 0.0f);
+        accLo = min(accLo, lo);
+        accHi = max(accHi, hi);
     }
-    reduceBounds(lo, hi, valid, bounds);
+    reduceBounds(accLo, accHi, bounds);
 }
 
 // World-space AABB of every instance = transformed corners of its BLAS root box (conservative), padded.
@@ -121,16 +137,14 @@ __global__ void k_instance_bounds(const ::float4* __restrict__ blasBounds, const
         primLo[i] = make_float4(lo.x, lo.y, lo.z, 0.0f);
         primHi[i] = make_float4(hi.x, hi.y, hi.z, 0.0f);
     }
-    reduceBounds(lo, hi, valid, bounds);
+    reduceBounds(lo, hi, bounds);
 }
 
 // Object-space AABB of one geometry (ordered-int atomics into bounds6), for the flat / two-level decision.
 __global__ void k_geometry_bounds(const ShaderVertex* __restrict__ vertices, const uint32_t* __restrict__ indices, uint32_t vertexBase, uint32_t indexBase,
                                   uint32_t triCount, int* bounds6) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    bool valid = t < triCount;
     float3 lo(FLT_MAX), hi(-FLT_MAX);
-    if (valid) {
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < triCount; t += gridDim.x * blockDim.x) {
         for (int k = 0; k < 3; k++) {
             uint32_t vi = indices[indexBase + t * 3u + k] + vertexBase;
             ::float4 p = *reinterpret_cast<const ::float4*>(vertices[vi].position);
@@ -139,12 +153,12 @@ __global__ void k_geometry_bounds(const ShaderVertex* __restrict__ vertices, con
             hi = max(hi, v);
         }
     }
-    reduceBounds(lo, hi, valid, bounds6);
+    reduceBounds(lo, hi, bounds6);
 }
 void launchGeometryBounds(const ShaderVertex* vertices, const uint32_t* indices, uint32_t vertexBase, uint32_t indexBase, uint32_t triCount, int* bounds6,
                           cudaStream_t st) {
     k_init_bounds<<<1, 32, 0, st>>>(bounds6);
-    if (triCount) k_geometry_bounds<<<(triCount + 255) / 256, 256, 0, st>>>(vertices, indices, vertexBase, indexBase, triCount, bounds6);
+    if (triCount) k_geometry_bounds<<<boundsGrid(triCount), 256, 0, st>>>(vertices, indices, vertexBase, indexBase, triCount, bounds6);
 }
 float orderedIntToFloatHost(int i) {
     int b = i >= 0 ? i : i ^ 0x7fffffff;
@@ -170,10 +184,9 @@ __global__ void k_flat_enumerate(const uint32_t* __restrict__ triOffsets, uint32
 __global__ void k_flat_bounds(const ShaderVertex* __restrict__ vertices, const uint32_t* __restrict__ indices, const uint2* __restrict__ flatIn,
                               const uint4* __restrict__ flatInstances, const float* __restrict__ world3x4, uint32_t total,
                               ::float4* __restrict__ primLo, ::float4* __restrict__ primHi, int* bounds) {
-    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    bool valid = p < total;
-    float3 lo(FLT_MAX), hi(-FLT_MAX);
-    if (valid) {
+    float3 accLo(FLT_MAX), accHi(-FLT_MAX);
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
+        float3 lo(FLT_MAX), hi(-FLT_MAX);
         const uint2 fp = flatIn[p];
         const uint4 inst = flatInstances[fp.x];
         const float* m = world3x4 + (size_t)fp.x * 12;
@@ -188,8 +201,10 @@ __global__ void k_flat_bounds(const ShaderVertex* __restrict__ vertices, const u
         padBox(lo, hi);
         primLo[p] = make_float4(lo.x, lo.y, lo.z, 0.0f);
         primHi[p] = make_float4(hi.x, hi.y, hi.z, 0.0f);
+        accLo = min(accLo, lo);
+        accHi = max(accHi, hi);
     }
-    reduceBounds(lo, hi, valid, bounds);
+    reduceBounds(accLo, accHi, bounds);
 }
 // Object-space triangle records of one unique geometry in primitive order (a.w = primitive index), shared by all of its instances.
 __global__ void k_pack_triangles(const ShaderVertex* __restrict__ vertices, const uint32_t* __restrict__ indices, uint32_t vertexBase, uint32_t indexBase,
@@ -777,7 +792,7 @@ bool AccelBuilder::buildBlas(cudaStream_t st, const ShaderVertex* vertices, cons
                              ::float4* blasBoundsOut, uint32_t* outNodeCount, uint32_t* outPrimCount) {
     if (!reserve(triCount)) return false;
     k_init_bounds<<<1, 32, 0, st>>>(bounds);
-    k_triangle_bounds<<<(triCount + 255) / 256, 256, 0, st>>>(vertices, indices, vertexBase, indexBase, triCount, primLo, primHi, bounds);
+    k_triangle_bounds<<<boundsGrid(triCount), 256, 0, st>>>(vertices, indices, vertexBase, indexBase, triCount, primLo, primHi, bounds);
     BuildTarget tgt = {};
     tgt.nodesOut = nodesOut; tgt.nodeBase = nodeBase; tgt.vertices = vertices; tgt.indices = indices;
     tgt.vertexBase = vertexBase; tgt.indexBase = indexBase; tgt.trianglesOut = trianglesOut; tgt.primBase = primBase;
@@ -808,7 +823,7 @@ bool AccelBuilder::buildFlat(cudaStream_t st, const ShaderVertex* vertices, cons
     const uint32_t grid = (totalPrims + 255) / 256;
     k_flat_enumerate<<<grid, 256, 0, st>>>(triOffsets, instanceCount, totalPrims, flatScratch);
     k_init_bounds<<<1, 32, 0, st>>>(bounds);
-    k_flat_bounds<<<grid, 256, 0, st>>>(vertices, indices, flatScratch, flatInstances, world3x4, totalPrims, primLo, primHi, bounds);
+    k_flat_bounds<<<boundsGrid(totalPrims), 256, 0, st>>>(vertices, indices, flatScratch, flatInstances, world3x4, totalPrims, primLo, primHi, bounds);
     BuildTarget tgt = {};
     tgt.nodesOut = nodesOut; tgt.nodeBase = nodeBase;
     tgt.flatIn = flatScratch; tgt.flatInstances = flatInstances; tgt.flatOut = flatOut;
