@@ -80,6 +80,15 @@ typedef struct VKRT_TextureUpload {
 
 typedef struct VKRT VKRT;
 
+typedef struct VKRT_TextureSnapshot { /* vkrt_types.h:266-273 */
+    uint32_t width;
+    uint32_t height;
+    uint32_t format;
+    uint32_t colorSpace;
+    uint32_t useCount;
+    char name[VKRT_NAME_LEN];
+} VKRT_TextureSnapshot;
+
 typedef struct VKRT_SceneSettingsSnapshot {
     Camera camera;
     uint32_t samplesPerPixel;
@@ -186,6 +195,7 @@ VKRT_HOST_API VKRT_Result VKRT_setExposure(VKRT* vkrt, float exposure);
 VKRT_HOST_API VKRT_Result VKRT_setEnvironmentLight(VKRT* vkrt, vkrt_vec3 color, float strength);
 VKRT_HOST_API VKRT_Result VKRT_setEnvironmentRotation(VKRT* vkrt, float rotationDegrees);
 VKRT_HOST_API VKRT_Result VKRT_setEnvironmentTextureFromPixels(VKRT* vkrt, const VKRT_TextureUpload* upload);
+VKRT_HOST_API VKRT_Result VKRT_setEnvironmentTextureFromFile(VKRT* vkrt, const char* path); /* vkrt.h:49; PNG / JPEG / EXR, stored LINEAR */
 VKRT_HOST_API VKRT_Result VKRT_clearEnvironmentTexture(VKRT* vkrt);
 VKRT_HOST_API VKRT_Result VKRT_setDebugMode(VKRT* vkrt, VKRT_DebugMode mode);
 VKRT_HOST_API VKRT_Result VKRT_setMisNeeEnabled(VKRT* vkrt, uint8_t enabled);
@@ -214,7 +224,11 @@ VKRT_HOST_API VKRT_Result VKRT_getMeshSnapshot(const VKRT* vkrt, uint32_t meshIn
 VKRT_HOST_API VKRT_Result VKRT_getMaterialCount(const VKRT* vkrt, uint32_t* outMaterialCount);
 VKRT_HOST_API VKRT_Result VKRT_getMaterialSnapshot(const VKRT* vkrt, uint32_t materialIndex, VKRT_MaterialSnapshot* outMaterial);
 VKRT_HOST_API VKRT_Result VKRT_getTextureCount(const VKRT* vkrt, uint32_t* outTextureCount);
+VKRT_HOST_API VKRT_Result VKRT_getTextureSnapshot(const VKRT* vkrt, uint32_t textureIndex, VKRT_TextureSnapshot* outTexture); /* vkrt.h:78 */
 VKRT_HOST_API VKRT_Result VKRT_addTextureFromPixels(VKRT* vkrt, const VKRT_TextureUpload* upload, uint32_t* outTextureIndex);
+VKRT_HOST_API VKRT_Result VKRT_addTextureFromFile(VKRT* vkrt, const char* path, const char* name, uint32_t colorSpace, uint32_t* outTextureIndex); /* vkrt.h:80-86 */
+VKRT_HOST_API VKRT_Result VKRT_removeTexture(VKRT* vkrt, uint32_t textureIndex); /* vkrt.h:87 */
+VKRT_HOST_API VKRT_Result VKRT_addTexturesBatch(VKRT* vkrt, const VKRT_TextureUpload* uploads, size_t uploadCount, uint32_t* outTextureIndices); /* vkrt.h:88-93 */
 VKRT_HOST_API VKRT_Result VKRT_setMaterialTexture(VKRT* vkrt, uint32_t materialIndex, uint32_t textureSlot, uint32_t textureIndex);
 VKRT_HOST_API VKRT_Result VKRT_addMaterial(VKRT* vkrt, const Material* material, const char* name, uint32_t* outMaterialIndex);
 VKRT_HOST_API VKRT_Result VKRT_setMaterialName(VKRT* vkrt, uint32_t materialIndex, const char* name);
@@ -235,6 +249,18 @@ VKRT_HOST_API void VKRT_decomposeMeshTransform(vkrt_mat4 worldTransform, vkrt_ve
 VKRT_HOST_API void VKRT_decomposeMeshNodeTransform(vkrt_mat4 worldTransform, vkrt_vec3 outPosition, vkrt_vec3 outRotation, vkrt_vec3 outScale);
 /* src/core/utility/packing.c:144-156 */
 VKRT_HOST_API void VKRT_packShaderVertex(const Vertex* vertex, ShaderVertex* outVertex);
+
+/* image decoding (src/core/utility/image.h:9-27): PNG / JPEG / EXR -> RGBA8 / RGBA16 UNORM / RGBA16F / RGBA32F; return 1 on success */
+typedef struct VKRT_LoadedImage {
+    void* pixels;
+    uint32_t width;
+    uint32_t height;
+    uint32_t format;
+    uint32_t colorSpace;
+} VKRT_LoadedImage;
+VKRT_HOST_API int vkrtLoadImageFromFile(const char* path, uint32_t preferredColorSpace, VKRT_LoadedImage* outImage);
+VKRT_HOST_API int vkrtLoadImageFromMemory(const void* data, size_t size, const char* mimeType, uint32_t preferredColorSpace, VKRT_LoadedImage* outImage);
+VKRT_HOST_API void vkrtFreeLoadedImage(VKRT_LoadedImage* image);
 
 /* ---- app layer: scene files, model import, procedural benchmark scenes, offline render loop ----
  * (src/app/scene/controller.c:1528-1597, src/app/mesh/loader.c:2133-2179, src/app/render/benchmark.c:13-293) */

@@ -84,3 +84,90 @@ def both_backends(prep, w, h, spectral=False, **cuda_kw):
         b.upload(prep, rgb2spec=table)
         b.resize(w, h)
     return o, g
+
+
+def textured(w, h, spp=2):
+    """Every texture format, wrap mode and slot on one stage: a floor with an sRGB RGBA8 checker (repeat, KHR_texture_transform scale +
+    rotation), a tangent-space normal map and an RGBA16 metallic-roughness map; a sphere with an RGBA16F albedo (mirrored repeat); an alpha-MASK cut-out in front of it (stochastic alpha in the traversal); a light with an RGBA32F emissive map (clamp);
+    and a lat-long RGBA32F environment."""
+    rng = np.random.default_rng(0x7E87)
+    yy, xx = np.mgrid[0:32, 0:32]
+    checker = ((xx // 4 + yy // 4) & 1).astype(np.uint8)
+    albedo8 = np.zeros((32, 32, 4), np.uint8)
+    albedo8[..., 0] = 40 + 180 * checker
+    albedo8[..., 1] = 200 - 120 * checker
+    albedo8[..., 2] = (xx * 8).astype(np.uint8)
+    albedo8[..., 3] = 255
+    nx, ny = np.sin(xx / 2.5) * 0.35, np.cos(yy / 3.5) * 0.35
+    nz = np.sqrt(np.clip(1 - nx * nx - ny * ny, 0, 1))
+    normal8 = np.dstack([(nx * 0.5 + 0.5) * 255, (ny * 0.5 + 0.5) * 255, (nz * 0.5 + 0.5) * 255, np.full_like(nx, 255)]).round().astype(np.uint8)
+    mr16 = np.zeros((16, 16, 4), np.uint16)
+    mr16[..., 1] = (rng.random((16, 16)) * 40000 + 8000).astype(np.uint16)    # G = roughness
+    mr16[..., 2] = ((np.mgrid[0:16, 0:16][1] // 8) * 65535).astype(np.uint16)   # B = metallic
+    mr16[..., 3] = 65535
+    sphere16f = np.ones((8, 16, 4), np.float16)
+    sphere16f[..., :3] = rng.random((8, 16, 3)).astype(np.float16) * 0.8 + 0.1
+    cut8 = np.full((16, 16, 4), 255, np.uint8)
+    cut8[..., :3] = (230, 200, 60)
+    cut8[..., 3] = np.where(((xx[:16, :16] - 8) ** 2 + (yy[:16, :16] - 8) ** 2) < 30, 0, 255).astype(np.uint8)
+    emis32 = np.ones((4, 4, 4), np.float32)
+    emis32[..., :3] = rng.random((4, 4, 3)).astype(np.float32) * 0.5 + 0.5
+    tt, pp = (np.arange(16) + 0.5) / 16 * np.pi, (np.arange(32) + 0.5) / 32 * 2 * np.pi
+    env32 = np.ones((16, 32, 4), np.float32)
+    env32[..., 0] = 0.2 + 0.6 * np.clip(np.cos(tt), 0, 1)[:, None]
+    env32[..., 1] = 0.3 + 0.2 * np.sin(pp)[None, :]
+    env32[..., 2] = 0.5 + 0.4 * np.clip(np.cos(tt), 0, 1)[:, None]
+
+    def tex(px, fmt, cs):
+        return dict(pixels=px, width=px.shape[1], height=px.shape[0], format=fmt, colorSpace=cs)
+    textures = [tex(albedo8, 0, 0), tex(normal8, 0, 1), tex(mr16, 1, 1), tex(sphere16f.view(np.uint16), 2, 1), tex(cut8, 0, 0), tex(emis32, 3, 1), tex(env32, 3, 1)]
+    REPEAT, CLAMP, MIRROR = 10497, 33071, 33648
+    mats = np.zeros(5, hr.MATERIAL)
+    mats[:] = hr.default_material()
+    floor = hr.default_material()
+    floor["baseColorTextureIndex"], floor["normalTextureIndex"], floor["metallicRoughnessTextureIndex"] = 0, 1, 2
+    floor["baseColorTextureTransform"] = (3.0, 3.0, 0.25, 0.1)
+    floor["textureRotations"] = (0.3, 0.0, 0.0, 0.0)
+    floor["normalTextureScale"] = 0.8
+    floor["metallicRoughnessTextureWrap"] = CLAMP | (MIRROR << 16)
+    floor["roughness"], floor["metallic"] = 1.0, 1.0
+    mats[1] = hr.sanitize_material(floor, texture_count=len(textures))
+    ball = hr.default_material()
+    ball["baseColorTextureIndex"] = 3
+    ball["baseColorTextureWrap"] = MIRROR | (MIRROR << 16)
+    ball["baseColorTextureTransform"] = (2.0, 1.5, 0.0, 0.0)
+    ball["roughness"] = 0.35
+    mats[2] = hr.sanitize_material(ball, texture_count=len(textures))
+    cut = hr.default_material()
+    cut["baseColorTextureIndex"] = 4
+    cut["alphaMode"], cut["alphaCutoff"] = 1, 0.5
+    mats[3] = hr.sanitize_material(cut, texture_count=len(textures))
+    lamp = hr.default_material()
+    lamp["emissionLuminance"], lamp["emissiveTextureIndex"] = 18.0, 5
+    lamp["emissiveTextureWrap"] = CLAMP | (CLAMP << 16)
+    mats[4] = hr.sanitize_material(lamp, texture_count=len(textures))
+    meshes = []
+    f = hr.quad_mesh("floor", 2.0)
+    f.material_index = 1
+    meshes.append(f)
+    s = hr.uv_sphere_mesh("ball", 0.55, 24, 12)
+    s.world = hr.build_mesh_transform((0.1, 0.2, 0.56), (0, 0, 30), (1, 1, 1))
+    s.material_index = 2
+    meshes.append(s)
+    c = hr.quad_mesh("cutout", 0.6)
+    c.world = hr.build_mesh_transform((-0.2, -0.9, 0.7), (80, 0, 10), (1, 1, 1))
+    c.material_index = 3
+    c.render_backfaces = 1
+    meshes.append(c)
+    lq = hr.quad_mesh("lamp", 0.5)
+    lq.world = hr.build_mesh_transform((0, 0, 2.2), (180, 0, 0), (1, 1, 1))
+    lq.material_index = 4
+    meshes.append(lq)
+    st = hr.Settings(camera_pos=(0.4, -3.2, 1.5), camera_target=(0, 0, 0.4), vfov=38.0)
+    scene = hr.Scene(meshes=meshes, materials=mats, settings=st, textures=textures)
+    prep = scene.prepare(w, h)
+    prep["sceneData"]["samplesPerPixel"] = spp
+    prep["sceneData"]["environmentTextureIndex"] = 6
+    prep["sceneData"]["environmentLight"] = (1.0, 1.0, 1.0, 1.0)
+    prep["sceneData"]["environmentRotation"] = 25.0
+    return prep

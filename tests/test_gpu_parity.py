@@ -96,6 +96,22 @@ def test_soup_ids_and_random_rays(accel):
     assert np.array_equal(o.trace_rays(rays, any_hit=True)[:, 0], g.trace_rays(rays, any_hit=True)[:, 0])
 
 
+@pytest.mark.parametrize("mode", ["rgb", "hero"])
+def test_textured_materials_alpha_cutout_and_environment_map(mode):
+    """All four texture formats, the three wrap modes, KHR_texture_transform, normal / metallic-roughness / emissive maps, a stochastic
+    alpha-MASK cut-out inside the traversal and a lat-long environment map (material/textures.slang, light/environment.slang)."""
+    w, h = 144, 96
+    prep = scenes.textured(w, h, spp=4)
+    spectral = mode != "rgb"
+    if spectral:
+        prep["sceneData"]["packedRenderSettings"] = H.hr.pack_render_settings(0, 1, 1)   # tone mapping none, spectral, hero
+    o, g = scenes.both_backends(prep, w, h, spectral=spectral)
+    _check_ids(o, g, prep["sceneData"])
+    o.render(prep["sceneData"], frames=2)
+    g.render(prep["sceneData"], frames=2)
+    _check_images(o, g, frac=0.985, rel_rmse=0.08)
+
+
 @pytest.mark.parametrize("debug_mode", [1, 2, 3, 4, 5, 12, 13, 14, 15, 16])
 def test_debug_views(debug_mode):
     w = h = 64

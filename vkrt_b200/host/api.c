@@ -2,6 +2,7 @@
 #include <time.h>
 
 #include "host_state.h"
+#include "image_decode.h"
 #include "../csrc/tiles.h"
 
 static double nowSeconds(void) {
@@ -481,21 +482,125 @@ VKRT_Result VKRT_getTextureCount(const VKRT* v, uint32_t* out) {
     *out = v->textureCount;
     return VKRT_SUCCESS;
 }
+/* users of a texture: material slots that name it, plus the environment (scene/textures.c:374-381) */
+static uint32_t textureMaterialUsers(const VKRT* v, uint32_t textureIndex) {
+    uint32_t users = 0;
+    for (uint32_t i = 0; i < v->materialCount; i++) {
+        const Material* m = &v->materials[i].material;
+        users += (m->baseColorTextureIndex == textureIndex) + (m->metallicRoughnessTextureIndex == textureIndex) + (m->normalTextureIndex == textureIndex) +
+                 (m->emissiveTextureIndex == textureIndex);
+    }
+    return users;
+}
+static uint32_t textureUsers(const VKRT* v, uint32_t textureIndex) {
+    return textureMaterialUsers(v, textureIndex) + (v->sceneSettings.environmentTextureIndex == textureIndex ? 1u : 0u);
+}
+VKRT_Result VKRT_getTextureSnapshot(const VKRT* v, uint32_t textureIndex, VKRT_TextureSnapshot* out) {
+    if (!v || !out || textureIndex >= v->textureCount) return VKRT_ERROR_INVALID_ARGUMENT;
+    const HostTexture* t = &v->textures[textureIndex];
+    memset(out, 0, sizeof(*out));
+    out->width = t->width; out->height = t->height; out->format = t->format; out->colorSpace = t->colorSpace;
+    out->useCount = textureMaterialUsers(v, textureIndex);
+    memcpy(out->name, t->name, VKRT_NAME_LEN);
+    return VKRT_SUCCESS;
+}
+/* scene/textures.c:438-482: all or nothing */
+VKRT_Result VKRT_addTexturesBatch(VKRT* v, const VKRT_TextureUpload* uploads, size_t uploadCount, uint32_t* outIndices) {
+    if (!v || !uploads || uploadCount == 0u) return VKRT_ERROR_INVALID_ARGUMENT;
+    VKRT_Result ready = requireReady(v);
+    if (ready != VKRT_SUCCESS) return ready;
+    for (size_t i = 0; i < uploadCount; i++) {
+        const VKRT_TextureUpload* up = &uploads[i];
+        if (!up->pixels || up->width == 0 || up->height == 0 || texelSize(up->format) == 0) return VKRT_ERROR_INVALID_ARGUMENT;
+        if (up->colorSpace == VKRT_TEXTURE_COLOR_SPACE_SRGB && up->format != VKRT_TEXTURE_FORMAT_RGBA8_UNORM) return VKRT_ERROR_INVALID_ARGUMENT;
+    }
+    if ((size_t)v->textureCount + uploadCount > VKRT_MAX_BINDLESS_TEXTURES) return VKRT_ERROR_OPERATION_FAILED;
+    const uint32_t before = v->textureCount;
+    for (size_t i = 0; i < uploadCount; i++) {
+        VKRT_Result r = VKRT_addTextureFromPixels(v, &uploads[i], outIndices ? &outIndices[i] : NULL);
+        if (r != VKRT_SUCCESS) {
+            while (v->textureCount > before) { free(v->textures[v->textureCount - 1u].pixels); v->textureCount--; }
+            return r;
+        }
+    }
+    return VKRT_SUCCESS;
+}
+/* scene/textures.c:484-516 + utility/image.c: decode a PNG / JPEG / EXR file and add it */
+VKRT_Result VKRT_addTextureFromFile(VKRT* v, const char* path, const char* name, uint32_t colorSpace, uint32_t* outIndex) {
+    if (outIndex) *outIndex = VKRT_INVALID_INDEX;
+    if (!v || !path || !path[0] || (colorSpace != VKRT_TEXTURE_COLOR_SPACE_SRGB && colorSpace != VKRT_TEXTURE_COLOR_SPACE_LINEAR)) return VKRT_ERROR_INVALID_ARGUMENT;
+    VKRT_Result ready = requireReady(v);
+    if (ready != VKRT_SUCCESS) return ready;
+    FILE* probe = fopen(path, "rb");
+    if (!probe) return VKRT_ERROR_INVALID_ARGUMENT;   /* resolveExistingPath failure */
+    fclose(probe);
+    HostImage image;
+    char why[256] = "";
+    if (!hostLoadImageFile(path, colorSpace, &image, why, sizeof(why))) return hostFail(v, VKRT_ERROR_OPERATION_FAILED, "%s", why);
+    const char* base = strrchr(path, '/');
+    VKRT_TextureUpload up = {name && name[0] ? name : (base ? base + 1 : path), image.pixels, image.width, image.height, image.format, image.colorSpace};
+    VKRT_Result r = VKRT_addTextureFromPixels(v, &up, outIndex);
+    hostFreeImage(&image);
+    return r;
+}
+/* scene/textures.c:518-578: refuses while a material still uses it; later indices shift down by one */
+VKRT_Result VKRT_removeTexture(VKRT* v, uint32_t textureIndex) {
+    VKRT_Result ready = requireReady(v);
+    if (ready != VKRT_SUCCESS) return ready;
+    if (textureIndex >= v->textureCount) return VKRT_ERROR_INVALID_ARGUMENT;
+    if (v->sceneSettings.environmentTextureIndex == textureIndex) v->sceneSettings.environmentTextureIndex = VKRT_INVALID_INDEX;
+    if (textureMaterialUsers(v, textureIndex) != 0u) return VKRT_ERROR_OPERATION_FAILED;
+    free(v->textures[textureIndex].pixels);
+    memmove(&v->textures[textureIndex], &v->textures[textureIndex + 1u], (size_t)(v->textureCount - textureIndex - 1u) * sizeof(HostTexture));
+    v->textureCount--;
+    for (uint32_t i = 0; i < v->materialCount; i++) {
+        Material* m = &v->materials[i].material;
+        uint32_t* idx[4] = {&m->baseColorTextureIndex, &m->metallicRoughnessTextureIndex, &m->normalTextureIndex, &m->emissiveTextureIndex};
+        for (int k = 0; k < 4; k++)
+            if (*idx[k] != VKRT_INVALID_INDEX && *idx[k] > textureIndex) (*idx[k])--;
+    }
+    uint32_t env = v->sceneSettings.environmentTextureIndex;   /* scene/environment.c:69-78 */
+    if (env != VKRT_INVALID_INDEX && env > textureIndex) v->sceneSettings.environmentTextureIndex = env - 1u;
+    v->texturesDirty = v->materialsDirty = 1;
+    hostResetSceneData(v);
+    return VKRT_SUCCESS;
+}
+/* scene/environment.c:9-37: the environment must be LINEAR; the texture it replaces is dropped when nothing else uses it */
+static VKRT_Result replaceEnvironmentTexture(VKRT* v, uint32_t next) {
+    uint32_t previous = v->sceneSettings.environmentTextureIndex;
+    if (next != VKRT_INVALID_INDEX && (next >= v->textureCount || v->textures[next].colorSpace != VKRT_TEXTURE_COLOR_SPACE_LINEAR)) return VKRT_ERROR_INVALID_ARGUMENT;
+    if (previous == next) return VKRT_SUCCESS;
+    v->sceneSettings.environmentTextureIndex = VKRT_INVALID_INDEX;
+    if (previous != VKRT_INVALID_INDEX && previous < v->textureCount && textureUsers(v, previous) == 0u) {
+        VKRT_Result r = VKRT_removeTexture(v, previous);
+        if (r != VKRT_SUCCESS) { v->sceneSettings.environmentTextureIndex = previous; return r; }
+        if (next != VKRT_INVALID_INDEX && previous < next) next--;
+    }
+    v->sceneSettings.environmentTextureIndex = next;
+    hostResetSceneData(v);
+    return VKRT_SUCCESS;
+}
 VKRT_Result VKRT_setEnvironmentTextureFromPixels(VKRT* v, const VKRT_TextureUpload* up) {
     uint32_t idx = VKRT_INVALID_INDEX;
     VKRT_Result r = VKRT_addTextureFromPixels(v, up, &idx);
     if (r != VKRT_SUCCESS) return r;
-    v->sceneSettings.environmentTextureIndex = idx;
-    hostResetSceneData(v);
-    return VKRT_SUCCESS;
+    r = replaceEnvironmentTexture(v, idx);
+    if (r != VKRT_SUCCESS && idx < v->textureCount && textureUsers(v, idx) == 0u) VKRT_removeTexture(v, idx);
+    return r;
+}
+VKRT_Result VKRT_setEnvironmentTextureFromFile(VKRT* v, const char* path) {
+    if (!v || !path || !path[0]) return VKRT_ERROR_INVALID_ARGUMENT;
+    uint32_t idx = VKRT_INVALID_INDEX;
+    VKRT_Result r = VKRT_addTextureFromFile(v, path, NULL, VKRT_TEXTURE_COLOR_SPACE_LINEAR, &idx);
+    if (r != VKRT_SUCCESS) return r;
+    r = replaceEnvironmentTexture(v, idx);
+    if (r != VKRT_SUCCESS && idx < v->textureCount && textureUsers(v, idx) == 0u) VKRT_removeTexture(v, idx);
+    return r;
 }
 VKRT_Result VKRT_clearEnvironmentTexture(VKRT* v) {
     VKRT_Result ready = requireReady(v);
     if (ready != VKRT_SUCCESS) return ready;
-    if (v->sceneSettings.environmentTextureIndex == VKRT_INVALID_INDEX) return VKRT_SUCCESS;
-    v->sceneSettings.environmentTextureIndex = VKRT_INVALID_INDEX;
-    hostResetSceneData(v);
-    return VKRT_SUCCESS;
+    return replaceEnvironmentTexture(v, VKRT_INVALID_INDEX);
 }
 
 /* ---- materials ------------------------------------------------------------------------------------------------------------ */
@@ -541,11 +646,28 @@ VKRT_Result VKRT_setMaterialTexture(VKRT* v, uint32_t materialIndex, uint32_t sl
     VKRT_Result ready = requireReady(v);
     if (ready != VKRT_SUCCESS) return ready;
     if (materialIndex >= v->materialCount || slot >= VKRT_MATERIAL_TEXTURE_SLOT_COUNT) return VKRT_ERROR_INVALID_ARGUMENT;
-    if (textureIndex != VKRT_INVALID_INDEX && textureIndex >= v->textureCount) return VKRT_ERROR_INVALID_ARGUMENT;
+    if (textureIndex != VKRT_INVALID_INDEX) {
+        if (textureIndex >= v->textureCount) return VKRT_ERROR_INVALID_ARGUMENT;
+        /* colour slots take sRGB or linear data, the data slots only linear (scene/textures.c:94-105) */
+        const int colourSlot = slot == VKRT_MATERIAL_TEXTURE_SLOT_BASE_COLOR || slot == VKRT_MATERIAL_TEXTURE_SLOT_EMISSIVE;
+        const uint32_t cs = v->textures[textureIndex].colorSpace;
+        if (!(cs == VKRT_TEXTURE_COLOR_SPACE_LINEAR || (colourSlot && cs == VKRT_TEXTURE_COLOR_SPACE_SRGB))) return VKRT_ERROR_INVALID_ARGUMENT;
+    }
     Material m = v->materials[materialIndex].material;
     uint32_t* idx[4] = {&m.baseColorTextureIndex, &m.metallicRoughnessTextureIndex, &m.normalTextureIndex, &m.emissiveTextureIndex};
+    uint32_t* wrap[4] = {&m.baseColorTextureWrap, &m.metallicRoughnessTextureWrap, &m.normalTextureWrap, &m.emissiveTextureWrap};
+    float* xf[4] = {m.baseColorTextureTransform, m.metallicRoughnessTextureTransform, m.normalTextureTransform, m.emissiveTextureTransform};
+    if (*idx[slot] == textureIndex) return VKRT_SUCCESS;
+    const uint32_t previous = *idx[slot];
     *idx[slot] = textureIndex;
-    return VKRT_setMaterial(v, materialIndex, &m);
+    *wrap[slot] = VKRT_TEXTURE_WRAP_DEFAULT;
+    m.textureTexcoordSets &= ~(0xffu << (8u * slot));
+    xf[slot][0] = xf[slot][1] = 1.0f; xf[slot][2] = xf[slot][3] = 0.0f;
+    m.textureRotations[slot] = 0.0f;
+    VKRT_Result r = VKRT_setMaterial(v, materialIndex, &m);
+    if (r != VKRT_SUCCESS) return r;
+    if (previous != VKRT_INVALID_INDEX && previous < v->textureCount && textureUsers(v, previous) == 0u) return VKRT_removeTexture(v, previous); /* api/mesh.c:397-402 */
+    return VKRT_SUCCESS;
 }
 VKRT_Result VKRT_getMaterialCount(const VKRT* v, uint32_t* out) {
     if (!v || !out) return VKRT_ERROR_INVALID_ARGUMENT;

@@ -10,7 +10,9 @@
  *     (:1646-1754), otherwise a fallback cross(up, n) (:1418-1446);
  *   - materials: metallic-roughness / specular-glossiness factors, KHR_materials_{specular, ior, transmission, volume,
  *     clearcoat, sheen, emissive_strength}, alpha mode / cutoff, doubleSided (:942-1078,:1472-1555).
- * Embedded images are not decoded (no PNG/JPEG decoder is vendored here); textured slots are left unbound with a warning. */
+ * Images (bufferView, data: URI or external file; PNG / JPEG / EXR through image_decode.c) are decoded once per (image, colour space)
+ * pair in the reference's order (loader.c:318-357) and bound with sampler wrap modes, texture coordinate set and KHR_texture_transform
+ * (loader.c:359-404, 905-940, 1486-1540). */
 #include "gltf_import.h"
 
 #include <math.h>
@@ -19,6 +21,7 @@
 #include <string.h>
 
 #include "hjson.h"
+#include "image_decode.h"
 #include "hmath.h"
 
 typedef struct {
@@ -28,7 +31,9 @@ typedef struct {
     GltfImport* out;
     char* error;
     size_t errorSize;
-    int warnedTextures;
+    const char* sourcePath;   /* the .glb, for relative image URIs */
+    struct { int image; uint32_t colorSpace; } refs[4096];
+    uint32_t refCount;
 } ImportCtx;
 
 static int fail(ImportCtx* c, const char* what) {
@@ -199,10 +204,148 @@ static void generateTangents(Vertex* v, size_t nv, const uint32_t* idx, size_t n
 /* ---- materials -------------------------------------------------------------------------------------------------------- */
 static float max3f(float a, float b, float c) { return fmaxf(a, fmaxf(b, c)); }
 
-static void warnTexture(ImportCtx* c, const hj_value* textureInfo) {
-    if (textureInfo && !c->warnedTextures) {
-        fprintf(stderr, "[vkrt host] glTF import: embedded textures are not decoded by this build; textured slots stay unbound\n");
-        c->warnedTextures = 1;
+/* ---- textures (loader.c:262-404) ---------------------------------------------------------------------------------------------- */
+/* texture coordinate set of a texture view: KHR_texture_transform.texCoord overrides textureInfo.texCoord (loader.c:378-384) */
+static uint32_t textureViewTexcoordSet(const hj_value* view) {
+    const hj_value* xf = hj_get(hj_get(view, "extensions"), "KHR_texture_transform");
+    const hj_value* t = hj_get(xf, "texCoord");
+    if (t && t->type == HJ_NUMBER && t->number >= 0.0) return (uint32_t)t->number;
+    double v = hj_number(hj_get(view, "texCoord"), 0.0);
+    return v >= 0.0 ? (uint32_t)v : 0u;
+}
+/* image index behind a texture view, -1 when there is none or the view uses a texture coordinate set above 1 (unsupported) */
+static int textureViewImage(ImportCtx* c, const hj_value* view) {
+    if (!view || view->type != HJ_OBJECT) return -1;
+    const hj_value* tex = hj_at(hj_get(c->doc, "textures"), (size_t)hj_number(hj_get(view, "index"), -1));
+    if (!tex) return -1;
+    const hj_value* src = hj_get(tex, "source");
+    if (!src || src->type != HJ_NUMBER || src->number < 0.0 || (size_t)src->number >= hj_count(hj_get(c->doc, "images"))) return -1;
+    if (textureViewTexcoordSet(view) > 1u) return -1;
+    return (int)src->number;
+}
+static void collectReference(ImportCtx* c, const hj_value* view, uint32_t colorSpace) {
+    int image = textureViewImage(c, view);
+    if (image < 0) return;
+    for (uint32_t i = 0; i < c->refCount; i++)
+        if (c->refs[i].image == image && c->refs[i].colorSpace == colorSpace) return;
+    if (c->refCount < sizeof(c->refs) / sizeof(c->refs[0])) { c->refs[c->refCount].image = image; c->refs[c->refCount].colorSpace = colorSpace; c->refCount++; }
+}
+static const hj_value* baseColorView(const hj_value* gm) {  /* loader.c:311-315 */
+    const hj_value* sg = hj_get(hj_get(gm, "extensions"), "KHR_materials_pbrSpecularGlossiness");
+    if (sg) return hj_get(sg, "diffuseTexture");
+    return hj_get(hj_get(gm, "pbrMetallicRoughness"), "baseColorTexture");
+}
+static int base64Value(int ch) {
+    if (ch >= 'A' && ch <= 'Z') return ch - 'A';
+    if (ch >= 'a' && ch <= 'z') return ch - 'a' + 26;
+    if (ch >= '0' && ch <= '9') return ch - '0' + 52;
+    if (ch == '+' || ch == '-') return 62;
+    if (ch == '/' || ch == '_') return 63;
+    return -1;
+}
+static unsigned char* decodeDataUri(const char* uri, size_t* outSize, char* mime, size_t mimeLen) {
+    const char* comma = strchr(uri, ',');
+    if (!comma || !strstr(uri, ";base64")) return NULL;
+    size_t ml = (size_t)(strcspn(uri + 5, ";,"));
+    snprintf(mime, mimeLen, "%.*s", (int)ml, uri + 5);
+    size_t n = strlen(comma + 1);
+    unsigned char* out = (unsigned char*)malloc(n * 3 / 4 + 4);
+    if (!out) return NULL;
+    uint32_t acc = 0;
+    int bits = 0;
+    size_t o = 0;
+    for (const char* p = comma + 1; *p; p++) {
+        int v = base64Value((unsigned char)*p);
+        if (v < 0) continue;
+        acc = (acc << 6) | (uint32_t)v;
+        bits += 6;
+        if (bits >= 8) { bits -= 8; out[o++] = (unsigned char)((acc >> bits) & 0xffu); }
+    }
+    *outSize = o;
+    return out;
+}
+static void percentDecode(char* s) {
+    char* w = s;
+    for (const char* r = s; *r; r++) {
+        if (r[0] == '%' && r[1] && r[2]) {
+            char hex[3] = {r[1], r[2], 0};
+            *w++ = (char)strtol(hex, NULL, 16);
+            r += 2;
+        } else {
+            *w++ = *r;
+        }
+    }
+    *w = 0;
+}
+/* loader.c:429-455 decodeTextureImage: external file, else bufferView bytes (data: URIs are decoded here as well) */
+static int decodeImageReference(ImportCtx* c, int imageIndex, uint32_t colorSpace, GltfTexture* out) {
+    const hj_value* image = hj_at(hj_get(c->doc, "images"), (size_t)imageIndex);
+    const char* uri = hj_string(hj_get(image, "uri"), NULL);
+    const char* mime = hj_string(hj_get(image, "mimeType"), NULL);
+    HostImage decoded;
+    char why[256] = "";
+    int ok = 0;
+    if (uri && uri[0] && strncmp(uri, "data:", 5) != 0) {
+        char rel[4096], full[8192];
+        snprintf(rel, sizeof(rel), "%s", uri);
+        percentDecode(rel);
+        const char* slash = strrchr(c->sourcePath, '/');
+        if (rel[0] == '/' || !slash) snprintf(full, sizeof(full), "%s", rel);
+        else snprintf(full, sizeof(full), "%.*s/%s", (int)(slash - c->sourcePath), c->sourcePath, rel);
+        ok = hostLoadImageFile(full, colorSpace, &decoded, why, sizeof(why));
+    } else if (uri && uri[0]) {
+        char uriMime[64] = "";
+        size_t n = 0;
+        unsigned char* bytes = decodeDataUri(uri, &n, uriMime, sizeof(uriMime));
+        if (bytes) ok = hostDecodeImage(bytes, n, mime ? mime : uriMime, "data URI", colorSpace, &decoded, why, sizeof(why));
+        free(bytes);
+    } else {
+        const hj_value* bv = hj_at(hj_get(c->doc, "bufferViews"), (size_t)hj_number(hj_get(image, "bufferView"), -1));
+        size_t off = (size_t)hj_number(hj_get(bv, "byteOffset"), 0), len = (size_t)hj_number(hj_get(bv, "byteLength"), 0);
+        if (bv && (int)hj_number(hj_get(bv, "buffer"), 0) == 0 && c->bin && len <= c->binSize && off <= c->binSize - len)
+            ok = hostDecodeImage(c->bin + off, len, mime, "glTF bufferView", colorSpace, &decoded, why, sizeof(why));
+        else snprintf(why, sizeof(why), "image %d has no readable data", imageIndex);
+    }
+    if (!ok) {
+        if (c->error && c->errorSize && !c->error[0]) snprintf(c->error, c->errorSize, "texture image %d: %s", imageIndex, why);
+        return 0;
+    }
+    out->pixels = decoded.pixels; out->width = decoded.width; out->height = decoded.height; out->format = decoded.format; out->colorSpace = decoded.colorSpace;
+    const char* name = hj_string(hj_get(image, "name"), NULL);   /* loader.c:457-465: image name, else texture name, else "Texture" */
+    if (!name || !name[0]) {
+        const hj_value* textures = hj_get(c->doc, "textures");
+        for (size_t t = 0; t < hj_count(textures) && (!name || !name[0]); t++)
+            if ((int)hj_number(hj_get(hj_at(textures, t), "source"), -1) == imageIndex) name = hj_string(hj_get(hj_at(textures, t), "name"), NULL);
+    }
+    snprintf(out->name, sizeof(out->name), "%s", name && name[0] ? name : "Texture");
+    return 1;
+}
+/* Binds a texture view to one material slot: index into GltfImport.textures, wrap modes, texcoord set, transform (loader.c:905-940). */
+static void bindTexture(ImportCtx* c, Material* m, uint32_t slot, const hj_value* view, uint32_t colorSpace) {
+    int image = textureViewImage(c, view);
+    if (image < 0) return;
+    uint32_t found = VKRT_INVALID_INDEX;
+    for (uint32_t i = 0; i < c->refCount; i++)
+        if (c->refs[i].image == image && c->refs[i].colorSpace == colorSpace) found = i;
+    if (found == VKRT_INVALID_INDEX) return;
+    uint32_t* idx[4] = {&m->baseColorTextureIndex, &m->metallicRoughnessTextureIndex, &m->normalTextureIndex, &m->emissiveTextureIndex};
+    uint32_t* wrap[4] = {&m->baseColorTextureWrap, &m->metallicRoughnessTextureWrap, &m->normalTextureWrap, &m->emissiveTextureWrap};
+    float* xf[4] = {m->baseColorTextureTransform, m->metallicRoughnessTextureTransform, m->normalTextureTransform, m->emissiveTextureTransform};
+    *idx[slot] = found;
+    const hj_value* tex = hj_at(hj_get(c->doc, "textures"), (size_t)hj_number(hj_get(view, "index"), -1));
+    const hj_value* sampler = hj_at(hj_get(c->doc, "samplers"), (size_t)hj_number(hj_get(tex, "sampler"), -1));
+    uint32_t ws = (uint32_t)hj_number(hj_get(sampler, "wrapS"), 0), wt = (uint32_t)hj_number(hj_get(sampler, "wrapT"), 0);
+    *wrap[slot] = (ws ? ws : VKRT_TEXTURE_WRAP_REPEAT) | ((wt ? wt : VKRT_TEXTURE_WRAP_REPEAT) << 16u);   /* loader.c:359-363 */
+    m->textureTexcoordSets = (m->textureTexcoordSets & ~(0xffu << (8u * slot))) | ((textureViewTexcoordSet(view) & 0xffu) << (8u * slot));
+    xf[slot][0] = xf[slot][1] = 1.0f; xf[slot][2] = xf[slot][3] = 0.0f;
+    m->textureRotations[slot] = 0.0f;
+    const hj_value* kt = hj_get(hj_get(view, "extensions"), "KHR_texture_transform");
+    if (kt) {   /* loader.c:386-404: scale.xy, offset.xy, rotation */
+        float sc[2] = {1.0f, 1.0f}, of[2] = {0.0f, 0.0f};
+        hj_floats(hj_get(kt, "scale"), sc, 2);
+        hj_floats(hj_get(kt, "offset"), of, 2);
+        xf[slot][0] = sc[0]; xf[slot][1] = sc[1]; xf[slot][2] = of[0]; xf[slot][3] = of[1];
+        m->textureRotations[slot] = (float)hj_number(hj_get(kt, "rotation"), 0.0);
     }
 }
 
@@ -217,15 +360,15 @@ static Material convertMaterial(ImportCtx* c, const hj_value* gm, Material m) {
         hj_floats(hj_get(sg, "diffuseFactor"), f4, 4);
         m.baseColor[0] = f4[0]; m.baseColor[1] = f4[1]; m.baseColor[2] = f4[2]; m.opacity = f4[3];
         m.roughness = 1.0f - (float)hj_number(hj_get(sg, "glossinessFactor"), 1.0);
-        warnTexture(c, hj_get(sg, "diffuseTexture"));
+        bindTexture(c, &m, VKRT_MATERIAL_TEXTURE_SLOT_BASE_COLOR, hj_get(sg, "diffuseTexture"), VKRT_TEXTURE_COLOR_SPACE_SRGB);
     } else if (pbr) {
         f4[0] = f4[1] = f4[2] = f4[3] = 1.0f;
         hj_floats(hj_get(pbr, "baseColorFactor"), f4, 4);
         m.baseColor[0] = f4[0]; m.baseColor[1] = f4[1]; m.baseColor[2] = f4[2]; m.opacity = f4[3];
         m.metallic = (float)hj_number(hj_get(pbr, "metallicFactor"), 1.0);
         m.roughness = (float)hj_number(hj_get(pbr, "roughnessFactor"), 1.0);
-        warnTexture(c, hj_get(pbr, "baseColorTexture"));
-        warnTexture(c, hj_get(pbr, "metallicRoughnessTexture"));
+        bindTexture(c, &m, VKRT_MATERIAL_TEXTURE_SLOT_BASE_COLOR, hj_get(pbr, "baseColorTexture"), VKRT_TEXTURE_COLOR_SPACE_SRGB);
+        bindTexture(c, &m, VKRT_MATERIAL_TEXTURE_SLOT_METALLIC_ROUGHNESS, hj_get(pbr, "metallicRoughnessTexture"), VKRT_TEXTURE_COLOR_SPACE_LINEAR);
     }
     const hj_value* e;
     if ((e = hj_get(ext, "KHR_materials_specular"))) m.specular = (float)hj_number(hj_get(e, "specularFactor"), 1.0);
@@ -258,9 +401,16 @@ static Material convertMaterial(ImportCtx* c, const hj_value* gm, Material m) {
         float mx = max3f(em[0], em[1], em[2]);
         if (mx > 0.0f) { m.emissionColor[0] = em[0] / mx; m.emissionColor[1] = em[1] / mx; m.emissionColor[2] = em[2] / mx; m.emissionLuminance = mx; }
         else { m.emissionColor[0] = m.emissionColor[1] = m.emissionColor[2] = 1.0f; m.emissionLuminance = 0.0f; }
-        warnTexture(c, hj_get(gm, "emissiveTexture"));
     }
-    warnTexture(c, hj_get(gm, "normalTexture"));
+    {   /* loader.c:1486-1540: normal map (scale > 0 else 1), then the emissive map */
+        const hj_value* nt = hj_get(gm, "normalTexture");
+        bindTexture(c, &m, VKRT_MATERIAL_TEXTURE_SLOT_NORMAL, nt, VKRT_TEXTURE_COLOR_SPACE_LINEAR);
+        if (m.normalTextureIndex != VKRT_INVALID_INDEX) {
+            float scale = (float)hj_number(hj_get(nt, "scale"), 1.0);
+            m.normalTextureScale = scale > 0.0f ? scale : 1.0f;
+        }
+        bindTexture(c, &m, VKRT_MATERIAL_TEXTURE_SLOT_EMISSIVE, hj_get(gm, "emissiveTexture"), VKRT_TEXTURE_COLOR_SPACE_SRGB);
+    }
     const char* am = hj_string(hj_get(gm, "alphaMode"), "OPAQUE");
     m.alphaMode = !strcmp(am, "MASK") ? VKRT_MATERIAL_ALPHA_MODE_MASK : (!strcmp(am, "BLEND") ? VKRT_MATERIAL_ALPHA_MODE_BLEND : VKRT_MATERIAL_ALPHA_MODE_OPAQUE);
     m.alphaCutoff = (float)hj_number(hj_get(gm, "alphaCutoff"), 0.5);
@@ -423,6 +573,8 @@ void gltfImportFree(GltfImport* imp) {
     free(imp->meshes);
     free(imp->materials);
     free(imp->materialNames);
+    for (uint32_t i = 0; i < imp->textureCount; i++) free(imp->textures[i].pixels);
+    free(imp->textures);
     memset(imp, 0, sizeof(*imp));
 }
 
@@ -463,7 +615,25 @@ int gltfImportFile(const char* path, GltfImport* out, char* error, size_t errorS
     /* materials */
     const hj_value* mats = hj_get(doc, "materials");
     uint32_t nm = (uint32_t)hj_count(mats);
-    if (nm) {
+    /* textures first: unique (image, colour space) pairs in material order (loader.c:318-357), decoded once each; a file whose image
+     * cannot be decoded fails to import, as upstream (loader.c:876-890) */
+    c.sourcePath = path;
+    for (uint32_t i = 0; i < nm; i++) {
+        const hj_value* gm = hj_at(mats, i);
+        collectReference(&c, baseColorView(gm), VKRT_TEXTURE_COLOR_SPACE_SRGB);
+        collectReference(&c, hj_get(hj_get(gm, "pbrMetallicRoughness"), "metallicRoughnessTexture"), VKRT_TEXTURE_COLOR_SPACE_LINEAR);
+        collectReference(&c, hj_get(gm, "normalTexture"), VKRT_TEXTURE_COLOR_SPACE_LINEAR);
+        collectReference(&c, hj_get(gm, "emissiveTexture"), VKRT_TEXTURE_COLOR_SPACE_SRGB);
+    }
+    if (c.refCount) {
+        out->textures = (GltfTexture*)calloc(c.refCount, sizeof(GltfTexture));
+        if (!out->textures) ok = fail(&c, "out of memory");
+        for (uint32_t i = 0; ok && i < c.refCount; i++) {
+            ok = decodeImageReference(&c, c.refs[i].image, c.refs[i].colorSpace, &out->textures[i]);
+            if (ok) out->textureCount = i + 1u;
+        }
+    }
+    if (ok && nm) {
         out->materials = (Material*)calloc(nm, sizeof(Material));
         out->materialNames = (char(*)[VKRT_NAME_LEN])calloc(nm, VKRT_NAME_LEN);
         if (!out->materials || !out->materialNames) ok = fail(&c, "out of memory");

@@ -15,12 +15,20 @@ typedef struct GltfMesh {
     char name[VKRT_NAME_LEN];
 } GltfMesh;
 
+typedef struct GltfTexture {   /* one decoded (image, colour space) pair; Material.*TextureIndex of this import index this list */
+    void* pixels;
+    uint32_t width, height, format, colorSpace;
+    char name[VKRT_NAME_LEN];
+} GltfTexture;
+
 typedef struct GltfImport {
     GltfMesh* meshes;
     uint32_t meshCount;
     Material* materials;
     char (*materialNames)[VKRT_NAME_LEN];
     uint32_t materialCount;
+    GltfTexture* textures;
+    uint32_t textureCount;
 } GltfImport;
 
 int gltfImportFile(const char* path, GltfImport* out, char* error, size_t errorSize); /* 1 = ok */

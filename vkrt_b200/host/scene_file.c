@@ -88,6 +88,24 @@ static Material parseMaterialJson(const hj_value* o) {
 }
 
 /* Uploads every mesh of one .glb as a batch; returns the index of its first mesh. */
+/* The import's decoded textures, appended in import order; *outTextureBase is the scene index of the import's texture 0. */
+static VKRT_Result uploadImportTextures(VKRT* vkrt, const GltfImport* imp, uint32_t* outTextureBase) {
+    *outTextureBase = vkrt->textureCount;
+    for (uint32_t i = 0; i < imp->textureCount; i++) {
+        const GltfTexture* t = &imp->textures[i];
+        VKRT_TextureUpload up = {t->name, t->pixels, t->width, t->height, t->format, t->colorSpace};
+        VKRT_Result r = VKRT_addTextureFromPixels(vkrt, &up, NULL);
+        if (r != VKRT_SUCCESS) return r;
+    }
+    return VKRT_SUCCESS;
+}
+static Material rebaseMaterialTextures(Material m, uint32_t textureBase) {
+    uint32_t* idx[4] = {&m.baseColorTextureIndex, &m.metallicRoughnessTextureIndex, &m.normalTextureIndex, &m.emissiveTextureIndex};
+    for (int k = 0; k < 4; k++)
+        if (*idx[k] != VKRT_INVALID_INDEX) *idx[k] += textureBase;
+    return m;
+}
+
 static VKRT_Result uploadImport(VKRT* vkrt, const GltfImport* imp, uint32_t* outFirst) {
     *outFirst = vkrt->meshCount;
     if (imp->meshCount == 0) return VKRT_SUCCESS;
@@ -118,8 +136,12 @@ VKRT_Result VKRT_appImportMesh(VKRT* vkrt, const char* glbPath, uint32_t* outFir
     VKRT_Result r = uploadImport(vkrt, &imp, &first);
     if (r == VKRT_SUCCESS) {
         /* standalone import: the file's materials are appended and assigned; node transforms are applied */
-        uint32_t materialBase = vkrt->materialCount;
-        for (uint32_t i = 0; i < imp.materialCount && r == VKRT_SUCCESS; i++) r = VKRT_addMaterial(vkrt, &imp.materials[i], imp.materialNames[i], NULL);
+        uint32_t materialBase = vkrt->materialCount, textureBase = 0;
+        r = uploadImportTextures(vkrt, &imp, &textureBase);
+        for (uint32_t i = 0; i < imp.materialCount && r == VKRT_SUCCESS; i++) {
+            Material m = rebaseMaterialTextures(imp.materials[i], textureBase);
+            r = VKRT_addMaterial(vkrt, &m, imp.materialNames[i], NULL);
+        }
         for (uint32_t i = 0; i < imp.meshCount && r == VKRT_SUCCESS; i++) {
             if (imp.meshes[i].materialIndex >= 0) r = VKRT_setMeshMaterialIndex(vkrt, first + i, materialBase + (uint32_t)imp.meshes[i].materialIndex);
             if (r == VKRT_SUCCESS) r = VKRT_setMeshTransformMatrix(vkrt, first + i, imp.meshes[i].world);
@@ -145,14 +167,14 @@ VKRT_Result VKRT_appLoadScene(VKRT* vkrt, const char* scenePath) {
     uint32_t* importFirst = NULL;
     uint32_t* importCount = NULL;
     uint32_t* savedToLoaded = NULL;
+    uint32_t* textureMap = NULL;
+    uint32_t textureMapCount = 0;
     hmat4* worlds = NULL;
     if (strcmp(hj_string(hj_get(root, "format"), ""), "vkrt.scene") != 0 || (int)hj_number(hj_get(root, "version"), 0) != 1) {
         r = hostFail(vkrt, VKRT_ERROR_OPERATION_FAILED, "%s: not a vkrt.scene version 1 document", scenePath);
         goto done;
     }
     if (vkrt->meshCount != 0) { r = hostFail(vkrt, VKRT_ERROR_OPERATION_FAILED, "VKRT_appLoadScene needs an empty scene"); goto done; }
-    if (hj_count(hj_get(root, "textureImports")) > 0 || hj_string(hj_get(root, "environmentTexturePath"), NULL))
-        fprintf(stderr, "[vkrt host] %s: texture imports need an image decoder that this build does not vendor; ignored\n", scenePath);
 
     /* 1. import every listed model (a file may repeat: its geometry dedups into instances) */
     char* pathCopy = strdup(scenePath);
@@ -171,7 +193,40 @@ VKRT_Result VKRT_appLoadScene(VKRT* vkrt, const char* scenePath) {
         if (!gltfImportFile(full, &imp, err, sizeof(err))) { r = hostFail(vkrt, VKRT_ERROR_OPERATION_FAILED, "import %s: %s", full, err); break; }
         r = uploadImport(vkrt, &imp, &importFirst[i]);
         importCount[i] = imp.meshCount;
+        /* the file's textures keep their import-order indices, which is what the saved materials name (controller.c:1586-1593) */
+        uint32_t textureBase = 0;
+        if (r == VKRT_SUCCESS) r = uploadImportTextures(vkrt, &imp, &textureBase);
         gltfImportFree(&imp);
+    }
+    /* 1b. standalone textures at their saved indices, then the environment map (controller.c:690-716,1274-1312) */
+    const hj_value* texImports = hj_get(root, "textureImports");
+    for (size_t k = 0; k < hj_count(texImports); k++) {
+        uint32_t saved = (uint32_t)hj_number(hj_get(hj_at(texImports, k), "index"), -1);
+        if (saved != VKRT_INVALID_INDEX && saved + 1u > textureMapCount) textureMapCount = saved + 1u;
+    }
+    textureMap = (uint32_t*)malloc((textureMapCount ? textureMapCount : 1u) * sizeof(uint32_t));
+    for (uint32_t k = 0; k < textureMapCount; k++) textureMap[k] = VKRT_INVALID_INDEX;
+    for (size_t k = 0; k < hj_count(texImports) && r == VKRT_SUCCESS; k++) {
+        const hj_value* jt = hj_at(texImports, k);
+        const char* rel = hj_string(hj_get(jt, "path"), NULL);
+        const hj_value* jIndex = hj_get(jt, "index");
+        const hj_value* jSpace = hj_get(jt, "colorSpace");
+        if (!rel || !jIndex || jIndex->type != HJ_NUMBER || !jSpace || jSpace->type != HJ_NUMBER) { r = hostFail(vkrt, VKRT_ERROR_OPERATION_FAILED, "textureImports[%zu] malformed", k); break; }
+        char full[4096];
+        if (rel[0] == '/') snprintf(full, sizeof(full), "%s", rel);
+        else snprintf(full, sizeof(full), "%s/%s", baseDir, rel);
+        uint32_t loaded = VKRT_INVALID_INDEX;
+        r = VKRT_addTextureFromFile(vkrt, full, NULL, (uint32_t)jSpace->number, &loaded);
+        if (r != VKRT_SUCCESS) { hostFail(vkrt, r, "textureImports[%zu]: %s: %s", k, full, VKRT_lastError(vkrt)); break; }
+        textureMap[(uint32_t)jIndex->number] = loaded;
+    }
+    const char* envRel = hj_string(hj_get(root, "environmentTexturePath"), NULL);
+    if (r == VKRT_SUCCESS && envRel && envRel[0]) {
+        char full[4096];
+        if (envRel[0] == '/') snprintf(full, sizeof(full), "%s", envRel);
+        else snprintf(full, sizeof(full), "%s/%s", baseDir, envRel);
+        r = VKRT_setEnvironmentTextureFromFile(vkrt, full);
+        if (r != VKRT_SUCCESS) hostFail(vkrt, r, "environmentTexturePath %s: %s", full, VKRT_lastError(vkrt));
     }
     free(pathCopy);
     if (r != VKRT_SUCCESS) goto done;
@@ -217,6 +272,11 @@ VKRT_Result VKRT_appLoadScene(VKRT* vkrt, const char* scenePath) {
         const hj_value* body = hj_get(jm, "material");
         if (!body || body->type != HJ_OBJECT || !hj_string(hj_get(jm, "name"), NULL)) { r = hostFail(vkrt, VKRT_ERROR_OPERATION_FAILED, "materials[%zu] malformed", k); break; }
         Material m = parseMaterialJson(body);
+        {   /* saved texture indices -> loaded ones (controller.c:640-662 remapStandaloneTextureIndices) */
+            uint32_t* ti[4] = {&m.baseColorTextureIndex, &m.metallicRoughnessTextureIndex, &m.normalTextureIndex, &m.emissiveTextureIndex};
+            for (int q = 0; q < 4; q++)
+                if (*ti[q] != VKRT_INVALID_INDEX && *ti[q] < textureMapCount && textureMap[*ti[q]] != VKRT_INVALID_INDEX) *ti[q] = textureMap[*ti[q]];
+        }
         if ((r = VKRT_setMaterial(vkrt, idx, &m)) == VKRT_SUCCESS) r = VKRT_setMaterialName(vkrt, idx, hj_string(hj_get(jm, "name"), ""));
     }
     /* 4. per-mesh state */
@@ -285,7 +345,7 @@ VKRT_Result VKRT_appLoadScene(VKRT* vkrt, const char* scenePath) {
             r = VKRT_cameraSetPose(vkrt, pos, tgt, up, vfov);
     }
 done:
-    free(importFirst); free(importCount); free(savedToLoaded); free(worlds);
+    free(importFirst); free(importCount); free(savedToLoaded); free(worlds); free(textureMap);
     hj_free(root);
     return r;
 }
