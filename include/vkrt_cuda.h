@@ -195,6 +195,9 @@ VKRT_CUDA_API uint64_t vkrt_cuda_max_local_pixels(const vkrt_cuda_ctx* ctx);
  * passed to vkrt_cuda_trace_primary). bytes must equal W*H*pixelSize. */
 VKRT_CUDA_API VKRT_Result vkrt_cuda_read_aov(vkrt_cuda_ctx* ctx, vkrt_cuda_aov which, void* dst, size_t bytes);
 VKRT_CUDA_API VKRT_Result vkrt_cuda_trace_primary(vkrt_cuda_ctx* ctx, const SceneData* sceneData);
+/* Replaces the 256 one-texel vkCmdCopyImageToBuffer regions of the auto-exposure probe (src/core/scene/exposure.c:126-185):
+ * out[4 i .. 4 i + 3] = accumulation RGBA (w = sample count) of pixel (xy[2 i], xy[2 i + 1]); pixels this rank does not own read 0. */
+VKRT_CUDA_API VKRT_Result vkrt_cuda_read_accum_samples(vkrt_cuda_ctx* ctx, const uint32_t* xy, uint32_t count, float* outRgba);
 
 /* Standalone traversal entry (no reference equivalent; used by the traversal benchmark and parity tests):
  * rays = n * {ox,oy,oz,tmin, dx,dy,dz,tmax} floats on the HOST, hits = n * {instance, primitive, t, u, v} (uint32/float bits).

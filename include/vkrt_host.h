@@ -188,6 +188,8 @@ VKRT_HOST_API VKRT_Result VKRT_invalidateAccumulation(VKRT* vkrt);
 VKRT_HOST_API VKRT_Result VKRT_setSamplesPerPixel(VKRT* vkrt, uint32_t samplesPerPixel);
 VKRT_HOST_API VKRT_Result VKRT_setPathDepth(VKRT* vkrt, uint32_t rrMinDepth, uint32_t rrMaxDepth);
 VKRT_HOST_API VKRT_Result VKRT_setAutoSPPEnabled(VKRT* vkrt, uint8_t enabled);
+VKRT_HOST_API VKRT_Result VKRT_setAutoSPPTargetFPS(VKRT* vkrt, uint32_t targetFPS);   /* vkrt.h:41; clamped to 30..360, 0 = 60 */
+VKRT_HOST_API VKRT_Result VKRT_setAutoExposureEnabled(VKRT* vkrt, uint8_t enabled);  /* vkrt.h:46; single rank only */
 VKRT_HOST_API VKRT_Result VKRT_setToneMappingMode(VKRT* vkrt, VKRT_ToneMappingMode toneMappingMode);
 VKRT_HOST_API VKRT_Result VKRT_setRenderMode(VKRT* vkrt, VKRT_RenderMode renderMode);
 VKRT_HOST_API VKRT_Result VKRT_setSpectralSamplingMode(VKRT* vkrt, VKRT_SpectralSamplingMode spectralSamplingMode);
@@ -249,6 +251,11 @@ VKRT_HOST_API void VKRT_decomposeMeshTransform(vkrt_mat4 worldTransform, vkrt_ve
 VKRT_HOST_API void VKRT_decomposeMeshNodeTransform(vkrt_mat4 worldTransform, vkrt_vec3 outPosition, vkrt_vec3 outRotation, vkrt_vec3 outScale);
 /* src/core/utility/packing.c:144-156 */
 VKRT_HOST_API void VKRT_packShaderVertex(const Vertex* vertex, ShaderVertex* outVertex);
+
+/* feedback controllers as pure step functions (src/core/scene/timing.c:121-178, exposure.c:14-67,139-147), for front ends and tests */
+VKRT_HOST_API uint32_t vkrtAutoSPPStep(float* ioControlMsPerSpp, float targetFrameMs, float measuredFrameMs, uint32_t samplesPerPixel);
+VKRT_HOST_API int vkrtAutoExposureStep(float* ioFilteredLuminance, const float* samplesRgba, uint32_t sampleCount, float currentExposure, float* outExposure);
+VKRT_HOST_API void vkrtAutoExposureProbePixels(uint32_t width, uint32_t height, uint32_t* outXY);
 
 /* image decoding (src/core/utility/image.h:9-27): PNG / JPEG / EXR -> RGBA8 / RGBA16 UNORM / RGBA16F / RGBA32F; return 1 on success */
 typedef struct VKRT_LoadedImage {

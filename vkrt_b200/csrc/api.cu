@@ -28,6 +28,7 @@ void launchShadeSort(const FrameParams& fp, uint32_t depth, int smCount, cudaStr
 void launchFilm(int mode, const FrameParams& fp, int firstChunk, int lastChunk, int grid, cudaStream_t st);
 void launchTrace(const TraceParams& tp, bool count, int grid, cudaStream_t st);  // picks the flat / two-level kernel from tp.scene.accel.flat
 void launchPrimaryRaygen(const FrameParams& fp, int jittered, int grid, cudaStream_t st);
+void launchProbeAccum(const ::float4* accum, const TileMap& tm, const uint32_t* l2g, const ::uint2* xy, uint32_t count, ::float4* out, cudaStream_t st);
 void launchPackRgb2spec(const float* table, uint32_t dataOffset, size_t cellCount, ::float4* cells, int grid, cudaStream_t st);
 void launchPrimaryStore(const FrameParams& fp, int grid, cudaStream_t st);
 void launchUntile(const void* src, void* dst, const TileMap& tm, const uint32_t* l2g, uint32_t words, int grid, cudaStream_t st);
@@ -982,6 +983,22 @@ static VKRT_Result tracePrimary(vkrt_cuda_ctx* ctx, int jittered) {
     launchTrace(makeTraceParams(ctx, 0, true, false), false, ctx->traceGrid, st);
     launchPrimaryStore(ctx->fp, ctx->smCount * 4, st);
     CU(cudaGetLastError());
+    return VKRT_SUCCESS;
+}
+
+VKRT_CUDA_API VKRT_Result vkrt_cuda_read_accum_samples(vkrt_cuda_ctx* ctx, const uint32_t* xy, uint32_t count, float* outRgba) {
+    if (!ctx || !xy || !outRgba) return VKRT_ERROR_INVALID_ARGUMENT;
+    if (!ctx->width) return fail(ctx, VKRT_ERROR_OPERATION_FAILED, "read_accum_samples before resize");
+    if (count == 0) return VKRT_SUCCESS;
+    cudaSetDevice(ctx->device);
+    CU(ctx->staging.alloc((size_t)count * 24 + 16));   // xy pairs, then RGBA
+    ::uint2* dxy = reinterpret_cast<::uint2*>(ctx->staging.p);
+    ::float4* dout = reinterpret_cast<::float4*>(reinterpret_cast<char*>(ctx->staging.p) + (((size_t)count * 8 + 15) & ~(size_t)15));
+    CU(cudaMemcpyAsync(dxy, xy, (size_t)count * 8, cudaMemcpyHostToDevice, ctx->stream));
+    launchProbeAccum(ctx->fp.film.accum[ctx->readIndex], ctx->tiles, ctx->l2g.p, dxy, count, dout, ctx->stream);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(outRgba, dout, (size_t)count * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
     return VKRT_SUCCESS;
 }
 

@@ -941,6 +941,29 @@ __global__ void __launch_bounds__(256) k_untile(const uint32_t* __restrict__ src
     }
 }
 
+// Accumulation texels at a few global pixel positions (auto-exposure probe): global pixel -> owning local tile by binary search in the
+// ascending local-to-global tile list.
+__global__ void __launch_bounds__(256) k_probe_accum(const ::float4* __restrict__ accum, TileMap tm, const uint32_t* __restrict__ l2g, const ::uint2* __restrict__ xy,
+                                                     uint32_t count, ::float4* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const ::uint2 p = xy[i];
+    ::float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.x < tm.width && p.y < tm.height && tm.localTileCount) {
+        const uint32_t gt = (p.y / tm.tileH) * tm.tilesX + p.x / tm.tileW;
+        uint32_t lo = 0, hi = tm.localTileCount;
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (l2g[mid] <= gt) lo = mid; else hi = mid;
+        }
+        if (l2g[lo] == gt) v = accum[(size_t)lo * tm.tileW * tm.tileH + (p.y % tm.tileH) * tm.tileW + p.x % tm.tileW];
+    }
+    out[i] = v;
+}
+void launchProbeAccum(const ::float4* accum, const TileMap& tm, const uint32_t* l2g, const ::uint2* xy, uint32_t count, ::float4* out, cudaStream_t st) {
+    k_probe_accum<<<(count + 255) / 256, 256, 0, st>>>(accum, tm, l2g, xy, count, out);
+}
+
 // One thread per mesh: the rotation trig the shade kernel would otherwise re-evaluate per hit (see MeshTrig).
 __global__ void __launch_bounds__(128) k_mesh_trig(const MeshInfo* __restrict__ infos, MeshTrig* __restrict__ out, uint32_t count) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

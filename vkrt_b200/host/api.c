@@ -271,9 +271,30 @@ VKRT_Result VKRT_setPathDepth(VKRT* v, uint32_t rrMin, uint32_t rrMax) {
     hostResetSceneData(v);
     return VKRT_SUCCESS;
 }
-VKRT_Result VKRT_setAutoSPPEnabled(VKRT* v, uint8_t enabled) {
+VKRT_Result VKRT_setAutoSPPEnabled(VKRT* v, uint8_t enabled) { /* api/settings.c:59-64 */
     if (!v) return VKRT_ERROR_INVALID_ARGUMENT;
-    v->sceneSettings.autoSPPEnabled = enabled ? 1 : 0; /* recorded; the offline loop here always runs a fixed spp per frame */
+    v->sceneSettings.autoSPPEnabled = enabled ? 1 : 0;
+    hostResetAutoSPPState(v, 0);
+    return VKRT_SUCCESS;
+}
+VKRT_Result VKRT_setAutoSPPTargetFPS(VKRT* v, uint32_t targetFPS) { /* api/settings.c:66-79; no display: refresh rate 60 */
+    if (!v) return VKRT_ERROR_INVALID_ARGUMENT;
+    if (targetFPS == 0) targetFPS = 60u;
+    if (targetFPS < 30u) targetFPS = 30u;
+    if (targetFPS > 360u) targetFPS = 360u;
+    v->sceneSettings.autoSPPTargetFPS = targetFPS;
+    v->autoSPPTargetFrameMs = 1000.0f / (float)targetFPS;
+    hostResetAutoSPPState(v, 0);
+    return VKRT_SUCCESS;
+}
+VKRT_Result VKRT_setAutoExposureEnabled(VKRT* v, uint8_t enabled) { /* api/settings.c:135-149 */
+    VKRT_Result ready = requireReady(v);
+    if (ready != VKRT_SUCCESS) return ready;
+    enabled = enabled ? 1u : 0u;
+    if (v->sceneSettings.autoExposureEnabled == enabled) return VKRT_SUCCESS;
+    v->sceneSettings.autoExposureEnabled = enabled;
+    v->autoExposureFilteredLuminance = 0.0f;
+    hostWriteSceneStateUniform(v);
     return VKRT_SUCCESS;
 }
 VKRT_Result VKRT_setToneMappingMode(VKRT* v, VKRT_ToneMappingMode mode) {
@@ -909,6 +930,7 @@ VKRT_Result VKRT_trace(VKRT* v) {
     }
     if ((r = cudaCheck(v, vkrt_cuda_render_frame(v->cuda, &v->sceneData, &v->lastFrameStats), "render_frame")) != VKRT_SUCCESS) return r;
     v->renderStatus.renderTimeMs = v->lastFrameStats.frameMs;
+    if ((r = hostUpdateAutoExposure(v)) != VKRT_SUCCESS) return r;
     v->totalDeviceMs += v->lastFrameStats.frameMs;
     v->totalExtensionRays += v->lastFrameStats.extensionRays;
     v->totalShadowRays += v->lastFrameStats.shadowRays;
@@ -937,8 +959,10 @@ VKRT_Result VKRT_endFrame(VKRT* v) { /* frame.c:370-402 */
         int contributed = v->frameTraced && !v->accumulationNeedsReset &&
                           !(v->renderStatus.renderPhase == VKRT_RENDER_PHASE_DENOISING || v->renderStatus.renderPhase >= VKRT_RENDER_PHASE_COMPLETE_RAW);
         if (contributed) {
+            const uint32_t renderedSPP = v->sceneData.samplesPerPixel;   /* frame.c:373: what this frame traced, before the controller moves it */
+            hostUpdateAutoSPP(v);
             v->renderStatus.accumulationFrame++;
-            v->renderStatus.totalSamples += v->sceneData.samplesPerPixel;
+            v->renderStatus.totalSamples += renderedSPP;
             v->sceneData.frameNumber++;
             /* the accumulation read/write swap happens inside vkrt_cuda_render_frame */
         }

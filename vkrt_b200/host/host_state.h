@@ -55,6 +55,8 @@ struct VKRT {
     /* dirty tracking (reference: revision counters in src/core/internal/state.c:105-128) */
     int geometryDirty, sceneResourcesDirty, materialsDirty, lightsDirty, texturesDirty, accelDirty, filmDirty;
     int accumulationNeedsReset;
+    /* feedback controllers (controllers.c): smoothed ms per spp, explicit frame budget, filtered probe luminance */
+    float autoSPPControlMs, autoSPPTargetFrameMs, autoExposureFilteredLuminance;
     int frameTraced, framePresented;
 
     /* prepared device-format arrays (what vkrt_cuda_set_* receives) */
@@ -87,6 +89,9 @@ Material hostSanitizeMaterial(const VKRT* vkrt, Material material);
 int hostMaterialMayRejectRayHit(const Material* material, float meshOpacity);
 VKRT_Result hostFail(VKRT* vkrt, VKRT_Result code, const char* fmt, ...);
 void hostResetSceneData(VKRT* vkrt);
+void hostResetAutoSPPState(VKRT* vkrt, int resetSamplesPerPixel);
+void hostUpdateAutoSPP(VKRT* vkrt);
+VKRT_Result hostUpdateAutoExposure(VKRT* vkrt);
 
 static inline float hostFiniteClampf(float v, float fallback, float lo, float hi) {
     if (!isfinite(v)) v = fallback;

@@ -561,7 +561,9 @@ void hostWriteSceneStateUniform(VKRT* vkrt) {
 }
 
 /* resetSceneData (uniform.c:227-245): restart accumulation */
-void hostResetSceneData(VKRT* vkrt) {
+void hostResetSceneData(VKRT* vkrt) {   /* scene/uniform.c:227-245 */
+    hostResetAutoSPPState(vkrt, 1);
+    vkrt->autoExposureFilteredLuminance = 0.0f;
     vkrt->sceneData.frameNumber = 0;
     vkrt->renderStatus.renderPhase = vkrt->renderStatus.renderPhase != VKRT_RENDER_PHASE_INACTIVE ? VKRT_RENDER_PHASE_SAMPLING : VKRT_RENDER_PHASE_INACTIVE;
     vkrt->renderStatus.accumulationFrame = 0;
