@@ -65,7 +65,7 @@ EXPORTS = [
     "vkrt_cuda_set_rgb2spec", "vkrt_cuda_build_accel", "vkrt_cuda_resize", "vkrt_cuda_reset_accumulation",
     "vkrt_cuda_render_frame", "vkrt_cuda_render_frame_async", "vkrt_cuda_sync", "vkrt_cuda_timer_begin", "vkrt_cuda_timer_end", "vkrt_cuda_nccl_unique_id",
     "vkrt_cuda_comm_init", "vkrt_cuda_gather", "vkrt_cuda_local_film", "vkrt_cuda_import_gathered",
-    "vkrt_cuda_max_local_pixels", "vkrt_cuda_read_aov", "vkrt_cuda_trace_primary", "vkrt_cuda_trace_rays",
+    "vkrt_cuda_max_local_pixels", "vkrt_cuda_read_aov", "vkrt_cuda_read_accum_samples", "vkrt_cuda_trace_primary", "vkrt_cuda_trace_rays",
 ]
 
 _lib = None
