@@ -266,12 +266,11 @@ VKRT_Result allocateWavefront(vkrt_cuda_ctx* ctx) {
         PathState& P = fp.st[s];
         ok &= (P.rayO = F4(cap)) && (P.rayD = F4(cap)) && (P.thr = F4(cap)) && (P.sigma = F4(cap)) && (P.techPdf = F4(cap)) &&
               (P.prevVertexTechPdf = F4(cap)) && (P.prevBsdfTechPdf = F4(cap)) && (P.heroMisc = F4(cap));
-        ok &= (P.record = U32(cap)) && (P.rng = U32(cap)) && (P.flags = U32(cap));
+        ok &= (P.meta = reinterpret_cast<::uint4*>(F4(cap))) != nullptr;
     }
     ok &= (fp.shO = F4(cap)) && (fp.shD = F4(cap)) && (fp.shContribution = F4(cap)) && (fp.shSeed = U32(cap)) && (fp.shTarget = U2(cap));
     ok &= ctx->hitA.alloc(cap) == cudaSuccess;
     fp.hitA = ctx->hitA.p;
-    ok &= (fp.hitB = F32(cap)) != nullptr;
     ok &= (fp.rec.radiance = F4(cap)) && (fp.rec.featA = F4(cap)) && (fp.rec.featB = F4(cap));
     ok &= (fp.rec.radianceScalar = F32(cap)) && (fp.rec.unitWavelength = F32(cap)) && (fp.rec.follow = F32(cap));
     Film& film = fp.film;
@@ -324,9 +323,9 @@ TraceParams makeTraceParams(vkrt_cuda_ctx* ctx, uint32_t depth, bool haveExt, bo
     if (haveExt) {
         tp.rayO = S.rayO;
         tp.rayD = S.rayD;
-        tp.raySeed = S.rng;
+        tp.raySeed = reinterpret_cast<const uint32_t*>(S.meta) + 1;
         tp.hitA = fp.hitA;
-        tp.hitB = fp.hitB;
+        tp.hitB = reinterpret_cast<float*>(S.meta) + 3;
         tp.extCount = fp.extCount + depth;
     }
     if (haveShadow) {
@@ -338,8 +337,9 @@ TraceParams makeTraceParams(vkrt_cuda_ctx* ctx, uint32_t depth, bool haveExt, bo
         tp.shCount = fp.shCount + (depth - 1u);
         tp.radiance = fp.rec.radiance;
         tp.radianceScalar = fp.rec.radianceScalar;
-        tp.pathFlags = S.flags;
+        tp.pathFlags = reinterpret_cast<uint32_t*>(S.meta) + 2;
     }
+    tp.slotStride = 4u;
     tp.workCounter = fp.traceWork + depth;
     tp.stats = (ctx->flags & VKRT_CUDA_FLAG_COUNT_RAYS) ? ctx->stats.p : nullptr;
     return tp;
@@ -1079,6 +1079,7 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_trace_rays(vkrt_cuda_ctx* ctx, const float* 
         tp.rayO = o.p; tp.rayD = d.p; tp.hitA = hA.p; tp.hitB = hB.p; tp.extCount = ctr.p;
     }
     tp.workCounter = ctr.p + 1;
+    tp.slotStride = 1u;
     CU(cudaEventRecord(ctx->evA, st));
     launchTrace(tp, false, ctx->traceGrid, st);
     CU(cudaEventRecord(ctx->evB, st));

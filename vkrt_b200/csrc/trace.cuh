@@ -32,6 +32,7 @@ struct TraceParams {
     const ::float4* rayO;        // origin.xyz, tMin
     const ::float4* rayD;        // direction.xyz, tMax
     const uint32_t* raySeed;     // rng at ray start; read only when an alpha-tested instance is met
+    uint32_t slotStride;         // words between consecutive slots of raySeed / hitB / pathFlags (1 = plain arrays, 4 = PathState::meta)
     ::uint4* hitA;               // instance, primitive, t bits, u bits
     float* hitB;                 // v
     const uint32_t* extCount;    // device-resident queue length
@@ -261,7 +262,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS) k_trace(const T
                             accept = closer;
                         }
                         if (accept && (curFlags & INSTANCE_FLAG_ALPHA_TESTED)) {
-                            const uint32_t seed = R.anyHit ? __ldg(P.shSeed + (R.index - extCount)) : (P.raySeed ? __ldg(P.raySeed + R.index) : 0u);
+                            const uint32_t seed = R.anyHit ? __ldg(P.shSeed + (R.index - extCount)) : (P.raySeed ? __ldg(P.raySeed + (size_t)R.index * P.slotStride) : 0u);
                             accept = alphaHitAccepted(P.scene, curInst, prim, float2(u, v), seed);
                         }
                         if (accept) {
@@ -324,7 +325,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS) k_trace(const T
                         accept = closer;
                     }
                     if (accept && (curFlags & INSTANCE_FLAG_ALPHA_TESTED)) {
-                        const uint32_t seed = R.anyHit ? __ldg(P.shSeed + (R.index - extCount)) : (P.raySeed ? __ldg(P.raySeed + R.index) : 0u);
+                        const uint32_t seed = R.anyHit ? __ldg(P.shSeed + (R.index - extCount)) : (P.raySeed ? __ldg(P.raySeed + (size_t)R.index * P.slotStride) : 0u);
                         accept = alphaHitAccepted(P.scene, curInst, prim, float2(u, v), seed);
                     }
                     if (accept) {
@@ -363,7 +364,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS) k_trace(const T
                     if (!R.anyHit) {
                         P.hitA[R.index] = make_uint4(R.hitInst, R.hitPrim, __float_as_uint(R.hitInst != VKRT_INVALID_INDEX ? R.tBest : 0.0f),
                                                       __float_as_uint(R.hitU));
-                        P.hitB[R.index] = R.hitV;
+                        P.hitB[(size_t)R.index * P.slotStride] = R.hitV;
                     } else {
                         const uint32_t k = R.index - extCount;
                         const bool occluded = R.hitInst != VKRT_INVALID_INDEX;
@@ -380,7 +381,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS) k_trace(const T
                                 }
                             } else if (!occluded) {  // unsupported transmission: NEE is not trusted at this vertex
                                 const uint32_t pos = target.y & 0x7fffffffu;
-                                if (pos != 0x7fffffffu) P.pathFlags[pos] &= ~1u;
+                                if (pos != 0x7fffffffu) P.pathFlags[(size_t)pos * P.slotStride] &= ~1u;
                             }
                         }
                     }

@@ -93,17 +93,13 @@ __global__ void __launch_bounds__(256) k_raygen(const FrameParams fp) {
         const PathState& S = fp.st[0];
         S.rayO[j] = toF4(ray.origin, ray.tMin);
         S.rayD[j] = toF4(ray.direction, ray.tMax);
-        S.record[j] = t;
-        S.rng[j] = rng;
+        S.meta[j] = make_uint4(t, rng, MODE == MODE_HERO ? (uint32_t)PF_HERO_ACTIVE : 0u, 0u);
         if (MODE == MODE_RGB) {
-            S.flags[j] = 0u;
             S.thr[j] = make_float4(1.f, 1.f, 1.f, 0.f);
         } else if (MODE == MODE_SINGLE) {
-            S.flags[j] = 0u;
             const float lambda = WAVELENGTH_MIN_NM + saturate(unit) * WAVELENGTH_RANGE_NM;
             S.thr[j] = make_float4(1.f, lambda, 0.f, 0.f);
         } else {
-            S.flags[j] = PF_HERO_ACTIVE;
             S.thr[j] = make_float4(1.f, 1.f, 1.f, 1.f);
             S.techPdf[j] = make_float4(1.f, 1.f, 1.f, 1.f);
             S.prevVertexTechPdf[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -323,7 +319,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const _
         // ================================ phase 1: unpack, miss, surface, material, closure state ================================
         Ray ray;
         uint32_t rec = 0u, rng = 0u, flags = 0u, hitInst = VKRT_INVALID_INDEX, hitPrim = 0u, lp = 0u, sampleIndex = 0u;
-        float hitT = 0.0f, hitU = 0.0f;
+        float hitT = 0.0f, hitU = 0.0f, hitV = 0.0f;
         float3 thrRgb(0.0f);
         float thrScalar = 0.0f, prevBsdfPdf = 0.0f, lambdaScalar = 0.0f, unit = 0.0f;
         float4 thr4(0.0f), wl4(0.0f), techPdf(0.0f);
@@ -340,9 +336,11 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const _
         if (live) {
             const ::float4 ro = S.rayO[i], rd = S.rayD[i];
             const ::uint4 ha = fp.hitA[i];
-            rec = S.record[i];
-            rng = S.rng[i];
-            flags = S.flags[i];
+            const ::uint4 slotMeta = S.meta[i];
+            rec = slotMeta.x;
+            rng = slotMeta.y;
+            flags = slotMeta.z;
+            hitV = __uint_as_float(slotMeta.w);
             const ::float4 thrRaw = S.thr[i];
             ray.origin = float3(ro.x, ro.y, ro.z);
             ray.direction = float3(rd.x, rd.y, rd.z);
@@ -429,7 +427,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const _
                 const ::float4 t0 = __ldg(tq), t1 = __ldg(tq + 1);
                 trig.sx = t0.x; trig.cx = t0.y; trig.sy = t0.z; trig.cy = t0.w; trig.sz = t1.x; trig.cz = t1.y; trig.pad0 = trig.pad1 = 0.0f;
             }
-            surface = reconstructSurfaceShading(sc, mesh, trig, hitPrim, float2(hitU, fp.hitB[i]), ray.direction);
+            surface = reconstructSurfaceShading(sc, mesh, trig, hitPrim, float2(hitU, hitV), ray.direction);
             Material material = loadMaterial(sc.materials + surface.materialIndex);
             {
                 const ShadingBasis unperturbed = makeShadingBasis(surface.shadingNormal, surface.tangent);
@@ -655,9 +653,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const _
                 const float3 off = isTransmission != 0u ? -surface.geometricNormal : surface.geometricNormal;
                 N.rayO[newPos] = toF4(hitPoint + off * SHADOW_ORIGIN_OFFSET, RAY_T_MIN);
                 N.rayD[newPos] = toF4(wi, RAY_T_MAX);
-                N.record[newPos] = rec;
-                N.rng[newPos] = rng;
-                N.flags[newPos] = flags;
+                N.meta[newPos] = make_uint4(rec, rng, flags, 0u);
                 if (MODE == MODE_RGB) {
                     N.thr[newPos] = toF4(thrRgb, prevBsdfPdf);
                     if (medium.absorptionActive()) N.sigma[newPos] = toF4(medium.absorptionSigma, 0.0f);
@@ -914,17 +910,17 @@ __global__ void __launch_bounds__(256) k_primary_raygen(const FrameParams fp, co
         const uint32_t j = allocSlots(fp.extCount);
         fp.st[0].rayO[j] = toF4(ray.origin, ray.tMin);
         fp.st[0].rayD[j] = toF4(ray.direction, ray.tMax);
-        fp.st[0].record[j] = lp;
-        fp.st[0].rng[j] = rng;
+        fp.st[0].meta[j] = make_uint4(lp, rng, 0u, 0u);
     }
 }
 __global__ void __launch_bounds__(256) k_primary_store(const FrameParams fp) {
     const uint32_t count = fp.extCount[0];
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
         const ::uint4 h = fp.hitA[i];
-        const uint32_t lp = fp.st[0].record[i];
+        const ::uint4 mt = fp.st[0].meta[i];
+        const uint32_t lp = mt.x;
         fp.film.hitId[lp] = make_uint2(h.x, h.y);
-        fp.film.hitTuv[lp] = make_float4(__uint_as_float(h.z), __uint_as_float(h.w), fp.hitB[i], 0.0f);
+        fp.film.hitTuv[lp] = make_float4(__uint_as_float(h.z), __uint_as_float(h.w), __uint_as_float(mt.w), 0.0f);
     }
 }
 

@@ -41,9 +41,9 @@ __host__ __device__ inline bool localPixelToGlobal(const TileMap& tm, const uint
 struct PathState {  // one set per ping-pong side
     ::float4* rayO;
     ::float4* rayD;
-    uint32_t* record;     // sample-record index
-    uint32_t* rng;
-    uint32_t* flags;
+    ::uint4* meta;        // {sample-record index, rng, path flags, hit v (float bits, written by k_trace for this slot)}: the four
+                          // words a vertex needs from its slot in ONE 16-byte gather (shading runs in material-sorted order, so every
+                          // separate array costs a 32-byte sector per vertex)
     ::float4* thr;        // RGB: throughput.xyz, prevBsdfPdf | single: throughput, lambda, prevBsdfPdf, - | hero: throughput4
     ::float4* sigma;      // medium absorption sigma (rgb or 4 wavelengths); valid iff PF_MEDIUM_ABSORPTION
     ::float4* techPdf;    // hero: techniquePathPdf
@@ -81,8 +81,7 @@ struct FrameParams {
     SceneData sd;
     TileMap tiles;
     PathState st[2];
-    ::uint4* hitA;
-    float* hitB;
+    ::uint4* hitA;           // instance, primitive, t, u of the slot's extension ray (v lives in PathState::meta.w)
     // shadow queue
     ::float4* shO;
     ::float4* shD;
