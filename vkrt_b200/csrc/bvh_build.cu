@@ -263,7 +263,7 @@ __global__ void k_morton(const ::float4* __restrict__ primLo, const ::float4* __
 // that stability only needs (a) per-warp digit counts, (b) an exclusive prefix over warps, (c) in-round match_any ranks.
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = 8;
-constexpr int RS_ROUNDS = 16;
+constexpr int RS_ROUNDS = 8;   // 2048-key tiles: 24 KB of keys + values in shared memory for the ordered scatter
 constexpr int RS_TILE = RS_THREADS * RS_ROUNDS;
 
 __device__ __forceinline__ void warpDigitCount(uint32_t (*warpHist)[256], int warp, uint32_t digit, bool valid) {
@@ -349,27 +349,52 @@ __global__ void __launch_bounds__(256) k_rs_scan_digits(uint32_t* __restrict__ d
     digitTotals[256 + threadIdx.x] = s[threadIdx.x];  // exclusive digit bases
 }
 
+// Scatter of one 8-bit pass. The tile is first ordered by digit in shared memory (stable: warp, round, lane order is the input
+// order), then written out: element i of the ordered tile goes to globalBase[digit] + i, so that the keys of one digit leave as one
+// contiguous run (a 2048-key tile has 8-key = 64-byte runs on average) instead of 32 scattered 8-byte stores per warp instruction.
 __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t* __restrict__ keysIn, const uint32_t* __restrict__ valsIn,
                                                            uint64_t* __restrict__ keysOut, uint32_t* __restrict__ valsOut, uint32_t n,
                                                            uint32_t shift, uint32_t numTiles, const uint32_t* __restrict__ tileHist,
                                                            const uint32_t* __restrict__ digitTotals) {
-    __shared__ uint32_t warpHist[RS_WARPS][256];
+    __shared__ uint32_t warpHist[RS_WARPS][256];   // per-warp digit counts, then running local offsets
+    __shared__ uint32_t globalBase[256];           // output position of the tile's first key of a digit, minus its local position
+    __shared__ uint32_t scanTmp[RS_WARPS];
+    __shared__ uint64_t sKeys[RS_TILE];
+    __shared__ uint32_t sVals[RS_TILE];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&warpHist[0][0])[i] = 0;
     __syncthreads();
-    const uint32_t base = blockIdx.x * RS_TILE + warp * (RS_ROUNDS * 32);
+    const uint32_t tileBase = blockIdx.x * RS_TILE;
+    const uint32_t base = tileBase + warp * (RS_ROUNDS * 32);
+    const uint32_t tileCount = min((uint32_t)RS_TILE, n - tileBase);
     uint64_t key[RS_ROUNDS];
+    uint32_t val[RS_ROUNDS];
 #pragma unroll
     for (int r = 0; r < RS_ROUNDS; r++) {
         uint32_t idx = base + r * 32 + lane;
         bool valid = idx < n;
         key[r] = valid ? keysIn[idx] : 0ull;
+        val[r] = valid ? valsIn[idx] : 0u;
         warpDigitCount(warpHist, warp, (uint32_t)((key[r] >> shift) & 0xffu), valid);
     }
     __syncthreads();
-    {   // thread d: turn per-warp counts of digit d into global output offsets
+    {   // thread d: block-exclusive start of digit d (scan over the 256 digit totals), then per-warp running offsets
         const uint32_t d = threadIdx.x;
-        uint32_t running = digitTotals[256 + d] + tileHist[d * numTiles + blockIdx.x];
+        uint32_t total = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; w++) total += warpHist[w][d];
+        uint32_t x = total;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) scanTmp[warp] = x;
+        __syncthreads();
+        uint32_t warpOffset = 0;
+        for (int w = 0; w < warp; w++) warpOffset += scanTmp[w];
+        const uint32_t localStart = warpOffset + x - total;
+        globalBase[d] = digitTotals[256 + d] + tileHist[d * numTiles + blockIdx.x] - localStart;
+        uint32_t running = localStart;
 #pragma unroll
         for (int w = 0; w < RS_WARPS; w++) {
             uint32_t c = warpHist[w][d];
@@ -390,11 +415,17 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t* __res
             uint32_t off = warpHist[warp][digit];
             __syncwarp(mask);
             if (rank == 0) warpHist[warp][digit] = off + __popc(mask);
-            uint32_t pos = off + rank;
-            keysOut[pos] = key[r];
-            valsOut[pos] = valsIn[idx];
+            sKeys[off + rank] = key[r];
+            sVals[off + rank] = val[r];
         }
         __syncwarp();
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < tileCount; i += RS_THREADS) {
+        const uint64_t k = sKeys[i];
+        const uint32_t pos = globalBase[(uint32_t)((k >> shift) & 0xffu)] + i;
+        keysOut[pos] = k;
+        valsOut[pos] = sVals[i];
     }
 }
 

@@ -7,14 +7,15 @@
  *   JPEG -> RGBA8 UNORM, alpha 255; baseline and extended sequential Huffman, 8-bit, 1 or 3 components, the IJG "islow" IDCT
  *           (TJFLAG_ACCURATEDCT), triangle-filter ("fancy") chroma upsampling for h2v1 / h2v2 and the IJG YCbCr tables, i.e. the same
  *           integers libjpeg-turbo produces; progressive and arithmetic-coded files are rejected;
- *   EXR  -> single-part scanline files, NONE / RLE / ZIPS / ZIP compression, HALF / FLOAT / UINT channels; RGBA16F when every
+ *   EXR  -> single-part scanline files, NONE / RLE / ZIPS / ZIP / PIZ compression, HALF / FLOAT / UINT channels; RGBA16F when every
  *           channel is HALF, else RGBA32F; R,G,B(,A) by name or by ".R" suffix, Y fallback, missing A = 1 (exr.cpp:40-172);
- *           tiled, multi-part, deep, PIZ / PXR24 / B44 / DWA files are rejected with a message.
+ *           tiled, multi-part, deep, PXR24 / B44 / DWA files are rejected with a message.
  */
 #include "image_decode.h"
 
 #include <math.h>
 #include <stdarg.h>
+#include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -762,6 +763,192 @@ static int exrRleDecode(const uint8_t* in, size_t inLen, uint8_t* outBuf, size_t
     return o == outLen;
 }
 
+
+/* ---- PIZ (OpenEXR's default for photographic data): a 16-bit value LUT from a presence bitmap, a 2-D Haar-like wavelet per channel
+ * plane and a canonical Huffman code with run-length escapes, as published in the OpenEXR technical documentation (ImfPizCompressor,
+ * ImfHuf, ImfWav). ---------------------------------------------------------------------------------------------------------------- */
+#define PIZ_HUF_ENCSIZE 65537          /* 65536 values + the run-length symbol */
+typedef struct PizBits { const uint8_t* p; const uint8_t* end; uint64_t acc; int count; } PizBits;
+static inline uint32_t pizGetBits(PizBits* b, int n) {
+    while (b->count < n) {
+        b->acc = (b->acc << 8) | (b->p < b->end ? *b->p : 0u);
+        b->p++;
+        b->count += 8;
+    }
+    b->count -= n;
+    return (uint32_t)((b->acc >> b->count) & ((1ull << n) - 1ull));
+}
+static int pizHufDecode(const uint8_t* data, size_t size, uint16_t* out, size_t outCount) {
+    if (size < 20) return 0;
+    uint32_t im, iM, nBits;
+    memcpy(&im, data, 4); memcpy(&iM, data + 4, 4); memcpy(&nBits, data + 12, 4);
+    if (im >= PIZ_HUF_ENCSIZE || iM >= PIZ_HUF_ENCSIZE || im > iM) return 0;
+    uint8_t* len = (uint8_t*)calloc(PIZ_HUF_ENCSIZE, 1);
+    uint32_t* sorted = (uint32_t*)malloc(sizeof(uint32_t) * PIZ_HUF_ENCSIZE);
+    if (!len || !sorted) { free(len); free(sorted); return 0; }
+    PizBits b = {data + 20, data + size, 0, 0};
+    /* packed code lengths: 6 bits each, 59..62 = short zero runs (2..5), 63 = long zero run (8 more bits + 6) */
+    for (uint32_t s = im; s <= iM; s++) {
+        uint32_t l = pizGetBits(&b, 6);
+        if (l == 63u) {
+            uint32_t run = pizGetBits(&b, 8) + 6u;
+            if (s + run > iM + 1u) { free(len); free(sorted); return 0; }
+            s += run - 1u;
+        } else if (l >= 59u) {
+            uint32_t run = l - 59u + 2u;
+            if (s + run > iM + 1u) { free(len); free(sorted); return 0; }
+            s += run - 1u;
+        } else {
+            len[s] = (uint8_t)l;
+        }
+    }
+    /* canonical codes: lengths 58..1, the first code of a length follows from the longer ones; symbols of one length in index order */
+    uint64_t count[59] = {0}, first[59] = {0};
+    uint32_t start[60] = {0};
+    for (uint32_t s = im; s <= iM; s++) count[len[s]]++;
+    uint64_t c = 0;
+    for (int l = 58; l > 0; l--) { uint64_t nc = (c + count[l]) >> 1; first[l] = c; c = nc; }
+    for (int l = 1; l <= 58; l++) start[l + 1] = start[l] + (uint32_t)count[l];
+    { uint32_t fill[60]; memcpy(fill, start, sizeof(fill)); for (uint32_t s = im; s <= iM; s++) if (len[s]) sorted[fill[len[s]]++] = s; }
+    /* the bit stream starts at the next byte boundary after the table */
+    const uint8_t* bitsStart = b.p - (b.count / 8);
+    PizBits d = {bitsStart, data + size, 0, 0};
+    uint64_t bitsLeft = nBits;
+    size_t o = 0;
+    int ok = 1;
+    while (bitsLeft > 0 && ok) {
+        uint64_t code = 0;
+        int l = 0;
+        uint32_t sym = 0xffffffffu;
+        while (l < 58 && bitsLeft > 0) {
+            code = (code << 1) | pizGetBits(&d, 1);
+            bitsLeft--;
+            l++;
+            if (count[l] && code >= first[l] && code - first[l] < count[l]) { sym = sorted[start[l] + (uint32_t)(code - first[l])]; break; }
+        }
+        if (sym == 0xffffffffu) {   /* trailing padding bits of the last byte are not a symbol */
+            break;
+        }
+        if (sym == iM) {            /* run-length symbol: repeat the previous value */
+            if (bitsLeft < 8 || o == 0) { ok = 0; break; }
+            uint32_t run = pizGetBits(&d, 8);
+            bitsLeft -= 8;
+            if (o + run > outCount) { ok = 0; break; }
+            for (uint32_t k = 0; k < run; k++) out[o + k] = out[o - 1];
+            o += run;
+        } else {
+            if (o >= outCount) { ok = 0; break; }
+            out[o++] = (uint16_t)sym;
+        }
+    }
+    free(len); free(sorted);
+    return ok && o == outCount;
+}
+static inline void pizWdec14(uint16_t l, uint16_t h, uint16_t* a, uint16_t* b) {
+    int ls = (int16_t)l, hs = (int16_t)h;
+    int ai = ls + (hs & 1) + (hs >> 1);
+    *a = (uint16_t)(int16_t)ai;
+    *b = (uint16_t)(int16_t)(ai - hs);
+}
+static inline void pizWdec16(uint16_t l, uint16_t h, uint16_t* a, uint16_t* b) {
+    int m = l, d = h;
+    int bb = (m - (d >> 1)) & 0xffff;
+    int aa = (d + bb - 0x8000) & 0xffff;
+    *b = (uint16_t)bb;
+    *a = (uint16_t)aa;
+}
+static void pizWav2Decode(uint16_t* in, int nx, int ox, int ny, int oy, uint16_t mx) {
+    const int w14 = mx < (1 << 14);
+    int n = nx > ny ? ny : nx, p = 1, p2;
+    while (p <= n) p <<= 1;
+    p >>= 1;
+    p2 = p;
+    p >>= 1;
+    while (p >= 1) {
+        uint16_t* py = in;
+        uint16_t* ey = in + (ptrdiff_t)oy * (ny - p2);
+        const int oy1 = oy * p, oy2 = oy * p2, ox1 = ox * p, ox2 = ox * p2;
+        uint16_t i00, i01, i10, i11;
+        for (; py <= ey; py += oy2) {
+            uint16_t* px = py;
+            uint16_t* ex = py + (ptrdiff_t)ox * (nx - p2);
+            for (; px <= ex; px += ox2) {
+                uint16_t* p01 = px + ox1;
+                uint16_t* p10 = px + oy1;
+                uint16_t* p11 = p10 + ox1;
+                if (w14) { pizWdec14(*px, *p10, &i00, &i10); pizWdec14(*p01, *p11, &i01, &i11); pizWdec14(i00, i01, px, p01); pizWdec14(i10, i11, p10, p11); }
+                else { pizWdec16(*px, *p10, &i00, &i10); pizWdec16(*p01, *p11, &i01, &i11); pizWdec16(i00, i01, px, p01); pizWdec16(i10, i11, p10, p11); }
+            }
+            if (nx & p) {
+                uint16_t* p10 = px + oy1;
+                if (w14) pizWdec14(*px, *p10, &i00, p10); else pizWdec16(*px, *p10, &i00, p10);
+                *px = i00;
+            }
+        }
+        if (ny & p) {
+            uint16_t* px = py;
+            uint16_t* ex = py + (ptrdiff_t)ox * (nx - p2);
+            for (; px <= ex; px += ox2) {
+                uint16_t* p01 = px + ox1;
+                if (w14) pizWdec14(*px, *p01, &i00, p01); else pizWdec16(*px, *p01, &i00, p01);
+                *px = i00;
+            }
+        }
+        p2 = p;
+        p >>= 1;
+    }
+}
+/* One PIZ block -> the same scanline-interleaved bytes an uncompressed block holds. wordsPerPixel[c] = 1 (HALF) or 2 (FLOAT / UINT). */
+static int exrPizDecode(const uint8_t* src, size_t srcLen, uint8_t* outBuf, size_t rawLen, uint32_t width, uint32_t lines, const int* wordsPerPixel, int nch) {
+    const size_t totalWords = rawLen / 2;
+    if (srcLen < 4) return 0;
+    uint16_t minNonZero, maxNonZero;
+    memcpy(&minNonZero, src, 2); memcpy(&maxNonZero, src + 2, 2);
+    uint8_t* bitmap = (uint8_t*)calloc(8192, 1);
+    uint16_t* lut = (uint16_t*)calloc(65536, sizeof(uint16_t));
+    uint16_t* tmp = (uint16_t*)malloc(totalWords * sizeof(uint16_t) + 2);
+    int ok = bitmap && lut && tmp;
+    size_t pos = 4;
+    if (ok && minNonZero <= maxNonZero) {
+        size_t nb = (size_t)maxNonZero - minNonZero + 1;
+        if (maxNonZero >= 8192 || pos + nb > srcLen) ok = 0;
+        else { memcpy(bitmap + minNonZero, src + pos, nb); pos += nb; }
+    }
+    uint16_t maxValue = 0;
+    if (ok) {
+        uint32_t k = 0;
+        for (uint32_t i = 0; i < 65536u; i++)
+            if (i == 0 || (bitmap[i >> 3] & (1u << (i & 7u)))) lut[k++] = (uint16_t)i;
+        maxValue = (uint16_t)(k - 1u);
+        int32_t hufLen = 0;
+        if (pos + 4 > srcLen) ok = 0;
+        else { memcpy(&hufLen, src + pos, 4); pos += 4; }
+        if (ok && (hufLen < 0 || pos + (size_t)hufLen > srcLen)) ok = 0;
+        if (ok) ok = pizHufDecode(src + pos, (size_t)hufLen, tmp, totalWords);
+    }
+    if (ok) {
+        uint16_t* plane = tmp;
+        for (int c = 0; c < nch; c++) {
+            for (int j = 0; j < wordsPerPixel[c]; j++) pizWav2Decode(plane + j, (int)width, wordsPerPixel[c], (int)lines, (int)width * wordsPerPixel[c], maxValue);
+            plane += (size_t)width * lines * wordsPerPixel[c];
+        }
+        for (size_t i = 0; i < totalWords; i++) tmp[i] = lut[tmp[i]];
+        /* channel-planar -> per scanline, channels in order */
+        uint16_t* o = (uint16_t*)outBuf;
+        for (uint32_t y = 0; y < lines; y++) {
+            const uint16_t* chanBase = tmp;
+            for (int c = 0; c < nch; c++) {
+                const size_t rowWords = (size_t)width * wordsPerPixel[c];
+                memcpy(o, chanBase + (size_t)y * rowWords, rowWords * 2);
+                o += rowWords;
+                chanBase += rowWords * lines;
+            }
+        }
+    }
+    free(bitmap); free(lut); free(tmp);
+    return ok;
+}
+
 static int decodeExr(const uint8_t* data, size_t size, const char* label, HostImage* out, char* err, size_t errLen) {
     if (size < 8 || data[0] != 0x76 || data[1] != 0x2f || data[2] != 0x31 || data[3] != 0x01) return imgFail(err, errLen, "Invalid EXR file: %s", label);
     const uint32_t versionField = (uint32_t)data[4] | ((uint32_t)data[5] << 8) | ((uint32_t)data[6] << 16) | ((uint32_t)data[7] << 24);
@@ -809,7 +996,7 @@ static int decodeExr(const uint8_t* data, size_t size, const char* label, HostIm
         pos = p + asz;
     }
     if (!nch || compression < 0 || !haveWindow || xmax < xmin || ymax < ymin) return imgFail(err, errLen, "EXR header decode from %s failed (missing attributes)", label);
-    if (compression > 3) return imgFail(err, errLen, "EXR decode from %s failed (compression %d: only NONE, RLE, ZIPS and ZIP are supported)", label, compression);
+    if (compression > 4) return imgFail(err, errLen, "EXR decode from %s failed (compression %d: only NONE, RLE, ZIPS, ZIP and PIZ are supported)", label, compression);
     const uint32_t W = (uint32_t)(xmax - xmin + 1), H = (uint32_t)(ymax - ymin + 1);
     if (W > (1u << 20) || H > (1u << 20)) return imgFail(err, errLen, "EXR image dimensions overflow for %s", label);
     size_t lineBytes = 0;
@@ -830,7 +1017,9 @@ static int decodeExr(const uint8_t* data, size_t size, const char* label, HostIm
         if (exrChannelMatches(ch[i].name, "Y")) iY = i;
     }
     if ((iR < 0 || iG < 0 || iB < 0) && iY < 0) return imgFail(err, errLen, "EXR image from %s did not contain RGB(A) or Y channels", label);
-    const uint32_t linesPerBlock = compression == 3 ? 16u : 1u;
+    const uint32_t linesPerBlock = compression == 3 ? 16u : (compression == 4 ? 32u : 1u);
+    int wordsPerPixel[16];
+    for (int i = 0; i < nch; i++) wordsPerPixel[i] = ch[i].type == 1 ? 1 : 2;
     const uint32_t blocks = (H + linesPerBlock - 1) / linesPerBlock;
     if (pos + (size_t)blocks * 8 > size) return imgFail(err, errLen, "EXR decode from %s failed (truncated offset table)", label);
     const size_t texel = allHalf ? 8u : 16u;
@@ -857,6 +1046,8 @@ static int decodeExr(const uint8_t* data, size_t size, const char* label, HostIm
         if (compression == 0 || dataSize == rawLen) {  /* a block that did not shrink is stored raw */
             if (dataSize != rawLen) { good = 0; why = "bad block size"; break; }
             memcpy(blockBuf, src, rawLen);
+        } else if (compression == 4) {
+            if (!exrPizDecode(src, dataSize, blockBuf, rawLen, W, lines, wordsPerPixel, nch)) { good = 0; why = "bad PIZ data"; break; }
         } else if (compression == 1) {
             if (!exrRleDecode(src, dataSize, tmpBuf, rawLen)) { good = 0; why = "bad RLE data"; break; }
             exrUnpredict(tmpBuf, rawLen, blockBuf);
