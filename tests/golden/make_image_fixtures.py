@@ -58,7 +58,8 @@ put("png_grey16", buf.getvalue(), np.dstack([g16, g16, g16, np.full_like(g16, 65
 ok, enc = cv2.imencode(".png", (rgba.astype(np.uint16) * 257)[..., [2, 1, 0, 3]])
 put("png_rgba16", enc.tobytes(), rgba.astype(np.uint16) * 257)
 
-# ---- EXR: float / half, NONE / RLE / ZIPS / ZIP, RGB / RGBA / Y ----
+# ---- EXR: float / half, NONE / RLE / ZIPS / ZIP / PIZ, RGB / RGBA / Y; one PXR24 file (unsupported: must be rejected) ----
+# a 70-row smooth image spans three 32-line PIZ blocks and exercises the 14-bit wavelet and the run-length symbol
 hdr = (rng.random((h, w, 3)) * 10).astype(np.float32)
 hdr[3, 4] = [1e4, 0.0, 1e-5]
 for tag, typ, comp, chans in [("float_none_rgb", cv2.IMWRITE_EXR_TYPE_FLOAT, cv2.IMWRITE_EXR_COMPRESSION_NO, 3),
@@ -66,7 +67,9 @@ for tag, typ, comp, chans in [("float_none_rgb", cv2.IMWRITE_EXR_TYPE_FLOAT, cv2
                               ("float_rle_y", cv2.IMWRITE_EXR_TYPE_FLOAT, cv2.IMWRITE_EXR_COMPRESSION_RLE, 1),
                               ("half_zips_rgb", cv2.IMWRITE_EXR_TYPE_HALF, cv2.IMWRITE_EXR_COMPRESSION_ZIPS, 3),
                               ("half_zip_rgba", cv2.IMWRITE_EXR_TYPE_HALF, cv2.IMWRITE_EXR_COMPRESSION_ZIP, 4),
-                              ("float_piz_rgb", cv2.IMWRITE_EXR_TYPE_FLOAT, cv2.IMWRITE_EXR_COMPRESSION_PIZ, 3)]:
+                              ("float_piz_rgb", cv2.IMWRITE_EXR_TYPE_FLOAT, cv2.IMWRITE_EXR_COMPRESSION_PIZ, 3),
+                              ("half_piz_rgba", cv2.IMWRITE_EXR_TYPE_HALF, cv2.IMWRITE_EXR_COMPRESSION_PIZ, 4),
+                              ("half_pxr24_rgb", cv2.IMWRITE_EXR_TYPE_HALF, cv2.IMWRITE_EXR_COMPRESSION_PXR24, 3)]:
     src = hdr if chans == 3 else (np.dstack([hdr, hdr[..., :1] * 0.1]) if chans == 4 else hdr[..., 0])
     bgr = src[..., ::-1] if chans == 3 else (src[..., [2, 1, 0, 3]] if chans == 4 else src)
     ok, enc = cv2.imencode(".exr", bgr, [cv2.IMWRITE_EXR_TYPE, typ, cv2.IMWRITE_EXR_COMPRESSION, comp])
@@ -78,6 +81,13 @@ for tag, typ, comp, chans in [("float_none_rgb", cv2.IMWRITE_EXR_TYPE_FLOAT, cv2
     if typ == cv2.IMWRITE_EXR_TYPE_HALF:
         want = want.astype(np.float16)
     put("exr_" + tag, enc.tobytes(), want)
+
+yy, xx = np.mgrid[0:70, 0:45]
+smooth = np.dstack([xx / 44.0, yy / 69.0, np.full(xx.shape, 0.25)]).astype(np.float32)
+ok, enc = cv2.imencode(".exr", smooth[..., ::-1], [cv2.IMWRITE_EXR_TYPE, cv2.IMWRITE_EXR_TYPE_HALF, cv2.IMWRITE_EXR_COMPRESSION, cv2.IMWRITE_EXR_COMPRESSION_PIZ])
+want = np.ones((70, 45, 4), np.float16)
+want[..., :3] = smooth
+put("exr_half_piz_smooth", enc.tobytes(), want)
 
 np.savez_compressed(os.path.join(HERE, "images.npz"), **out)
 print("wrote", os.path.join(HERE, "images.npz"), sum(v.nbytes for v in out.values()), "bytes in", len(out), "arrays")
