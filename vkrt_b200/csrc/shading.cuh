@@ -153,13 +153,14 @@ static constexpr uint RGB2SPEC_SMEM_RES = 64u;
 // then 7 entries of the block) replace six dependent ones.
 VK_D uint rgb2specFindInterval(const float* __restrict__ scale, uint res, float x) {
     if (res == 64u) {
-        uint block = 0u;
-#pragma unroll
-        for (int k = 8; k < 64; k += 8) block += scale[k] <= x ? 1u : 0u;
+        // all loads of a round are issued before the first comparison: two load latencies per search instead of fourteen
+        const float p0 = scale[8], p1 = scale[16], p2 = scale[24], p3 = scale[32], p4 = scale[40], p5 = scale[48], p6 = scale[56];
+        const uint block = (p0 <= x ? 1u : 0u) + (p1 <= x ? 1u : 0u) + (p2 <= x ? 1u : 0u) + (p3 <= x ? 1u : 0u) + (p4 <= x ? 1u : 0u) +
+                           (p5 <= x ? 1u : 0u) + (p6 <= x ? 1u : 0u);
         const float* s = scale + 8u * block;
-        uint left = 8u * block;
-#pragma unroll
-        for (int k = 1; k < 8; k++) left += s[k] <= x ? 1u : 0u;
+        const float q1 = s[1], q2 = s[2], q3 = s[3], q4 = s[4], q5 = s[5], q6 = s[6], q7 = s[7];
+        const uint left = 8u * block + (q1 <= x ? 1u : 0u) + (q2 <= x ? 1u : 0u) + (q3 <= x ? 1u : 0u) + (q4 <= x ? 1u : 0u) +
+                          (q5 <= x ? 1u : 0u) + (q6 <= x ? 1u : 0u) + (q7 <= x ? 1u : 0u);
         return min(left, 62u);
     }
     int left = 0;
@@ -180,13 +181,17 @@ VK_D uint rgb2specFindInterval(const float* __restrict__ scale, uint res, float 
 VK_NOINLINE float3 rgb2specFetchTable(const ::float4* __restrict__ cells, const float* __restrict__ scale, uint res, float3 rgb) {
     float z = max(rgb.x, max(rgb.y, rgb.z));
     if (z <= RGB2SPEC_EPSILON) return float3(0.0f);
+    // rgb2spec.slang:39-44: the LAST channel that reaches the maximum dominates; the other two follow in cyclic order. Written as
+    // selects: indexing a float3 with a runtime channel compiles to branches.
     uint dominantChannel = 0u;
-    for (uint channel = 1u; channel < 3u; ++channel) {
-        if (rgb[int(channel)] >= rgb[int(dominantChannel)]) dominantChannel = channel;
-    }
+    float top = rgb.x;
+    if (rgb.y >= top) { dominantChannel = 1u; top = rgb.y; }
+    if (rgb.z >= top) dominantChannel = 2u;
+    const float cx = dominantChannel == 0u ? rgb.y : (dominantChannel == 1u ? rgb.z : rgb.x);
+    const float cy = dominantChannel == 0u ? rgb.z : (dominantChannel == 1u ? rgb.x : rgb.y);
     float xyScale = float(res - 1u) / z;
-    float x = rgb[int((dominantChannel + 1u) % 3u)] * xyScale;
-    float y = rgb[int((dominantChannel + 2u) % 3u)] * xyScale;
+    float x = cx * xyScale;
+    float y = cy * xyScale;
     uint xi = min(uint(x), res - 2u);
     uint yi = min(uint(y), res - 2u);
     uint zi = rgb2specFindInterval(scale, res, z);
