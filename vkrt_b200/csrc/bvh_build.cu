@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -514,7 +515,7 @@ struct CollapseParams {
     const uint32_t* subCount;
     const uint32_t* sortedVals;   // sorted position -> original primitive index
     uint32_t primCount;
-    uint32_t maxLeaf;             // 3 for triangles, 1 for instances
+    uint32_t maxLeaf;             // primitives per leaf slot (1; the node format allows up to 3)
     Bvh8Node* nodesOut;           // global node array
     uint32_t nodeBase;            // global index of this BVH's root node
     uint32_t* counters;           // [0] work-out count, [1] nodes allocated (local), [2] primitives emitted (local)
@@ -790,7 +791,10 @@ bool AccelBuilder::buildFromBoxes(cudaStream_t st, uint32_t n, const BuildTarget
     CollapseParams P = {};
     P.nodeLo = nodeLo; P.nodeHi = nodeHi; P.subFirst = subFirst; P.subCount = subCount; P.sortedVals = vals[cur];
     P.primCount = n;
-    P.maxLeaf = tgt.instancesOut ? 1u : 3u;
+    // One primitive per leaf slot. A watertight triangle test costs ~4 child-box tests and runs at half their lane efficiency, so a
+    // slot box that culls a single triangle pays for itself: 3 -> 1 triangles per slot took the 10 M-triangle soup from 13.4 to 4.5
+    // triangle tests per ray for 1.3 more node visits (762 -> 1020 Mrays/s) and the cornell box from 3.1 to 2.3 (profiles/r01_notes.md).
+    P.maxLeaf = 1u;
     P.nodesOut = tgt.nodesOut; P.nodeBase = tgt.nodeBase; P.counters = counters;
     P.vertices = tgt.vertices; P.indices = tgt.indices; P.vertexBase = tgt.vertexBase; P.indexBase = tgt.indexBase;
     P.trianglesOut = tgt.trianglesOut; P.primBase = tgt.primBase;
