@@ -43,9 +43,10 @@ FLAG_COUNT_RAYS, FLAG_STAGE_TIMING = 1, 4
 B_EXT_RAY = 52          # trace: read rayO 16 + rayD 16, write hitA 16 + hitB 4
 B_SHADOW_RAY = 40       # trace: read shO 16 + shD 16 + shTarget 8 (contribution/radiance only touched when unoccluded)
 B_NODE, B_TRI, B_INSTANCE = 80, 48, 64
-B_SHADE_READ_HERO = 32 + 20 + 12 + 16 + 16 + 16    # ray, hit, record/rng/flags, thr4, heroMisc, techPdf
+B_SHADE_READ_HERO = 32 + 16 + 16 + 16 + 16 + 16    # ray, hitA, meta {record, rng, flags, hit v}, thr4, heroMisc, techPdf
+B_SHADE_READ_FRESH = 32                             # thr4 + techPdf are constants at depth 0 and are not read for camera paths
 B_SHADE_SURFACE = 12 + 144 + 80 + 32 + 272           # indices, 3 ShaderVertex, MeshInfo, MeshTrig, Material
-B_SHADE_WRITE_PATH_HERO = 32 + 12 + 16 + 16 + 16 + 16 + 16
+B_SHADE_WRITE_PATH_HERO = 32 + 16 + 16 + 16 + 16 + 16 + 16   # ray, meta, thr4, heroMisc, techPdf, prevVertexTechPdf, prevBsdfTechPdf
 B_SHADE_WRITE_SHADOW = 16 + 16 + 16 + 8 + 4
 B_SHADE_FEATURES = 36                                 # featA, featB, follow at depth 0
 
@@ -420,7 +421,8 @@ def _run_ours(args, real_stdout):
             hc.close()
         shade_launches = launches - trace_launches   # raygen + shade + film
         n_shade = args.steps * 8                     # k_shade launches proper (rrMaxDepth = 8)
-        shade_bytes = ext * (B_SHADE_READ_HERO + B_SHADE_SURFACE) + max(ext - local_paths, 0) * B_SHADE_WRITE_PATH_HERO + sh * B_SHADE_WRITE_SHADOW + local_paths * B_SHADE_FEATURES
+        shade_bytes = (ext * (B_SHADE_READ_HERO + B_SHADE_SURFACE) - local_paths * B_SHADE_READ_FRESH + max(ext - local_paths, 0) * B_SHADE_WRITE_PATH_HERO +
+                       sh * B_SHADE_WRITE_SHADOW + local_paths * B_SHADE_FEATURES)
         trace_bytes = ext * B_EXT_RAY + sh * B_SHADOW_RAY
         if visits:
             trace_bytes += (ext + sh) * (visits["nodes_per_ray"] * B_NODE + visits["triangles_per_ray"] * B_TRI + visits["instances_per_ray"] * B_INSTANCE)

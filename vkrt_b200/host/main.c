@@ -83,6 +83,11 @@ int main(int argc, char** argv) {
     VKRT_getBuildStats(vkrt, &bs);
     printf("Acceleration structure: %.3f ms, %llu triangles in %u BLAS, %u instances, %llu BVH8 nodes\n", bs.buildMs, (unsigned long long)bs.triangleCount,
            bs.uniqueGeometries, bs.instanceCount, (unsigned long long)bs.bvh8NodeCount);
+    {   /* the first build of a process also pays for scratch allocation and module loading: time a rebuild of the same scene */
+        vkrt_cuda_build_stats again;
+        if (vkrt_cuda_build_accel(VKRT_cudaContext(vkrt), &again) == VKRT_SUCCESS)
+            printf("Acceleration structure rebuild: %.3f ms (%.1f M triangles/s)\n", again.buildMs, again.buildMs > 0 ? (double)again.triangleCount / again.buildMs / 1e3 : 0.0);
+    }
     printf("Offline render complete: %.3f s, %.2f samples/s, %.3f ms/sample, %u spp/frame, actual %llu samples\n", res.seconds, res.samplesPerSecond,
            res.samples ? res.seconds * 1000.0 / (double)res.samples : 0.0, res.samplesPerFrame, (unsigned long long)res.samples);
     printf("  %ux%u: %.1f Mpaths/s, %.1f Mrays/s (%llu extension + %llu shadow rays)\n", width, height, res.mpathsPerSecond,
