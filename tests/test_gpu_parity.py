@@ -156,6 +156,46 @@ def test_accumulation_is_a_running_mean_and_deterministic():
     assert np.array_equal(a.view(np.uint32), g1.read(H.AOV_ACCUM).view(np.uint32)), "re-render must be bit-identical"
 
 
+def test_full_size_frame_properties():
+    """BASELINE config C2 at full size (1920x1080, spectral hero, 16 spp per frame = 33.2 M paths), where the oracle would take minutes:
+    size-independent properties instead. (1) a frame rendered in three sample chunks equals the unchunked frame bit for bit; (2) the
+    union of two tile-partitioned ranks equals it bit for bit; (3) sample counts are exact; (4) the 2 M primary-hit ids of the 1080p frame equal
+    the oracle's (primary visibility alone is cheap enough on the CPU)."""
+    w, h, spp = 1920, 1080, 16
+    prep = scenes.cornell(w, h, spp=spp)
+    prep["sceneData"]["packedRenderSettings"] = H.hr.pack_render_settings(0, 1, 1)
+    table = scenes.rgb2spec()
+    full = H.CudaBackend(max_paths=w * h * spp)
+    full.upload(prep, rgb2spec=table)
+    full.resize(w, h)
+    full.render(prep["sceneData"], frames=2)
+    ref = full.read(H.AOV_ACCUM)
+    assert np.all(ref[..., 3] == 2.0 * spp)
+    assert np.isfinite(ref).all() and float(ref[..., :3].mean()) > 0.0
+    chunked = H.CudaBackend(max_paths=w * h * 6)     # 16 spp in chunks of 6 + 6 + 4
+    chunked.upload(prep, rgb2spec=table)
+    chunked.resize(w, h)
+    chunked.render(prep["sceneData"], frames=2)
+    assert np.array_equal(ref.view(np.uint32), chunked.read(H.AOV_ACCUM).view(np.uint32))
+    chunked.close()
+    acc = np.zeros_like(ref)
+    for r in range(2):
+        g = H.CudaBackend(rank=r, world_size=2, max_paths=w * h * spp // 2 + 65536)
+        g.upload(prep, rgb2spec=table)
+        g.resize(w, h)
+        g.render(prep["sceneData"], frames=2)
+        acc += g.read(H.AOV_ACCUM)
+        g.close()
+    assert np.array_equal(ref.view(np.uint32), acc.view(np.uint32))
+    gpu_ids = full.read(H.AOV_HITID_CENTER)
+    full.close()
+    o = H.OracleBackend()
+    o.upload(prep)
+    o.resize(w, h)
+    o.trace_primary(prep["sceneData"])
+    assert np.array_equal(gpu_ids, o.read(H.AOV_HITID_CENTER))
+
+
 def test_tile_partition_matches_single_gpu():
     """Two ranks on one device: the union of their tile-compact films equals the single-rank image bit for bit."""
     w, h = 200, 120  # not a multiple of the tile size

@@ -20,7 +20,10 @@ namespace vk {
 
 constexpr int TRACE_STACK = 40;
 constexpr int TRACE_BLOCK = 128;
-constexpr int REFILL_THRESHOLD = 20;
+#ifndef TRACE_REFILL
+#define TRACE_REFILL 20
+#endif
+constexpr int REFILL_THRESHOLD = TRACE_REFILL;
 #ifndef TRACE_MIN_BLOCKS
 #define TRACE_MIN_BLOCKS 6   // 80 registers: 24 warps per SM (measured best, profiles/r01_notes.md)
 #endif
