@@ -216,19 +216,6 @@ __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS) k_trace(const T
                     if (COUNT) nNodes++;
                     G = make_uint2(childBase, (hits & 0xff000000u) | imask);
                     Gt = make_uint2(primBase, hits & 0x00ffffffu);
-#ifdef TRACE_PREFETCH_DEFERRED
-                    {   // the second-nearest hit child waits on the stack while the nearest subtree is walked: pull its node towards the SM now
-                        const uint32_t inner = hits & 0xff000000u;
-                        const uint32_t rest = inner & ~(0x80000000u >> __clz(inner | 1u));
-                        if (rest) {
-                            const int bit2 = 31 - __clz(rest);
-                            const uint32_t slot2 = (uint32_t)(bit2 - 24) ^ octinv;
-                            const Bvh8Node* nn = A.nodes + childBase + __popc(imask & ((1u << slot2) - 1u));
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(nn));
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(nn) + 64));
-                        }
-                    }
-#endif
                 } else if (G.y) {  // a primitive group that was parked on the stack
                     Gt = G;
                     G = make_uint2(0u, 0u);
