@@ -9,7 +9,8 @@
 //   triangles   : 3 x ::float4 per triangle in leaf order: v0.xyz|prim, v1.xyz|-, v2.xyz|-   (48 B, object space)
 //   instances   : 64 B per TLAS leaf: inverse 3x4 (row-major, 3 x ::float4) + {blasRoot, triBase, flags, instanceIndex}
 // Flat variant (vkrt_cuda_build_accel picks it when instancing does not pay): ONE BVH over the world-space boxes of all
-// instanced triangles; leaves index `flatPrims` {triangle record, instance}; triangles stay in object space and the ray is taken into
+// instanced triangles; leaves index leaf-ordered 48-byte triangle records {v0 | primitive, v1 | instance, v2} (gathered once after the
+// build from the builder's `flatPrims` {triangle record, instance} list); triangles stay in object space and the ray is taken into
 // the instance's space at the triangle test, so hits are bit-identical to the two-level structure.
 #pragma once
 #include <cstdint>
@@ -55,9 +56,9 @@ struct Lbvh {
 
 struct AccelView {
     const Bvh8Node* nodes;
-    const ::float4* triangles;          // two-level: BLAS leaf order; flat: primitive order per unique geometry
+    const ::float4* triangles;          // two-level: BLAS leaf order; flat: leaf order of the single BVH, b.w = instance
     const InstanceRecord* instances;    // two-level: TLAS leaf order; flat: instance order
-    const ::uint2* flatPrims;           // flat only, leaf order: x = triangle record, y = instance
+    const ::uint2* flatPrims;           // flat only, leaf order: x = triangle record, y = instance (build product; traversal reads `triangles`)
     uint32_t tlasRoot;      // node index of the TLAS root (flat: of the single BVH)
     uint32_t instanceCount; // 0 = nothing to hit
     uint32_t flat;          // 1 = single-level BVH over instanced triangles

@@ -120,6 +120,7 @@ struct vkrt_cuda_ctx {
     DevBuf<::float4> triangles;
     DevBuf<InstanceRecord> instanceRecords, instancesLeafOrder;
     DevBuf<::uint2> flatPrims;
+    DevBuf<::float4> flatTriangles;   // flat variant: leaf-ordered triangle records, b.w = instance (what k_trace<.., true> reads)
     bool accelFlat = false;
     DevBuf<::float4> blasBounds;
     DevBuf<uint32_t> instanceBlas;
@@ -239,7 +240,7 @@ SceneView makeSceneView(vkrt_cuda_ctx* c) {
     v.spectral.cells = c->rgb2specCells.p;
     v.spectral.scale = c->rgb2spec.p + c->rgb2specInfo.scaleOffset;
     v.accel.nodes = c->nodes.p;
-    v.accel.triangles = c->triangles.p;
+    v.accel.triangles = c->accelFlat ? c->flatTriangles.p : c->triangles.p;
     v.accel.instances = c->instancesLeafOrder.p;
     v.accel.tlasRoot = c->tlasRoot;
     v.accel.instanceCount = (uint32_t)c->hostMeshInfos.size();
@@ -738,6 +739,8 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_build_accel(vkrt_cuda_ctx* ctx, vkrt_cuda_bu
         if (primCount != total) return fail(ctx, VKRT_ERROR_OPERATION_FAILED, "flat BVH emitted %u of %u triangles", primCount, total);
         CU(ctx->nodes.alloc(std::max(nodeCount, 1u)));
         launchRelocateNodes(scratchNodes.p, ctx->nodes.p, nodeCount, 0u, 0u, st);
+        CU(ctx->flatTriangles.alloc((size_t)std::max(total, 1u) * 3));
+        launchFlatGatherTriangles(ctx->flatPrims.p, ctx->triangles.p, total, ctx->flatTriangles.p, st);
         CU(cudaEventRecord(ctx->evB, st));
         CU(cudaStreamSynchronize(st));
         CU(cudaGetLastError());

@@ -430,6 +430,23 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t* __res
     }
 }
 
+// Flat variant: leaf-ordered triangle records with the instance in b.w, gathered from the per-geometry records (traversal then needs
+// one load stage per triangle test instead of {leaf entry -> record}).
+__global__ void __launch_bounds__(256) k_flat_gather_triangles(const uint2* __restrict__ flatPrims, const ::float4* __restrict__ src, uint32_t total,
+                                                               ::float4* __restrict__ dst) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint2 fp = flatPrims[i];
+        const ::float4* s = src + (size_t)fp.x * 3;
+        ::float4 a = s[0], b = s[1], c = s[2];
+        b.w = __uint_as_float(fp.y);
+        ::float4* d = dst + (size_t)i * 3;
+        d[0] = a; d[1] = b; d[2] = c;
+    }
+}
+void launchFlatGatherTriangles(const uint2* flatPrims, const ::float4* src, uint32_t total, ::float4* dst, cudaStream_t st) {
+    if (total) k_flat_gather_triangles<<<boundsGrid(total), 256, 0, st>>>(flatPrims, src, total, dst);
+}
+
 // ---- Karras 2012 hierarchy -------------------------------------------------------------------------------------------
 __device__ __forceinline__ int deltaKeys(const uint64_t* __restrict__ keys, int n, int i, uint64_t ki, int j) {
     if (j < 0 || j >= n) return -1;

@@ -227,13 +227,15 @@ __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS) k_trace(const T
                 Gt.y &= Gt.y - 1u;
                 const uint32_t primIndex = Gt.x + (uint32_t)i;
                 if (FLAT) {
-                    // ---- single-level BVH: the leaf entry names {triangle record, instance}; the triangle stays in object space and the
-                    // ray is taken into the instance's space (cached per lane until the instance changes) -> same arithmetic, same bits
-                    // as the two-level structure.
-                    const ::uint2 fp = __ldg(A.flatPrims + primIndex);
+                    // ---- single-level BVH: the leaf-ordered triangle record carries its instance in b.w (ONE load stage per test); the
+                    // triangle stays in object space and the ray is taken into the instance's space (cached per lane until the instance
+                    // changes) -> same arithmetic, same bits as the two-level structure.
+                    const ::float4* tri = A.triangles + (size_t)primIndex * 3;
+                    const ::float4 a = __ldg(tri), b = __ldg(tri + 1), c = __ldg(tri + 2);
+                    const uint32_t triInst = __float_as_uint(b.w);
                     bool testable = true;
-                    if (fp.y != curInst) {
-                        const InstanceRecord* rec = A.instances + fp.y;
+                    if (triInst != curInst) {
+                        const InstanceRecord* rec = A.instances + triInst;
                         const ::uint4 meta = __ldg(reinterpret_cast<const ::uint4*>(rec) + 3);
                         const ::float4 r0 = __ldg(reinterpret_cast<const ::float4*>(rec));
                         const ::float4 r1 = __ldg(reinterpret_cast<const ::float4*>(rec) + 1);
@@ -243,7 +245,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS) k_trace(const T
                         const float3 od = xformVector(i0, i1, i2, R.d);
                         curFlags = meta.y;
                         if (makeRayShear(od, shear)) {
-                            curInst = fp.y;
+                            curInst = triInst;
                             if (COUNT) nInst++;
                         } else {
                             curInst = VKRT_INVALID_INDEX;
@@ -252,8 +254,6 @@ __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS) k_trace(const T
                     }
                     if (testable && R.anyHit && R.sawTransmissive && (curFlags & INSTANCE_FLAG_TRANSMISSIVE)) testable = false;
                     if (testable) {
-                        const ::float4* tri = A.triangles + (size_t)fp.x * 3;
-                        const ::float4 a = __ldg(tri), b = __ldg(tri + 1), c = __ldg(tri + 2);
                         if (COUNT) nTris++;
                         float t, u, v;
                         bool accept = watertightTriangle(objO, shear, float3(a.x, a.y, a.z), float3(b.x, b.y, b.z), float3(c.x, c.y, c.z), t, u, v) && t > R.tMin;
