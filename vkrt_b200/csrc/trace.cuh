@@ -293,12 +293,13 @@ __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS) k_trace(const T
                     G = make_uint2(0u, 0u);
                     Gt.y = 0u;
                     const InstanceRecord* rec = A.instances + primIndex;
+                    // the whole 64-byte record in one load stage (skipped instances are rare)
                     const ::uint4 meta = __ldg(reinterpret_cast<const ::uint4*>(rec) + 3);
+                    const ::float4 r0 = __ldg(reinterpret_cast<const ::float4*>(rec));
+                    const ::float4 r1 = __ldg(reinterpret_cast<const ::float4*>(rec) + 1);
+                    const ::float4 r2 = __ldg(reinterpret_cast<const ::float4*>(rec) + 2);
                     const bool skip = (meta.y & INSTANCE_FLAG_EMPTY) || (R.anyHit && R.sawTransmissive && (meta.y & INSTANCE_FLAG_TRANSMISSIVE));
                     if (!skip) {
-                        const ::float4 r0 = __ldg(reinterpret_cast<const ::float4*>(rec));
-                        const ::float4 r1 = __ldg(reinterpret_cast<const ::float4*>(rec) + 1);
-                        const ::float4 r2 = __ldg(reinterpret_cast<const ::float4*>(rec) + 2);
                         const float4 i0(r0.x, r0.y, r0.z, r0.w), i1(r1.x, r1.y, r1.z, r1.w), i2(r2.x, r2.y, r2.z, r2.w);
                         const float3 oo = xformPoint(i0, i1, i2, R.o);
                         const float3 od = xformVector(i0, i1, i2, R.d);
