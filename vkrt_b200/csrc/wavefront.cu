@@ -62,34 +62,66 @@ __device__ __forceinline__ float4 heroWavelengths(float unit) {
 // ----------------------------------------------------------------------------------------------------------------------
 // raygen: RaygenPixelState + PathCommonState.initCommon (integrator/path/state.slang:60-79,140-146,160-196)
 // ----------------------------------------------------------------------------------------------------------------------
+// Queue slots for the threads of a block that have `want` set: ONE atomic per block (a 1080p x 16 spp chunk is 1 M warps; one atomic per
+// warp on the same counter serialises in L2 at ~1 ns each and was a third of k_raygen). Every thread of the block must call it.
+__device__ __forceinline__ uint32_t blockAllocSlots(uint32_t* counter, bool want) {
+    __shared__ uint32_t sWarp[32];
+    __shared__ uint32_t sBase;
+    const unsigned m = __ballot_sync(0xffffffffu, want);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = (blockDim.x + 31) >> 5;
+    if (lane == 0) sWarp[warp] = __popc(m);
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t c = lane < warps ? sWarp[lane] : 0u, x = c;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane < warps) sWarp[lane] = x - c;              // exclusive prefix of the warp counts
+        if (lane == 31 && x) sBase = atomicAdd(counter, x);
+    }
+    __syncthreads();
+    const uint32_t slot = sBase + sWarp[warp] + __popc(m & ((1u << lane) - 1u));
+    __syncthreads();                                         // sWarp / sBase are reused by the next trip
+    return slot;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(256) k_raygen(const FrameParams fp) {
     const uint32_t lpc = fp.tiles.localPixelCount;
     const uint32_t total = fp.chunkSamples * lpc;
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
-        // zero the sample record (coalesced)
-        fp.rec.radiance[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-        fp.rec.featA[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-        fp.rec.featB[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-        fp.rec.follow[t] = 0.0f;
-        if (MODE == MODE_HERO) fp.rec.radianceScalar[t] = 0.0f;
-        const uint32_t s = t / lpc, lp = t - s * lpc;
-        uint32_t gx, gy;
-        if (!localPixelToGlobal(fp.tiles, fp.tiles.localToGlobalTile, lp, gx, gy)) continue;
-        if (!insideViewport(fp.sd, (int)gx, (int)gy)) continue;
-        const float prevW = fp.film.accum[fp.readIndex][lp].w;
-        const uint32_t previousSamples = (uint32_t)(prevW + 0.5f);
-        const uint32_t sampleIndex = fp.chunkFirstSample + s;
-        uint32_t rng = initPixelSeed((int)gx, (int)gy, fp.sd.frameNumber, previousSamples + sampleIndex);
-        const float jx = rand(rng);
-        const float jy = rand(rng);
-        const Ray ray = makePrimaryRayExact(fp.sd, (int)gx, (int)gy, float2(__fsub_rn(jx, 0.5f), __fsub_rn(jy, 0.5f)));
+    for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
+        const uint32_t t = base + threadIdx.x;
+        bool valid = t < total;
+        uint32_t rng = 0u;
         float unit = 0.0f;
-        if (MODE != MODE_RGB) {
-            unit = sampleUniformWavelengthUnit(rng, previousSamples + sampleIndex);
-            fp.rec.unitWavelength[t] = unit;
+        Ray ray;
+        if (valid) {
+            // zero the sample record (coalesced)
+            fp.rec.radiance[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+            fp.rec.featA[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+            fp.rec.featB[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+            fp.rec.follow[t] = 0.0f;
+            if (MODE == MODE_HERO) fp.rec.radianceScalar[t] = 0.0f;
+            const uint32_t s = t / lpc, lp = t - s * lpc;
+            uint32_t gx, gy;
+            valid = localPixelToGlobal(fp.tiles, fp.tiles.localToGlobalTile, lp, gx, gy) && insideViewport(fp.sd, (int)gx, (int)gy);
+            if (valid) {
+                const float prevW = fp.film.accum[fp.readIndex][lp].w;
+                const uint32_t previousSamples = (uint32_t)(prevW + 0.5f);
+                const uint32_t sampleIndex = fp.chunkFirstSample + s;
+                rng = initPixelSeed((int)gx, (int)gy, fp.sd.frameNumber, previousSamples + sampleIndex);
+                const float jx = rand(rng);
+                const float jy = rand(rng);
+                ray = makePrimaryRayExact(fp.sd, (int)gx, (int)gy, float2(__fsub_rn(jx, 0.5f), __fsub_rn(jy, 0.5f)));
+                if (MODE != MODE_RGB) {
+                    unit = sampleUniformWavelengthUnit(rng, previousSamples + sampleIndex);
+                    fp.rec.unitWavelength[t] = unit;
+                }
+            }
         }
-        const uint32_t j = allocSlots(fp.extCount);
+        const uint32_t j = blockAllocSlots(fp.extCount, valid);
+        if (!valid) continue;
         const PathState& S = fp.st[0];
         S.rayO[j] = toF4(ray.origin, ray.tMin);
         S.rayD[j] = toF4(ray.direction, ray.tMax);
