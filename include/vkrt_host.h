@@ -268,6 +268,8 @@ typedef struct VKRT_LoadedImage {
 VKRT_HOST_API int vkrtLoadImageFromFile(const char* path, uint32_t preferredColorSpace, VKRT_LoadedImage* outImage);
 VKRT_HOST_API int vkrtLoadImageFromMemory(const void* data, size_t size, const char* mimeType, uint32_t preferredColorSpace, VKRT_LoadedImage* outImage);
 VKRT_HOST_API void vkrtFreeLoadedImage(VKRT_LoadedImage* image);
+/* baseline 4:4:4 JPEG writer behind VKRT_saveRenderImage("*.jpg") (src/core/utility/export/image.c:220-263 uses quality 95) */
+VKRT_HOST_API int vkrtWriteJPEGFromRGBA8(const char* path, const uint8_t* rgba8, uint32_t width, uint32_t height, int quality);
 
 /* ---- app layer: scene files, model import, procedural benchmark scenes, offline render loop ----
  * (src/app/scene/controller.c:1528-1597, src/app/mesh/loader.c:2133-2179, src/app/render/benchmark.c:13-293) */

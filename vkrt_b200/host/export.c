@@ -8,6 +8,7 @@
 #include <zlib.h>
 
 #include "host_state.h"
+#include "image_decode.h"
 
 static void mul3(const float m[9], const float v[3], float out[3]) {
     for (int r = 0; r < 3; r++) out[r] = (m[r * 3 + 0] * v[0]) + (m[r * 3 + 1] * v[1]) + (m[r * 3 + 2] * v[2]);
@@ -153,6 +154,15 @@ VKRT_Result VKRT_saveRenderImageEx(VKRT* v, const char* path, const VKRT_RenderE
     if (!v || !path || !path[0]) return VKRT_ERROR_INVALID_ARGUMENT;
     if (!v->initialized || v->hostOnly || !v->cuda) return VKRT_ERROR_OPERATION_FAILED;
     if (settings && settings->denoiseEnabled) return hostFail(v, VKRT_ERROR_OPERATION_FAILED, "OIDN denoising is outside this path; save with denoiseEnabled = 0");
+    char withExtension[4096];
+    {   /* export/image.c:134-149 resolveRenderImagePath: a path without an extension is saved as PNG */
+        const char* base = strrchr(path, '/');
+        base = base ? base + 1 : path;
+        if (!strchr(base, '.')) {
+            if (snprintf(withExtension, sizeof(withExtension), "%s.png", path) >= (int)sizeof(withExtension)) return VKRT_ERROR_INVALID_ARGUMENT;
+            path = withExtension;
+        }
+    }
     const uint32_t w = v->renderWidth, h = v->renderHeight;
     const size_t px = (size_t)w * h;
     VKRT_Result r;
@@ -183,7 +193,19 @@ VKRT_Result VKRT_saveRenderImageEx(VKRT* v, const char* path, const VKRT_RenderE
         free(out);
         return r;
     }
-    return hostFail(v, VKRT_ERROR_INVALID_ARGUMENT, "%s: unsupported image format (use .exr or .png; JPEG needs libjpeg-turbo)", path);
+    if (hasSuffix(path, ".jpg") || hasSuffix(path, ".jpeg")) {   /* export/image.c:298-327: RGBA16 UNORM output -> 8 bits, quality 95, 4:4:4 */
+        uint16_t* out = (uint16_t*)malloc(px * 8);
+        uint8_t* out8 = (uint8_t*)malloc(px * 4);
+        if (!out || !out8) { free(out); free(out8); return VKRT_ERROR_OUT_OF_MEMORY; }
+        r = vkrt_cuda_read_aov(v->cuda, VKRT_CUDA_AOV_OUTPUT_RGBA16, out, px * 8);
+        if (r == VKRT_SUCCESS) {
+            for (size_t i = 0; i < px * 4; i++) out8[i] = (uint8_t)((((uint32_t)out[i] * 255u) + 32767u) / 65535u);
+            if (!hostWriteJpegRgba8(path, out8, w, h, 95)) { remove(path); r = hostFail(v, VKRT_ERROR_OPERATION_FAILED, "cannot write %s", path); }
+        } else hostFail(v, r, "read_aov: %s", vkrt_cuda_last_error(v->cuda));
+        free(out); free(out8);
+        return r;
+    }
+    return hostFail(v, VKRT_ERROR_INVALID_ARGUMENT, "%s: unsupported render export format (use .png, .jpg or .exr)", path);
 }
 VKRT_Result VKRT_saveRenderImage(VKRT* v, const char* path) {
     VKRT_RenderExportSettings s;

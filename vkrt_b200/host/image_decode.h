@@ -16,4 +16,6 @@ int hostDecodeImage(const void* data, size_t size, const char* mimeType, const c
                     size_t errLen);
 int hostLoadImageFile(const char* path, uint32_t preferredColorSpace, HostImage* out, char* err, size_t errLen);
 void hostFreeImage(HostImage* image);
+/* baseline JPEG, 4:4:4, IJG quality scale (jpeg_encode.c; reference: export/image.c:220-263 writes quality 95). 1 on success. */
+int hostWriteJpegRgba8(const char* path, const uint8_t* rgba8, uint32_t width, uint32_t height, int quality);
 #endif
