@@ -24,6 +24,9 @@ constexpr int TRACE_BLOCK = 128;
 #define TRACE_REFILL 20
 #endif
 constexpr int REFILL_THRESHOLD = TRACE_REFILL;
+#ifndef TRACE_PRIM_VOTE
+#define TRACE_PRIM_VOTE 8   // lanes with a pending primitive wait until 8 of them can run the primitive section together (0 = every trip)
+#endif
 #ifndef TRACE_MIN_BLOCKS
 #define TRACE_MIN_BLOCKS 6   // 80 registers: 24 warps per SM (measured best, profiles/r01_notes.md)
 #endif
@@ -222,7 +225,16 @@ __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS) k_trace(const T
                 }
             }
 
+#if TRACE_PRIM_VOTE > 0
+            // The primitive section runs when at least TRACE_PRIM_VOTE lanes have a pending primitive, or when no lane of the warp has
+            // node work left to do meanwhile: pending lanes sit out a few node trips and then test their primitives together.
+            const unsigned inLoop = __activemask();
+            const unsigned pending = __ballot_sync(inLoop, Gt.y != 0u);
+            const bool runPrims = __popc(pending) >= TRACE_PRIM_VOTE || pending == inLoop;
+            if (Gt.y && runPrims) {
+#else
             if (Gt.y) {
+#endif
                 const int i = __ffs(Gt.y) - 1;
                 Gt.y &= Gt.y - 1u;
                 const uint32_t primIndex = Gt.x + (uint32_t)i;
