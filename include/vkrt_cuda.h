@@ -61,7 +61,8 @@ enum {
     VKRT_CUDA_FLAG_NO_MATERIAL_SORT = 1u << 1, /* shade in queue order instead of material-sorted order */
     VKRT_CUDA_FLAG_STAGE_TIMING = 1u << 2,    /* vkrt_cuda_render_frame records a CUDA event after every launch and fills traceMs / shadeMs */
     VKRT_CUDA_FLAG_FORCE_TWO_LEVEL = 1u << 3, /* always build BLAS per unique geometry + TLAS (default: chosen from the instancing ratio) */
-    VKRT_CUDA_FLAG_FORCE_FLAT = 1u << 4       /* always build one BVH over all instanced triangles */
+    VKRT_CUDA_FLAG_FORCE_FLAT = 1u << 4,      /* always build one BVH over all instanced triangles */
+    VKRT_CUDA_FLAG_DEEP_STACK = 1u << 5       /* always traverse with the deep-tree kernel (default: chosen from the depth of the built trees) */
 };
 
 typedef struct vkrt_cuda_build_stats {

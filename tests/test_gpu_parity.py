@@ -280,6 +280,26 @@ def test_default_accel_choice():
     g.close()
 
 
+@pytest.mark.parametrize("accel", [8, 16])
+def test_deep_stack_kernel_is_bit_identical(accel):
+    """The traversal stack size follows the depth of the built trees (api.cu: stackNeed); the deep-tree instantiation of
+    k_trace (VKRT_CUDA_FLAG_DEEP_STACK = 32 forces it) must give the same hits and the same film, bit for bit."""
+    w, h = 128, 96
+    prep = scenes.instanced(w, h, count=64, spp=2)
+    films, ids = [], []
+    for extra in (0, 32):
+        g = H.CudaBackend(flags=accel | extra)
+        g.upload(prep)
+        g.resize(w, h)
+        g.trace_primary(prep["sceneData"])
+        ids.append(g.read(H.AOV_HITID_CENTER).copy())
+        g.render(prep["sceneData"], frames=2)
+        films.append(g.read(H.AOV_ACCUM).copy())
+        g.close()
+    assert np.array_equal(ids[0], ids[1])
+    assert np.array_equal(films[0].view(np.uint32), films[1].view(np.uint32))
+
+
 def test_dispersive_glass_hero_collapse():
     """Rough glass with an Abbe number: hero paths collapse to one wavelength on refraction (spectral_hero/transport.slang:77-87)."""
     w = h = 96

@@ -62,7 +62,7 @@ struct AccelView {
     uint32_t tlasRoot;      // node index of the TLAS root (flat: of the single BVH)
     uint32_t instanceCount; // 0 = nothing to hit
     uint32_t flat;          // 1 = single-level BVH over instanced triangles
-    uint32_t pad;
+    uint32_t stackNeed;     // upper bound of the traversal stack entries a ray can need (from the built tree depths); picks the k_trace stack size
 };
 
 } // namespace vk

@@ -122,6 +122,7 @@ struct vkrt_cuda_ctx {
     DevBuf<::uint2> flatPrims;
     DevBuf<::float4> flatTriangles;   // flat variant: leaf-ordered triangle records, b.w = instance (what k_trace<.., true> reads)
     bool accelFlat = false;
+    uint32_t stackNeed = 0;  // traversal stack entries the built trees can require (AccelView::stackNeed)
     DevBuf<::float4> blasBounds;
     DevBuf<uint32_t> instanceBlas;
     uint32_t tlasRoot = 0;
@@ -246,7 +247,7 @@ SceneView makeSceneView(vkrt_cuda_ctx* c) {
     v.accel.instanceCount = (uint32_t)c->hostMeshInfos.size();
     v.accel.flatPrims = c->flatPrims.p;
     v.accel.flat = c->accelFlat ? 1u : 0u;
-    v.accel.pad = 0u;
+    v.accel.stackNeed = (c->flags & VKRT_CUDA_FLAG_DEEP_STACK) ? (uint32_t)TRACE_STACK_DEEP : c->stackNeed;
     return v;
 }
 
@@ -737,6 +738,10 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_build_accel(vkrt_cuda_ctx* ctx, vkrt_cuda_bu
                                     ctx->flatPrims.p, &nodeCount, &primCount))
             return fail(ctx, VKRT_ERROR_OPERATION_FAILED, "flat BVH build failed: %s", ctx->builder.err);
         if (primCount != total) return fail(ctx, VKRT_ERROR_OPERATION_FAILED, "flat BVH emitted %u of %u triangles", primCount, total);
+        // one parked node group per level (+ margin): the traversal kernel is chosen by this bound, deeper trees are refused
+        ctx->stackNeed = ctx->builder.lastLevels + 2u;
+        if (ctx->stackNeed > (uint32_t)TRACE_STACK_DEEP)
+            return fail(ctx, VKRT_ERROR_OPERATION_FAILED, "flat BVH has %u levels: deeper than the traversal stack (%d)", ctx->builder.lastLevels, TRACE_STACK_DEEP);
         CU(ctx->nodes.alloc(std::max(nodeCount, 1u)));
         launchRelocateNodes(scratchNodes.p, ctx->nodes.p, nodeCount, 0u, 0u, st);
         CU(ctx->flatTriangles.alloc((size_t)std::max(total, 1u) * 3));
@@ -773,7 +778,7 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_build_accel(vkrt_cuda_ctx* ctx, vkrt_cuda_bu
     CU(ctx->blasBounds.alloc(std::max<size_t>(blas.size(), 1) * 2));
     cudaStream_t st = ctx->stream;
     CU(cudaEventRecord(ctx->evA, st));
-    uint32_t primBase = 0;
+    uint32_t primBase = 0, maxBlasLevels = 0;
     std::vector<::float4> emptyBounds = {make_float4(1e30f, 1e30f, 1e30f, 0.f), make_float4(-1e30f, -1e30f, -1e30f, 0.f)};
     for (size_t b = 0; b < blas.size(); b++) {
         BlasDesc& d = blas[b];
@@ -788,6 +793,7 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_build_accel(vkrt_cuda_ctx* ctx, vkrt_cuda_bu
             return fail(ctx, VKRT_ERROR_OPERATION_FAILED, "BLAS build failed: %s", ctx->builder.err);
         if (primCount != d.triCount) return fail(ctx, VKRT_ERROR_OPERATION_FAILED, "BLAS %zu emitted %u of %u triangles", b, primCount, d.triCount);
         d.nodeCount = nodeCount;
+        maxBlasLevels = std::max(maxBlasLevels, ctx->builder.lastLevels);
         primBase += d.triCount;
     }
     CU(cudaEventRecord(ctx->evB, st));
@@ -827,7 +833,7 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_build_accel(vkrt_cuda_ctx* ctx, vkrt_cuda_bu
     }
     cudaEvent_t evC;
     CU(cudaEventCreate(&evC));
-    uint32_t tlasNodes = 0, tlasPrims = 0;
+    uint32_t tlasNodes = 0, tlasPrims = 0, tlasLevels = 0;
     ctx->tlasRoot = (uint32_t)finalNodes;
     if (n > 0) {
         if (!ctx->builder.buildTlas(st, ctx->blasBounds.p, ctx->instanceBlas.p, ctx->world3x4.p, ctx->instanceRecords.p, n, scratchNodes.p, tlasNodeBase,
@@ -836,6 +842,13 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_build_accel(vkrt_cuda_ctx* ctx, vkrt_cuda_bu
             return fail(ctx, VKRT_ERROR_OPERATION_FAILED, "TLAS build failed: %s", ctx->builder.err);
         }
         launchRelocateNodes(scratchNodes.p + tlasNodeBase, ctx->nodes.p + ctx->tlasRoot, tlasNodes, tlasNodeBase, ctx->tlasRoot, st);
+        tlasLevels = ctx->builder.lastLevels;
+    }
+    // one parked node group per level, two entries parked when a ray enters an instance (+ margin)
+    ctx->stackNeed = tlasLevels + 2u + maxBlasLevels + 2u;
+    if (ctx->stackNeed > (uint32_t)TRACE_STACK_DEEP) {
+        cudaEventDestroy(evC);
+        return fail(ctx, VKRT_ERROR_OPERATION_FAILED, "BVH has %u + %u levels: deeper than the traversal stack (%d)", tlasLevels, maxBlasLevels, TRACE_STACK_DEEP);
     }
     CU(cudaEventRecord(evC, st));
     CU(cudaStreamSynchronize(st));

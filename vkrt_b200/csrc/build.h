@@ -48,6 +48,7 @@ public:
                    uint32_t instanceCount, const float* world3x4, uint32_t totalPrims, uint2* flatScratch, Bvh8Node* nodesOut, uint32_t nodeBase,
                    uint2* flatOut, uint32_t* outNodeCount, uint32_t* outPrimCount);
     char err[512] = {0};
+    uint32_t lastLevels = 0;  // BVH8 levels of the most recent build (number of collapse rounds)
 
 private:
     bool buildFromBoxes(cudaStream_t st, uint32_t n, const BuildTarget& tgt, uint32_t* outNodeCount, uint32_t* outPrimCount);

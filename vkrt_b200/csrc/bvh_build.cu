@@ -824,7 +824,9 @@ bool AccelBuilder::buildFromBoxes(cudaStream_t st, uint32_t n, const BuildTarget
     uint32_t workCount = 1;
     int wq = 0;
     uint32_t hostCounters[4];
+    lastLevels = 0;
     while (workCount > 0) {
+        lastLevels++;
         k_collapse<<<(workCount + 63) / 64, 64, 0, st>>>(P, work[wq], workCount, work[1 - wq]);
         CK(cudaMemcpyAsync(hostCounters, counters, sizeof(hostCounters), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));

@@ -18,7 +18,8 @@
 
 namespace vk {
 
-constexpr int TRACE_STACK = 40;
+constexpr int TRACE_STACK = 40;        // stack entries of the default kernel: one per BVH8 level + 2 per instance entry (AccelView::stackNeed)
+constexpr int TRACE_STACK_DEEP = 192;  // second instantiation for degenerate (chain-like) trees; deeper trees are refused at build time
 constexpr int TRACE_BLOCK = 128;
 #ifndef TRACE_REFILL
 #define TRACE_REFILL 20
@@ -132,7 +133,7 @@ struct LaneRay {
     bool anyHit, sawTransmissive, active;
 };
 
-template <bool COUNT, bool FLAT>
+template <bool COUNT, bool FLAT, int STACK>
 __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS) k_trace(const TraceParams P) {
     const int lane = threadIdx.x & 31;
     const uint32_t extCount = P.extCount ? *P.extCount : 0u;
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS) k_trace(const T
     const uint32_t total = extCount + shCount;
     const AccelView& A = P.scene.accel;
 
-    uint2 stack[TRACE_STACK];
+    uint2 stack[STACK];
     int sp = 0;
     LaneRay R;
     R.active = false;
@@ -212,7 +213,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS) k_trace(const T
                     const int bit = 31 - __clz(G.y & 0xff000000u);
                     const uint32_t slot = (uint32_t)(bit - 24) ^ octinv;
                     G.y &= ~(1u << bit);
-                    if (G.y & 0xff000000u) { if (sp < TRACE_STACK) stack[sp++] = G; }
+                    if (G.y & 0xff000000u) { if (sp < STACK) stack[sp++] = G; }
                     const uint32_t nodeIndex = G.x + __popc(G.y & 0xffu & ((1u << slot) - 1u));
                     uint32_t childBase, primBase, imask;
                     const uint32_t hits = intersectNode8(A.nodes + nodeIndex, o, idir, octinv, one, R.tMin, R.tBest, childBase, primBase, imask);
@@ -300,8 +301,8 @@ __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS) k_trace(const T
                     }
                 } else if (!inBlas) {
                     // TLAS leaf = instance: park the remaining TLAS work and descend into the BLAS
-                    if (Gt.y) { if (sp < TRACE_STACK) stack[sp++] = Gt; }
-                    if (G.y & 0xff000000u) { if (sp < TRACE_STACK) stack[sp++] = G; }
+                    if (Gt.y) { if (sp < STACK) stack[sp++] = Gt; }
+                    if (G.y & 0xff000000u) { if (sp < STACK) stack[sp++] = G; }
                     G = make_uint2(0u, 0u);
                     Gt.y = 0u;
                     const InstanceRecord* rec = A.instances + primIndex;

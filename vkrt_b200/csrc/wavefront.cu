@@ -1012,8 +1012,8 @@ void launchMeshTrig(const MeshInfo* infos, MeshTrig* out, uint32_t count, cudaSt
 int traceBlocksPerSm(bool count) {
     int n = 0;
     // the two-level variant has the larger register footprint; one grid size serves both
-    if (count) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace<true, false>, TRACE_BLOCK, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace<false, false>, TRACE_BLOCK, 0);
+    if (count) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace<true, false, TRACE_STACK>, TRACE_BLOCK, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace<false, false, TRACE_STACK>, TRACE_BLOCK, 0);
     return n > 0 ? n : 1;
 }
 int shadeBlocksPerSm(int mode) {
@@ -1040,10 +1040,16 @@ void launchFilm(int mode, const FrameParams& fp, int firstChunk, int lastChunk, 
     else if (mode == MODE_SINGLE) k_film<MODE_SINGLE><<<grid, 256, 0, st>>>(fp, firstChunk, lastChunk);
     else k_film<MODE_HERO><<<grid, 256, 0, st>>>(fp, firstChunk, lastChunk);
 }
+template <int STACK>
+static void launchTraceStack(const TraceParams& tp, bool count, bool flat, int grid, cudaStream_t st) {
+    if (count) { if (flat) k_trace<true, true, STACK><<<grid, TRACE_BLOCK, 0, st>>>(tp); else k_trace<true, false, STACK><<<grid, TRACE_BLOCK, 0, st>>>(tp); }
+    else { if (flat) k_trace<false, true, STACK><<<grid, TRACE_BLOCK, 0, st>>>(tp); else k_trace<false, false, STACK><<<grid, TRACE_BLOCK, 0, st>>>(tp); }
+}
 void launchTrace(const TraceParams& tp, bool count, int grid, cudaStream_t st) {
     const bool flat = tp.scene.accel.flat != 0u;
-    if (count) { if (flat) k_trace<true, true><<<grid, TRACE_BLOCK, 0, st>>>(tp); else k_trace<true, false><<<grid, TRACE_BLOCK, 0, st>>>(tp); }
-    else { if (flat) k_trace<false, true><<<grid, TRACE_BLOCK, 0, st>>>(tp); else k_trace<false, false><<<grid, TRACE_BLOCK, 0, st>>>(tp); }
+    // the stack size follows the depth of the built trees (api.cu refuses trees deeper than TRACE_STACK_DEEP)
+    if (tp.scene.accel.stackNeed > (uint32_t)TRACE_STACK) launchTraceStack<TRACE_STACK_DEEP>(tp, count, flat, grid, st);
+    else launchTraceStack<TRACE_STACK>(tp, count, flat, grid, st);
 }
 void launchPrimaryRaygen(const FrameParams& fp, int jittered, int grid, cudaStream_t st) { k_primary_raygen<<<grid, 256, 0, st>>>(fp, jittered); }
 void launchPrimaryStore(const FrameParams& fp, int grid, cudaStream_t st) { k_primary_store<<<grid, 256, 0, st>>>(fp); }
