@@ -62,7 +62,11 @@ enum {
     VKRT_CUDA_FLAG_STAGE_TIMING = 1u << 2,    /* vkrt_cuda_render_frame records a CUDA event after every launch and fills traceMs / shadeMs */
     VKRT_CUDA_FLAG_FORCE_TWO_LEVEL = 1u << 3, /* always build BLAS per unique geometry + TLAS (default: chosen from the instancing ratio) */
     VKRT_CUDA_FLAG_FORCE_FLAT = 1u << 4,      /* always build one BVH over all instanced triangles */
-    VKRT_CUDA_FLAG_DEEP_STACK = 1u << 5       /* always traverse with the deep-tree kernel (default: chosen from the depth of the built trees) */
+    VKRT_CUDA_FLAG_DEEP_STACK = 1u << 5,      /* always traverse with the deep-tree kernel (default: chosen from the depth of the built trees) */
+    VKRT_CUDA_FLAG_ENV_IMPORTANCE = 1u << 6   /* EXTENSION (not in the reference, which reads the environment map on a miss only:
+                                                 src/shaders/light/environment.slang:16-27): next-event estimation also samples the
+                                                 lat-long environment texture by luminance x sin(theta), MIS-combined with BSDF sampling.
+                                                 Same expectation, different samples: off by default so that results match the reference's. */
 };
 
 typedef struct vkrt_cuda_build_stats {

@@ -171,3 +171,54 @@ def textured(w, h, spp=2):
     prep["sceneData"]["environmentLight"] = (1.0, 1.0, 1.0, 1.0)
     prep["sceneData"]["environmentRotation"] = 25.0
     return prep
+
+
+def sunlit(w, h, spp=16, lamp=False, balls=True):
+    """A matte floor, a matte ball and a glossy ball under a lat-long RGBA32F environment whose energy sits in a small, very bright
+    sun (16 of 2048 texels): the case environment-map importance sampling exists for. `lamp` adds an emissive quad, so that the one
+    light sample per vertex has to be split between the environment and the emissive triangles. Roughness stays <= 0.5: the reference
+    draws GGX normals with the bounded-VNDF sampler (ggx.slang:180) but reports the unbounded VNDF density (ggx.slang:88-99), so for
+    alpha -> 1 a BSDF-sampled estimate sits 1 - 2.6 % above the quadrature of its own eval (measured on the oracle), and an estimator
+    that moves weight from BSDF sampling to light sampling inherits that offset. Below alpha = 0.25 the two agree to 0.05 %."""
+    env = np.ones((32, 64, 4), np.float32)
+    tt = (np.arange(32) + 0.5) / 32 * np.pi
+    env[..., 0] = 0.05 + 0.05 * np.clip(np.cos(tt), 0, 1)[:, None]
+    env[..., 1] = 0.07 + 0.06 * np.clip(np.cos(tt), 0, 1)[:, None]
+    env[..., 2] = 0.10 + 0.10 * np.clip(np.cos(tt), 0, 1)[:, None]
+    env[6:10, 20:24, :3] = (260.0, 230.0, 180.0)
+    textures = [dict(pixels=env, width=64, height=32, format=3, colorSpace=1)]
+    mats = np.zeros(5, hr.MATERIAL)
+    mats[:] = hr.default_material()
+    for k, (col, rough, metal) in enumerate([((0.7, 0.7, 0.7), 0.5, 0.0), ((0.8, 0.3, 0.2), 0.45, 0.0), ((0.9, 0.8, 0.5), 0.25, 1.0)]):
+        m = hr.default_material()
+        m["baseColor"], m["roughness"], m["metallic"] = col, rough, metal
+        mats[1 + k] = hr.sanitize_material(m, texture_count=1)
+    lm = hr.default_material()
+    lm["emissionLuminance"] = 12.0
+    mats[4] = hr.sanitize_material(lm, texture_count=1)
+    meshes = []
+    f = hr.quad_mesh("floor", 2.5)
+    f.material_index = 1
+    meshes.append(f)
+    if balls:
+        a = hr.uv_sphere_mesh("matte", 0.5, 24, 12)
+        a.world = hr.build_mesh_transform((-0.6, 0.1, 0.5), (0, 0, 0), (1, 1, 1))
+        a.material_index = 2
+        meshes.append(a)
+        b = hr.uv_sphere_mesh("glossy", 0.45, 24, 12)
+        b.world = hr.build_mesh_transform((0.6, -0.2, 0.45), (0, 0, 0), (1, 1, 1))
+        b.material_index = 3
+        meshes.append(b)
+    if lamp:
+        lq = hr.quad_mesh("lamp", 0.4)
+        lq.world = hr.build_mesh_transform((0.0, 0.6, 1.8), (180, 0, 0), (1, 1, 1))
+        lq.material_index = 4
+        meshes.append(lq)
+    st = hr.Settings(camera_pos=(0.3, -3.4, 1.6), camera_target=(0, 0, 0.35), vfov=38.0)
+    scene = hr.Scene(meshes=meshes, materials=mats, settings=st, textures=textures)
+    prep = scene.prepare(w, h)
+    prep["sceneData"]["samplesPerPixel"] = spp
+    prep["sceneData"]["environmentTextureIndex"] = 0
+    prep["sceneData"]["environmentLight"] = (1.0, 1.0, 1.0, 1.0)
+    prep["sceneData"]["environmentRotation"] = 40.0
+    return prep

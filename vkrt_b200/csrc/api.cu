@@ -26,6 +26,7 @@ void launchRaygen(int mode, const FrameParams& fp, int grid, cudaStream_t st);
 void launchShade(int mode, const FrameParams& fp, uint32_t depth, int grid, cudaStream_t st);
 void launchShadeSort(const FrameParams& fp, uint32_t depth, int smCount, cudaStream_t st);
 void launchFilm(int mode, const FrameParams& fp, int firstChunk, int lastChunk, int grid, cudaStream_t st);
+void launchEnvWeights(const SceneView& sc, uint32_t textureIndex, float* out, int grid, cudaStream_t st);
 void launchTrace(const TraceParams& tp, bool count, int grid, cudaStream_t st);  // picks the flat / two-level kernel from tp.scene.accel.flat
 void launchPrimaryRaygen(const FrameParams& fp, int jittered, int grid, cudaStream_t st);
 void launchProbeAccum(const ::float4* accum, const TileMap& tm, const uint32_t* l2g, const ::uint2* xy, uint32_t count, ::float4* out, cudaStream_t st);
@@ -113,6 +114,11 @@ struct vkrt_cuda_ctx {
     std::vector<DevBuf<uint8_t>*> texturePixels;
     DevBuf<TextureView> textures;
     uint32_t textureCount = 0;
+    // environment-map importance sampling (extension, VKRT_CUDA_FLAG_ENV_IMPORTANCE): table of the texture it was built from
+    DevBuf<float> envAliasQ, envPdfUv;
+    DevBuf<uint32_t> envAliasIdx;
+    uint32_t envTableTexture = VKRT_INVALID_INDEX, envTableW = 0, envTableH = 0;
+    bool envTableUsable = false;
 
     // accel
     AccelBuilder builder;
@@ -206,7 +212,7 @@ void invertAffine3x4(const float m[12], float out[12]) {
     out[11] = (float)(-(r20 * tx + r21 * ty + r22 * tz));
 }
 
-uint32_t modeFlagsFor(const SceneData& sd) {
+uint32_t modeFlagsFor(const SceneData& sd, bool envImportance) {
     uint32_t f = 0;
     if (sd.debugMode == VKRT_DEBUG_MODE_BSDF_ONLY) f |= MODE_BSDF_ONLY;
     if (sd.debugMode == VKRT_DEBUG_MODE_NEE_ONLY) f |= MODE_NEE_ONLY;
@@ -216,7 +222,7 @@ uint32_t modeFlagsFor(const SceneData& sd) {
     if (sd.debugMode == VKRT_DEBUG_MODE_DENOISER_FEATURE_VALIDITY) f |= MODE_DN_VALIDITY;
     if (sd.debugMode == VKRT_DEBUG_MODE_DENOISER_FEATURE_DEPTH) f |= MODE_DN_DEPTH;
     if (sd.debugMode == VKRT_DEBUG_MODE_DENOISER_FOLLOW_SPECULAR) f |= MODE_DN_FOLLOW;
-    if (sd.misNeeEnabled != 0u && sd.emissiveMeshCount > 0u) f |= MODE_NEE_ENABLED;
+    if (sd.misNeeEnabled != 0u && (sd.emissiveMeshCount > 0u || envImportance)) f |= MODE_NEE_ENABLED;
     return f;
 }
 
@@ -247,6 +253,7 @@ SceneView makeSceneView(vkrt_cuda_ctx* c) {
     v.accel.instanceCount = (uint32_t)c->hostMeshInfos.size();
     v.accel.flatPrims = c->flatPrims.p;
     v.accel.flat = c->accelFlat ? 1u : 0u;
+    v.env = {};
     v.accel.stackNeed = (c->flags & VKRT_CUDA_FLAG_DEEP_STACK) ? (uint32_t)TRACE_STACK_DEEP : c->stackNeed;
     return v;
 }
@@ -307,14 +314,75 @@ VKRT_Result resetAccumulation(vkrt_cuda_ctx* ctx) {
     return VKRT_SUCCESS;
 }
 
+// Builds (once per environment texture) the alias table the extension samples: texel weights on the device, Vose's method in
+// double precision on the host. Returns false when the texture carries no energy (the extension then stays off for the frame).
+VKRT_Result ensureEnvTable(vkrt_cuda_ctx* ctx, uint32_t textureIndex) {
+    if (ctx->envTableTexture == textureIndex) return VKRT_SUCCESS;
+    ctx->envTableTexture = textureIndex;
+    ctx->envTableUsable = false;
+    TextureView tv;
+    CU(cudaMemcpy(&tv, ctx->textures.p + textureIndex, sizeof(tv), cudaMemcpyDeviceToHost));
+    const uint64_t n64 = (uint64_t)tv.width * tv.height;
+    if (n64 == 0 || n64 > (1ull << 26)) return VKRT_SUCCESS;
+    const uint32_t n = (uint32_t)n64;
+    CU(ctx->envPdfUv.alloc(n));
+    launchEnvWeights(makeSceneView(ctx), textureIndex, ctx->envPdfUv.p, ctx->smCount * 8, ctx->stream);
+    std::vector<float> w(n);
+    CU(cudaMemcpyAsync(w.data(), ctx->envPdfUv.p, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    double sum = 0.0;
+    for (float x : w) sum += x;
+    if (!(sum > 0.0)) return VKRT_SUCCESS;
+    std::vector<double> scaled(n);
+    std::vector<float> q(n), pdfUv(n);
+    std::vector<uint32_t> alias(n), small, large;
+    for (uint32_t i = 0; i < n; i++) {
+        const double pmf = w[i] / sum;
+        pdfUv[i] = (float)(pmf * n);
+        scaled[i] = pmf * n;
+        alias[i] = i;
+        (scaled[i] < 1.0 ? small : large).push_back(i);
+    }
+    while (!small.empty() && !large.empty()) {
+        const uint32_t a = small.back(), b = large.back();
+        small.pop_back();
+        q[a] = (float)scaled[a];
+        alias[a] = b;
+        scaled[b] -= 1.0 - scaled[a];
+        if (scaled[b] < 1.0) { large.pop_back(); small.push_back(b); }
+    }
+    for (uint32_t i : large) q[i] = 1.0f;
+    for (uint32_t i : small) q[i] = 1.0f;
+    CU(ctx->envPdfUv.upload(pdfUv.data(), n, ctx->stream));
+    CU(ctx->envAliasQ.upload(q.data(), n, ctx->stream));
+    CU(ctx->envAliasIdx.upload(alias.data(), n, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->envTableW = tv.width;
+    ctx->envTableH = tv.height;
+    ctx->envTableUsable = true;
+    return VKRT_SUCCESS;
+}
+
 void fillFrameParams(vkrt_cuda_ctx* ctx, const SceneData& sd) {
     FrameParams& fp = ctx->fp;
     fp.scene = makeSceneView(ctx);
+    const bool envImportance = (ctx->flags & VKRT_CUDA_FLAG_ENV_IMPORTANCE) && sd.environmentTextureIndex < ctx->textureCount &&
+                               ctx->envTableTexture == sd.environmentTextureIndex && ctx->envTableUsable;
+    if (envImportance) {
+        EnvDistribution& e = fp.scene.env;
+        e.aliasQ = ctx->envAliasQ.p;
+        e.aliasIdx = ctx->envAliasIdx.p;
+        e.pdfUv = ctx->envPdfUv.p;
+        e.width = ctx->envTableW;
+        e.height = ctx->envTableH;
+        e.pEnv = sd.emissiveMeshCount > 0u ? 0.5f : 1.0f;
+        e.active = 1u;
+    }
     fp.sd = sd;
     fp.tiles = ctx->tiles;
     fp.tiles.localToGlobalTile = ctx->l2g.p;
     fp.readIndex = ctx->readIndex;
-    fp.modeFlags = modeFlagsFor(sd);
+    fp.modeFlags = modeFlagsFor(sd, envImportance);
 }
 
 TraceParams makeTraceParams(vkrt_cuda_ctx* ctx, uint32_t depth, bool haveExt, bool haveShadow) {
@@ -361,6 +429,10 @@ VKRT_Result enqueueFrame(vkrt_cuda_ctx* ctx, const SceneData* sceneData, uint32_
     if (sd.rrMaxDepth > 64u) sd.rrMaxDepth = 64u;
     const uint32_t spp = std::max(sd.samplesPerPixel, 1u);
     sd.samplesPerPixel = spp;
+    if ((ctx->flags & VKRT_CUDA_FLAG_ENV_IMPORTANCE) && sd.environmentTextureIndex < ctx->textureCount) {
+        const VKRT_Result r = ensureEnvTable(ctx, sd.environmentTextureIndex);
+        if (r != VKRT_SUCCESS) return r;
+    }
     fillFrameParams(ctx, sd);
     FrameParams& fp = ctx->fp;
     const uint32_t lpc = ctx->tiles.localPixelCount;
@@ -584,6 +656,8 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_set_textures(vkrt_cuda_ctx* ctx, const vkrt_
     CU(ctx->textures.upload(views.data(), textureCount, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->textureCount = textureCount;
+    ctx->envTableTexture = VKRT_INVALID_INDEX;  // the importance-sampling table follows the texture set
+    ctx->envTableUsable = false;
     return VKRT_SUCCESS;
 }
 

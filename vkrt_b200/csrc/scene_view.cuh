@@ -12,6 +12,19 @@ struct TextureView {
     uint32_t width, height, format, colorSpace;
 };
 
+// Optional extension (not in the reference, which looks the environment up on a miss only — light/environment.slang:16-27): a
+// piecewise-constant distribution over the texels of the lat-long environment map, weight = luminance x sin(theta), sampled through
+// an alias table by the next-event estimation and combined with BSDF sampling by the same MIS as the emissive triangles. Off unless
+// the context was created with VKRT_CUDA_FLAG_ENV_IMPORTANCE and the scene has an environment texture.
+struct EnvDistribution {
+    const float* aliasQ;        // [width * height]
+    const uint32_t* aliasIdx;
+    const float* pdfUv;         // probability density over the unit (u, v) square: pmf x width x height
+    uint32_t width, height;
+    float pEnv;                 // probability that a vertex's light sample goes to the environment (1 when there are no emissive triangles)
+    uint32_t active;
+};
+
 struct SceneView {
     const ShaderVertex* vertices;
     const uint32_t* indices;
@@ -29,6 +42,7 @@ struct SceneView {
     const float* srgbLut;  // 256 entries, computed once on the host (identical to the oracle's table)
     SpectralTables spectral;
     AccelView accel;
+    EnvDistribution env;
 };
 
 // ---- textures: LOD 0, bilinear, Vulkan texel-centre convention, sRGB decode per texel (core/scene/textures.c:141-209) ----

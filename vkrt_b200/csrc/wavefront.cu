@@ -242,6 +242,47 @@ struct DirectLightSurfaceSample {
     float shadowDistance, pdfSolidAngle;
     bool valid;
 };
+
+// ---- environment-map importance sampling (extension, see EnvDistribution) ----------------------------------------------------------
+// Solid-angle density of sampleEnvironmentLight for a direction: the inverse of sampleEnvironmentRadiance's lat-long mapping.
+static __device__ __noinline__ float environmentPdf(const SceneView& sc, const SceneData& scene, float3 worldDir) {
+    const EnvDistribution& E = sc.env;
+    const float3 dir = normalize(worldDir);
+    const float phi = atan2f(dir.y, dir.x) + scene.environmentRotation * (PI / 180.0f);
+    const float theta = acosf(clamp(dir.z, -1.0f, 1.0f));
+    const float sinTheta = sinf(theta);
+    if (!(sinTheta > 1e-6f)) return 0.0f;
+    const float u = frac(phi * (0.5f * INV_PI) + 0.5f), v = theta * INV_PI;
+    const uint32_t x = min((uint32_t)(u * float(E.width)), E.width - 1u), y = min((uint32_t)(v * float(E.height)), E.height - 1u);
+    return __ldg(E.pdfUv + (size_t)y * E.width + x) / (2.0f * PI * PI * sinTheta);
+}
+// One direction towards the environment: texel by the alias method (48 random bits for the cell, so that millions of texels are
+// addressed uniformly, one more number for the alias coin), uniform inside the texel. 5 random numbers.
+static __device__ __noinline__ DirectLightSurfaceSample sampleEnvironmentLight(const SceneView& sc, const SceneData& scene, uint& rng) {
+    const EnvDistribution& E = sc.env;
+    DirectLightSurfaceSample s;
+    s.valid = false;
+    s.shadowDistance = s.pdfSolidAngle = 0.0f;
+    const uint32_t n = E.width * E.height;
+    const uint64_t hi = (uint64_t)(rand(rng) * 16777216.0f), lo = (uint64_t)(rand(rng) * 16777216.0f);
+    uint32_t texel = (uint32_t)((((hi << 24) | lo) * (uint64_t)n) >> 48);
+    texel = min(texel, n - 1u);
+    if (!(rand(rng) < __ldg(E.aliasQ + texel))) texel = __ldg(E.aliasIdx + texel);
+    const uint32_t ty = texel / E.width, tx = texel - ty * E.width;
+    const float u = (float(tx) + rand(rng)) / float(E.width);
+    const float v = (float(ty) + rand(rng)) / float(E.height);
+    const float phi = (u - 0.5f) * (2.0f * PI) - scene.environmentRotation * (PI / 180.0f);
+    const float theta = v * PI;
+    const float sinTheta = sinf(theta), cosTheta_ = cosf(theta);
+    if (!(sinTheta > 1e-6f)) return s;
+    s.wi = float3(sinTheta * cosf(phi), sinTheta * sinf(phi), cosTheta_);
+    s.pdfSolidAngle = __ldg(E.pdfUv + texel) / (2.0f * PI * PI * sinTheta);
+    if (!(s.pdfSolidAngle > 0.0f)) return s;
+    s.emission = sampleEnvironmentRadiance(sc, scene, s.wi);
+    s.shadowDistance = RAY_T_MAX;
+    s.valid = true;
+    return s;
+}
 __device__ __forceinline__ DirectLightSurfaceSample sampleDirectLightSurface(const SceneView& sc, const SceneData& scene, float3 hitPoint, uint& rng) {
     DirectLightSurfaceSample s;
     s.valid = false;
@@ -318,7 +359,7 @@ __device__ __forceinline__ float computeSpectralMISWeight(float4 sampled, float4
 #else
 #define SHADE_SUBPHASE_BARRIER()
 #endif
-template <int MODE>
+template <int MODE, bool ENVIS>
 __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ FrameParams fp, const uint32_t depth) {
     const uint32_t count = fp.extCount[depth];
     const PathState& S = fp.st[depth & 1u];
@@ -411,7 +452,21 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const _
             // ---- miss: environment (loop.slang:4-6, */transport.slang accumulate*Environment) -------------------------
             if (hitInst == VKRT_INVALID_INDEX) {
                 if (!neeOnly && !mediumHasActiveBoundary(medium)) {
-                    const float3 env = sampleEnvironmentRadiance(sc, scene, ray.direction);
+                    float3 env = sampleEnvironmentRadiance(sc, scene, ray.direction);
+                    float heroWeight = (MODE == MODE_HERO && heroActive) ? heroWavelengthBalanceWeight(techPdf) : 1.0f;
+                    if (ENVIS) {
+                        // the environment is also reached by next-event estimation: weight the BSDF-sampled arrival exactly like an
+                        // emitter hit (integrator.slang:79-85 / mis_weights.slang:18-42 with the environment's solid-angle density)
+                        if ((fp.modeFlags & MODE_NEE_ENABLED) && (flags & PF_PREV_VERTEX_NEE_ALLOWED) && depth > 0u) {
+                            const float lp2 = environmentPdf(sc, scene, ray.direction) * sc.env.pEnv;
+                            if (MODE == MODE_HERO && heroActive) {
+                                const float4 pv = fromF4(S.prevVertexTechPdf[i]), pb = fromF4(S.prevBsdfTechPdf[i]);
+                                heroWeight = computeSpectralMISWeight(pv * pb, pv * lp2);
+                            } else if (prevBsdfPdf > 0.0f && lp2 > 0.0f) {
+                                env = env * powerHeuristic(prevBsdfPdf, lp2);
+                            }
+                        }
+                    }
                     if (MODE == MODE_RGB) {
                         ::float4 r = fp.rec.radiance[rec];
                         const float3 c = thrRgb * env;
@@ -420,7 +475,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const _
                     } else if (MODE == MODE_SINGLE) {
                         fp.rec.radiance[rec].x += thrScalar * spectralScalarFromLinearSrgb(T, env, lambdaScalar);
                     } else if (heroActive) {
-                        const float4 c = thr4 * heroWavelengthBalanceWeight(techPdf) * spectralScalarFromLinearSrgb4(T, env, wl4);
+                        const float4 c = thr4 * heroWeight * spectralScalarFromLinearSrgb4(T, env, wl4);
                         ::float4 r = fp.rec.radiance[rec];
                         r.x += c.x; r.y += c.y; r.z += c.z; r.w += c.w;
                         fp.rec.radiance[rec] = r;
@@ -511,7 +566,22 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const _
         uint32_t shadowSeed = 0u;
         bool shadowScalarLane = false;
         if (live && neeEnabled && currentVertexNeeAllowed && cosTheta(state.wo) > 0.0f) {
-            const DirectLightSurfaceSample ls = sampleDirectLightSurface(sc, scene, hitPoint, rng);
+            DirectLightSurfaceSample ls;
+            if (ENVIS) {
+                // one light sample per vertex, as in the reference: it goes to the environment with probability pEnv (a random number
+                // is spent on the choice only when the scene has emissive triangles too), and both densities carry that probability
+                const float pEnv = sc.env.pEnv;
+                if (pEnv >= 1.0f || rand(rng) < pEnv) {
+                    ls = sampleEnvironmentLight(sc, scene, rng);
+                    ls.pdfSolidAngle *= pEnv;
+                    if (mediumHasActiveBoundary(medium)) ls.valid = false;  // the environment is not seen from inside a medium (loop.slang:4-6)
+                } else {
+                    ls = sampleDirectLightSurface(sc, scene, hitPoint, rng);
+                    ls.pdfSolidAngle *= 1.0f - pEnv;
+                }
+            } else {
+                ls = sampleDirectLightSurface(sc, scene, hitPoint, rng);
+            }
             if (ls.valid) {
                 const float3 shadowOffset = dot(ls.wi, surface.geometricNormal) >= 0.0f ? surface.geometricNormal : -surface.geometricNormal;
                 const float3 shadowOrigin = hitPoint + shadowOffset * SHADOW_ORIGIN_OFFSET;
@@ -571,7 +641,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const _
                     if (MODE == MODE_HERO && heroActive) {
                         float misWeight = heroWavelengthBalanceWeight(techPdf);
                         if (misActive) {
-                            const float lp2 = lightPdfAreaToSolidAngle(mesh.lightPdfArea, surface.geometricNormal, ray.direction, hitT);
+                            const float lp2 = lightPdfAreaToSolidAngle(mesh.lightPdfArea, surface.geometricNormal, ray.direction, hitT) * (ENVIS ? 1.0f - sc.env.pEnv : 1.0f);
                             const float4 pv = fromF4(S.prevVertexTechPdf[i]), pb = fromF4(S.prevBsdfTechPdf[i]);
                             misWeight = computeSpectralMISWeight(pv * pb, pv * lp2);
                         }
@@ -582,7 +652,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const _
                     } else {
                         float misWeight = 1.0f;
                         if (misActive && prevBsdfPdf > 0.0f) {
-                            const float lp2 = lightPdfAreaToSolidAngle(mesh.lightPdfArea, surface.geometricNormal, ray.direction, hitT);
+                            const float lp2 = lightPdfAreaToSolidAngle(mesh.lightPdfArea, surface.geometricNormal, ray.direction, hitT) * (ENVIS ? 1.0f - sc.env.pEnv : 1.0f);
                             misWeight = lp2 <= 0.0f ? 1.0f : powerHeuristic(prevBsdfPdf, lp2);
                         }
                         if (MODE == MODE_RGB) {
@@ -1018,9 +1088,9 @@ int traceBlocksPerSm(bool count) {
 }
 int shadeBlocksPerSm(int mode) {
     int n = 0;
-    if (mode == MODE_RGB) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shade<MODE_RGB>, SHADE_BLOCK, 0);
-    else if (mode == MODE_SINGLE) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shade<MODE_SINGLE>, SHADE_BLOCK, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shade<MODE_HERO>, SHADE_BLOCK, 0);
+    if (mode == MODE_RGB) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shade<MODE_RGB, false>, SHADE_BLOCK, 0);
+    else if (mode == MODE_SINGLE) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shade<MODE_SINGLE, false>, SHADE_BLOCK, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shade<MODE_HERO, false>, SHADE_BLOCK, 0);
     return n > 0 ? n : 1;
 }
 
@@ -1031,10 +1101,29 @@ void launchRaygen(int mode, const FrameParams& fp, int grid, cudaStream_t st) {
     else k_raygen<MODE_HERO><<<grid, 256, 0, st>>>(fp);
 }
 void launchShade(int mode, const FrameParams& fp, uint32_t depth, int grid, cudaStream_t st) {
-    if (mode == MODE_RGB) k_shade<MODE_RGB><<<grid, SHADE_BLOCK, 0, st>>>(fp, depth);
-    else if (mode == MODE_SINGLE) k_shade<MODE_SINGLE><<<grid, SHADE_BLOCK, 0, st>>>(fp, depth);
-    else k_shade<MODE_HERO><<<grid, SHADE_BLOCK, 0, st>>>(fp, depth);
+    if (fp.scene.env.active) {  // environment-map importance sampling: separate instantiations, the default kernels are untouched
+        if (mode == MODE_RGB) k_shade<MODE_RGB, true><<<grid, SHADE_BLOCK, 0, st>>>(fp, depth);
+        else if (mode == MODE_SINGLE) k_shade<MODE_SINGLE, true><<<grid, SHADE_BLOCK, 0, st>>>(fp, depth);
+        else k_shade<MODE_HERO, true><<<grid, SHADE_BLOCK, 0, st>>>(fp, depth);
+        return;
+    }
+    if (mode == MODE_RGB) k_shade<MODE_RGB, false><<<grid, SHADE_BLOCK, 0, st>>>(fp, depth);
+    else if (mode == MODE_SINGLE) k_shade<MODE_SINGLE, false><<<grid, SHADE_BLOCK, 0, st>>>(fp, depth);
+    else k_shade<MODE_HERO, false><<<grid, SHADE_BLOCK, 0, st>>>(fp, depth);
 }
+// weight of every environment texel for the importance-sampling table: luminance x sin(theta of the texel row)
+__global__ void k_env_weights(const SceneView sc, uint32_t textureIndex, float* __restrict__ out) {
+    const TextureView t = sc.textures[textureIndex];
+    const uint32_t n = t.width * t.height;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t y = i / t.width, x = i - y * t.width;
+        const float4 c = fetchTexel(sc, t, (int)x, (int)y);
+        float w = linearSrgbLuminance(float3(c.x, c.y, c.z)) * sinf(PI * (float(y) + 0.5f) / float(t.height));
+        if (!(w > 0.0f) || !(w < 3.0e38f)) w = 0.0f;
+        out[i] = w;
+    }
+}
+void launchEnvWeights(const SceneView& sc, uint32_t textureIndex, float* out, int grid, cudaStream_t st) { k_env_weights<<<grid, 256, 0, st>>>(sc, textureIndex, out); }
 void launchFilm(int mode, const FrameParams& fp, int firstChunk, int lastChunk, int grid, cudaStream_t st) {
     if (mode == MODE_RGB) k_film<MODE_RGB><<<grid, 256, 0, st>>>(fp, firstChunk, lastChunk);
     else if (mode == MODE_SINGLE) k_film<MODE_SINGLE><<<grid, 256, 0, st>>>(fp, firstChunk, lastChunk);

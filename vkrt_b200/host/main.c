@@ -27,6 +27,7 @@ static void printHelp(void) {
     printf("  --render-output <path>    Save the image after completion (.exr linear, .png tone-mapped 16-bit)\n");
     printf("  --spectral <0|1|2>        Override render mode: 0 RGB, 1 spectral single wavelength, 2 spectral hero\n");
     printf("  --rgb2spec <path>         rgb2spec coefficient table (default: assets/rgb2spec/srgb.coeff)\n");
+    printf("  --env-importance          Extension: next-event estimation also samples the environment texture (not in the reference)\n");
     printf("\nFile Formats:\n  Import: binary glTF (.glb; geometry + scalar material factors)\n  Export: Image (.png, .exr)\n");
     printf("\nRequirements:\n  An NVIDIA B200 (sm_100a) and libvkrt_cuda.so\n");
 }
@@ -34,7 +35,7 @@ static void printHelp(void) {
 int main(int argc, char** argv) {
     const char* scene = NULL; const char* import = NULL; const char* output = NULL; const char* instancedGlb = NULL; const char* rgb2spec = "assets/rgb2spec/srgb.coeff";
     uint32_t width = 3840, height = 2160, samples = 16384, spp = 16, soup = 0, instanced = 0;
-    int device = -1, emptyScene = 0, spectral = -1;
+    int device = -1, emptyScene = 0, spectral = -1, envImportance = 0;
     for (int i = 1; i < argc; i++) {
         const char* a = argv[i];
 #define NEXT() (i + 1 < argc ? argv[++i] : (fprintf(stderr, "missing value for %s\n", a), exit(2), ""))
@@ -54,6 +55,7 @@ int main(int argc, char** argv) {
         else if (!strcmp(a, "--render-output")) output = NEXT();
         else if (!strcmp(a, "--spectral")) spectral = atoi(NEXT());
         else if (!strcmp(a, "--rgb2spec")) rgb2spec = NEXT();
+        else if (!strcmp(a, "--env-importance")) envImportance = 1;
         else { fprintf(stderr, "unknown option %s (see --help)\n", a); return 2; }
     }
     VKRT* vkrt = NULL;
@@ -61,6 +63,7 @@ int main(int argc, char** argv) {
     VKRT_CreateInfo ci;
     VKRT_defaultCreateInfo(&ci);
     ci.width = width; ci.height = height; ci.preferredDeviceIndex = device;
+    if (envImportance) ci.cudaFlags |= VKRT_CUDA_FLAG_ENV_IMPORTANCE;
     if (VKRT_initWithCreateInfo(vkrt, &ci) != VKRT_SUCCESS) { fprintf(stderr, "init failed: %s\n", VKRT_lastError(vkrt)); VKRT_destroy(vkrt); return 1; }
     VKRT_Result r = VKRT_SUCCESS;
     if (soup) r = VKRT_appGenerateSoup(vkrt, soup, 0);
