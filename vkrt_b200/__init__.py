@@ -21,6 +21,8 @@ FLAG_NO_MATERIAL_SORT = 2
 FLAG_STAGE_TIMING = 4
 FLAG_FORCE_TWO_LEVEL = 8
 FLAG_FORCE_FLAT = 16
+FLAG_DEEP_STACK = 32
+FLAG_ENV_IMPORTANCE = 64   # extension: environment-map importance sampling (not in the reference; include/vkrt_cuda.h)
 
 VKRT_SUCCESS = 0
 _ERRORS = {0: "SUCCESS", -1: "INVALID_ARGUMENT", -2: "OPERATION_FAILED", -3: "OUT_OF_MEMORY", -4: "DEVICE_LOST",

@@ -43,6 +43,7 @@ __device__ __forceinline__ float orderedToFloat(int i) { return __int_as_float(i
 __global__ void k_init_bounds(int* bounds) {
     if (threadIdx.x < 3) bounds[threadIdx.x] = floatToOrdered(FLT_MAX);
     else if (threadIdx.x < 6) bounds[threadIdx.x] = floatToOrdered(-FLT_MAX);
+    else if (threadIdx.x < 8) bounds[threadIdx.x] = 0;  // padding of the 8-int slot (copied to the host with the rest)
 }
 
 // Block-level reduction of per-thread boxes, then ONE set of six ordered-int atomics per block. Every thread of the block must call
