@@ -4,7 +4,8 @@
 Workload (BASELINE.json configs[1]): the bundled cornell scene (assets/scenes/cornell.json, bunny.glb standing in
 for the missing dragon.glb), 1920x1080, renderMode = spectral, spectralSamplingMode = hero, depth 4..8, NEE + MIS on, a procedural
 lat-long HDR sky as environment map (the bundled .exr environments are missing blobs upstream). One STEP = one frame
-(VKRT_draw) of `spp_per_step` samples per pixel over the whole image = W*H*spp camera paths; 1024 spp = 64 such steps at N = 1.
+(VKRT_draw) of `spp_per_step` samples per pixel over the whole image = W*H*spp camera paths; 1024 spp = 32 such steps at N = 1
+(32 spp per step: the frame's fixed cost — kernel tails, 45 launches — is ~1.2 ms, B200 probe: 8 / 16 / 32 / 64 spp per frame = 480 / 497 / 502 / 508 Mpaths/s).
 
   python bench.py --gpus N --steps K --warmup W            our arm (one process per GPU under torchrun for N > 1)
   python bench.py --impl reference ...                     the reference's algorithm on the host CPU (the oracle restatement;
@@ -12,13 +13,13 @@ lat-long HDR sky as environment map (the bundled .exr environments are missing b
 
 Multi-GPU: the image is partitioned into interleaved 32x32 tiles (vkrt_b200/csrc/tiles.h), the scene is replicated, there is no
 data-path collective; the film is gathered to rank 0 over NCCL once at the end of the timed region. Per-GPU work is kept fixed as N
-grows (spp_per_step = 16*N over the same 1080p image => "weak" scaling, value = all paths of all ranks / max-over-ranks time).
+grows (spp_per_step = 32*N over the same 1080p image => "weak" scaling, value = all paths of all ranks / max-over-ranks time).
 
 Timing: `value` = device time between two CUDA events recorded on the library's own stream (vkrt_cuda_timer_begin/end) around K
 asynchronously enqueued frames, inputs (scene, BVH, film) resident in HBM, barrier + synchronize on both sides, max over ranks.
 `e2e` = the same K frames through the public host API (VKRT_draw: SceneData comes from host memory every frame) plus a device->host
 read of the accumulation image into pinned memory every step (after an NCCL gather for N > 1), host wall clock, max over ranks.
-The per-step working set (wavefront queues, ~13 GB) is far larger than the 126 MB L2, so no explicit L2 flush is needed.
+The per-step working set (wavefront queues, ~28 GB) is far larger than the 126 MB L2, so no explicit L2 flush is needed.
 """
 import argparse
 import ctypes as C
@@ -480,7 +481,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
-    ap.add_argument("--spp", type=int, default=16, help="samples per pixel per step and per GPU")
+    ap.add_argument("--spp", type=int, default=32, help="samples per pixel per step and per GPU")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work spent on the cpu_baseline sample")
     ap.add_argument("--ref-step-seconds", type=float, default=3.0, help="CPU work per step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")

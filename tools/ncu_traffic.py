@@ -17,7 +17,7 @@ per = collections.defaultdict(lambda: collections.defaultdict(float))
 unit_scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
 for r in rows:
     name = r["Kernel Name"].split("(")[0].replace("void ", "").replace("vk::", "")
-    if name.startswith("k_shade<2>") or name.startswith("k_shade<(int)2>"):
+    if name.startswith(("k_shade<2>", "k_shade<(int)2>", "k_shade<2, 0>", "k_shade<(int)2, (bool)0>")):
         key = "k_shade<hero>"
     elif name.startswith("k_trace<0") or name.startswith("k_trace<(bool)0"):
         key = "k_trace"
