@@ -376,8 +376,8 @@ static inline int jExtend(int v, int n) { return v < (1 << (n - 1)) ? v - (1 << 
 #define J_FIX_2_053119869 16819
 #define J_FIX_2_562915447 20995
 #define J_FIX_3_072711026 25172
-#define J_DESCALE(x, n) (((x) + (1 << ((n) - 1))) >> (n))
-static inline uint8_t jClampSample(int v) {
+#define J_DESCALE(x, n) (((x) + ((int64_t)1 << ((n) - 1))) >> (n))
+static inline uint8_t jClampSample(int64_t v) {
     v += 128;
     return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
 }
@@ -388,21 +388,21 @@ static void jIdctIslow(const int16_t* coef, const uint16_t* quant, uint8_t* out,
         const uint16_t* q = quant + c;
         int* w = ws + c;
         if (!in[8] && !in[16] && !in[24] && !in[32] && !in[40] && !in[48] && !in[56]) {
-            int dc = (in[0] * q[0]) * 4;
-            for (int r = 0; r < 8; r++) w[r * 8] = dc;
+            int64_t dc = ((int64_t)in[0] * q[0]) * 4;
+            for (int r = 0; r < 8; r++) w[r * 8] = (int)dc;
             continue;
         }
-        int z2 = in[16] * q[16], z3 = in[48] * q[48];
-        int z1 = (z2 + z3) * J_FIX_0_541196100;
-        int tmp2 = z1 + z3 * (-J_FIX_1_847759065);
-        int tmp3 = z1 + z2 * J_FIX_0_765366865;
-        z2 = in[0] * q[0]; z3 = in[32] * q[32];
-        int tmp0 = (z2 + z3) * 8192, tmp1 = (z2 - z3) * 8192;
-        int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
-        tmp0 = in[56] * q[56]; tmp1 = in[40] * q[40]; tmp2 = in[24] * q[24]; tmp3 = in[8] * q[8];
+        int64_t z2 = (int64_t)in[16] * q[16], z3 = (int64_t)in[48] * q[48];
+        int64_t z1 = (z2 + z3) * J_FIX_0_541196100;
+        int64_t tmp2 = z1 + z3 * (-J_FIX_1_847759065);
+        int64_t tmp3 = z1 + z2 * J_FIX_0_765366865;
+        z2 = (int64_t)in[0] * q[0]; z3 = (int64_t)in[32] * q[32];
+        int64_t tmp0 = (z2 + z3) * 8192, tmp1 = (z2 - z3) * 8192;
+        int64_t tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+        tmp0 = (int64_t)in[56] * q[56]; tmp1 = (int64_t)in[40] * q[40]; tmp2 = (int64_t)in[24] * q[24]; tmp3 = (int64_t)in[8] * q[8];
         z1 = tmp0 + tmp3; z2 = tmp1 + tmp2; z3 = tmp0 + tmp2;
-        int z4 = tmp1 + tmp3;
-        int z5 = (z3 + z4) * J_FIX_1_175875602;
+        int64_t z4 = tmp1 + tmp3;
+        int64_t z5 = (z3 + z4) * J_FIX_1_175875602;
         tmp0 *= J_FIX_0_298631336; tmp1 *= J_FIX_2_053119869; tmp2 *= J_FIX_3_072711026; tmp3 *= J_FIX_1_501321110;
         z1 *= -J_FIX_0_899976223; z2 *= -J_FIX_2_562915447; z3 *= -J_FIX_1_961570560; z4 *= -J_FIX_0_390180644;
         z3 += z5; z4 += z5;
@@ -416,20 +416,20 @@ static void jIdctIslow(const int16_t* coef, const uint16_t* quant, uint8_t* out,
         const int* w = ws + r * 8;
         uint8_t* o = out + r * stride;
         if (!w[1] && !w[2] && !w[3] && !w[4] && !w[5] && !w[6] && !w[7]) {
-            uint8_t dc = jClampSample(J_DESCALE(w[0], 5));
-            for (int c = 0; c < 8; c++) o[c] = dc;
+            uint8_t dcs = jClampSample(J_DESCALE(w[0], 5));
+            for (int c = 0; c < 8; c++) o[c] = dcs;
             continue;
         }
-        int z2 = w[2], z3 = w[6];
-        int z1 = (z2 + z3) * J_FIX_0_541196100;
-        int tmp2 = z1 + z3 * (-J_FIX_1_847759065);
-        int tmp3 = z1 + z2 * J_FIX_0_765366865;
-        int tmp0 = (w[0] + w[4]) * 8192, tmp1 = (w[0] - w[4]) * 8192;
-        int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+        int64_t z2 = w[2], z3 = w[6];
+        int64_t z1 = (z2 + z3) * J_FIX_0_541196100;
+        int64_t tmp2 = z1 + z3 * (-J_FIX_1_847759065);
+        int64_t tmp3 = z1 + z2 * J_FIX_0_765366865;
+        int64_t tmp0 = ((int64_t)w[0] + w[4]) * 8192, tmp1 = ((int64_t)w[0] - w[4]) * 8192;
+        int64_t tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
         tmp0 = w[7]; tmp1 = w[5]; tmp2 = w[3]; tmp3 = w[1];
         z1 = tmp0 + tmp3; z2 = tmp1 + tmp2; z3 = tmp0 + tmp2;
-        int z4 = tmp1 + tmp3;
-        int z5 = (z3 + z4) * J_FIX_1_175875602;
+        int64_t z4 = tmp1 + tmp3;
+        int64_t z5 = (z3 + z4) * J_FIX_1_175875602;
         tmp0 *= J_FIX_0_298631336; tmp1 *= J_FIX_2_053119869; tmp2 *= J_FIX_3_072711026; tmp3 *= J_FIX_1_501321110;
         z1 *= -J_FIX_0_899976223; z2 *= -J_FIX_2_562915447; z3 *= -J_FIX_1_961570560; z4 *= -J_FIX_0_390180644;
         z3 += z5; z4 += z5;
@@ -446,7 +446,7 @@ static int jDecodeBlock(JDec* d, JComp* c, int16_t* coef) {
     int t = jDecodeHuff(d, &d->dc[c->td]);
     if (t < 0 || t > 16) return 0;
     int diff = t ? jExtend(jGetBits(d, t), t) : 0;
-    c->dcPred += diff;
+    c->dcPred = (int)((unsigned)c->dcPred + (unsigned)diff);  /* wraps instead of overflowing on corrupt streams */
     coef[0] = (int16_t)c->dcPred;
     for (int k = 1; k < 64;) {
         int rs = jDecodeHuff(d, &d->ac[c->ta]);
@@ -997,8 +997,9 @@ static int decodeExr(const uint8_t* data, size_t size, const char* label, HostIm
     }
     if (!nch || compression < 0 || !haveWindow || xmax < xmin || ymax < ymin) return imgFail(err, errLen, "EXR header decode from %s failed (missing attributes)", label);
     if (compression > 4) return imgFail(err, errLen, "EXR decode from %s failed (compression %d: only NONE, RLE, ZIPS, ZIP and PIZ are supported)", label, compression);
-    const uint32_t W = (uint32_t)(xmax - xmin + 1), H = (uint32_t)(ymax - ymin + 1);
-    if (W > (1u << 20) || H > (1u << 20)) return imgFail(err, errLen, "EXR image dimensions overflow for %s", label);
+    const int64_t W64 = (int64_t)xmax - xmin + 1, H64 = (int64_t)ymax - ymin + 1;  /* 64-bit: corrupt windows span the whole int range */
+    if (W64 > (1 << 20) || H64 > (1 << 20)) return imgFail(err, errLen, "EXR image dimensions overflow for %s", label);
+    const uint32_t W = (uint32_t)W64, H = (uint32_t)H64;
     size_t lineBytes = 0;
     int allHalf = 1;
     for (int i = 0; i < nch; i++) {
@@ -1033,12 +1034,12 @@ static int decodeExr(const uint8_t* data, size_t size, const char* label, HostIm
     for (uint32_t b = 0; b < blocks && good; b++) {
         uint64_t off;
         memcpy(&off, data + pos + (size_t)b * 8, 8);
-        if (off + 8 > size) { good = 0; why = "bad block offset"; break; }
+        if (off > size || size - off < 8) { good = 0; why = "bad block offset"; break; }  /* no wrap for offsets near 2^64 */
         int32_t y0;
         uint32_t dataSize;
         memcpy(&y0, data + off, 4);
         memcpy(&dataSize, data + off + 4, 4);
-        if (off + 8 + dataSize > size || y0 < ymin || y0 > ymax) { good = 0; why = "bad block header"; break; }
+        if (dataSize > size - off - 8 || y0 < ymin || y0 > ymax) { good = 0; why = "bad block header"; break; }
         const uint32_t firstLine = (uint32_t)(y0 - ymin);
         const uint32_t lines = firstLine + linesPerBlock <= H ? linesPerBlock : H - firstLine;
         const size_t rawLen = lineBytes * lines;
