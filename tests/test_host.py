@@ -171,3 +171,28 @@ def test_alias_table_reconstructs_pmf():
         np.add.at(rec, np.arange(n), q.astype(np.float64) / n)
         np.add.at(rec, idx.astype(np.int64), (1.0 - q.astype(np.float64)) / n)
         assert np.allclose(rec, pmf, atol=2e-6)
+
+
+def test_glb_with_an_out_of_range_index_fails_to_import(tmp_path):
+    """src/app/mesh/loader.c:1855-1862: an index >= vertexCount fails the primitive and with it the import (it would otherwise become an
+    out-of-bounds vertex fetch on the device)."""
+    import json
+    import struct
+    from vkrt_b200 import host
+    raw = bytearray(open(os.path.join(H.ROOT, "assets", "models", "cube.glb"), "rb").read())
+    json_len = struct.unpack_from("<I", raw, 12)[0]
+    doc = json.loads(raw[20:20 + json_len].decode())
+    acc = doc["accessors"][doc["meshes"][0]["primitives"][0]["indices"]]
+    view = doc["bufferViews"][acc["bufferView"]]
+    at = 20 + json_len + 8 + view.get("byteOffset", 0) + acc.get("byteOffset", 0)
+    width = {5121: 1, 5123: 2, 5125: 4}[acc["componentType"]]
+    raw[at:at + width] = b"\xff" * width
+    bad = tmp_path / "bad_index.glb"
+    bad.write_bytes(bytes(raw))
+    hs = host.Host(host_only=True, width=64, height=36)
+    with pytest.raises(Exception):
+        hs.import_mesh(str(bad))
+    assert hs.mesh_count() == 0
+    hs.import_mesh(os.path.join(H.ROOT, "assets", "models", "cube.glb"))   # the unmodified file still imports
+    assert hs.mesh_count() == 1
+    hs.close()

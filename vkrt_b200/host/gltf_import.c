@@ -502,7 +502,10 @@ static int importPrimitive(ImportCtx* c, const hj_value* gmesh, const hj_value* 
         ni = a.count;
         idx = (uint32_t*)malloc((ni ? ni : 1) * sizeof(uint32_t));
         if (!idx) { free(v); return fail(c, "out of memory"); }
-        for (size_t i = 0; i < ni; i++) idx[i] = readIndex(&a, i); /* indices are always widened to uint32 */
+        for (size_t i = 0; i < ni; i++) {
+            idx[i] = readIndex(&a, i); /* indices are always widened to uint32 */
+            if (idx[i] >= nv) { free(idx); free(v); return fail(c, "index out of range"); } /* loader.c:1859: the primitive, and with it the import, fails */
+        }
     } else {
         ni = nv;
         idx = (uint32_t*)malloc(ni * sizeof(uint32_t));
