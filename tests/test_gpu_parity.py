@@ -359,6 +359,22 @@ def test_environment_importance_flag_is_inert_without_environment_texture():
     assert np.array_equal(films[0].view(np.uint32), films[1].view(np.uint32))
 
 
+def test_out_of_range_index_is_refused_at_build():
+    """The ABI copies caller buffers in; an index that does not address a vertex of its geometry is refused by vkrt_cuda_build_accel
+    (VKRT_ERROR_INVALID_ARGUMENT) before any kernel dereferences it."""
+    prep = scenes.cornell(32, 32)
+    prep["indices"] = prep["indices"].copy()
+    prep["indices"][7] = 0x7FFFFFF0
+    g = H.CudaBackend()
+    with pytest.raises(Exception, match="build_accel"):
+        g.upload(prep)
+    g.close()
+    g = H.CudaBackend()
+    g.upload(scenes.cornell(32, 32))   # the intact scene builds
+    assert g.build_stats.triangleCount > 0
+    g.close()
+
+
 def test_dispersive_glass_hero_collapse():
     """Rough glass with an Abbe number: hero paths collapse to one wavelength on refraction (spectral_hero/transport.slang:77-87)."""
     w = h = 96

@@ -682,7 +682,7 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_build_accel(vkrt_cuda_ctx* ctx, vkrt_cuda_bu
     cudaSetDevice(ctx->device);
     const uint32_t n = (uint32_t)ctx->hostMeshInfos.size();
     // --- unique geometries (geometry.c:166-210 decides sharing on the host; here it arrives as geometrySource) ---
-    struct BlasDesc { uint32_t vertexBase, indexBase, triCount, nodeBase, primBase, nodeCount; };
+    struct BlasDesc { uint32_t vertexBase, indexBase, triCount, nodeBase, primBase, nodeCount, vertexLimit; };
     std::vector<BlasDesc> blas;
     std::vector<uint32_t> instanceBlas(n);
     std::map<std::tuple<uint32_t, uint32_t, uint32_t>, uint32_t> byRange;
@@ -692,6 +692,7 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_build_accel(vkrt_cuda_ctx* ctx, vkrt_cuda_bu
         const MeshInfo& mi = ctx->hostMeshInfos[i];
         if ((uint64_t)mi.indexBase + mi.indexCount > ctx->indexCount) return fail(ctx, VKRT_ERROR_INVALID_ARGUMENT, "instance %u: index range out of bounds", i);
         if (mi.materialIndex >= ctx->hostMaterials.size()) return fail(ctx, VKRT_ERROR_INVALID_ARGUMENT, "instance %u: material index out of range", i);
+        if ((uint64_t)mi.vertexBase + mi.vertexCount > ctx->vertexCount) return fail(ctx, VKRT_ERROR_INVALID_ARGUMENT, "instance %u: vertex range out of bounds", i);
         auto key = std::make_tuple(mi.vertexBase, mi.indexBase, mi.indexCount);
         uint32_t b;
         bool found = false;
@@ -704,7 +705,7 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_build_accel(vkrt_cuda_ctx* ctx, vkrt_cuda_bu
         }
         if (!found) {
             b = (uint32_t)blas.size();
-            blas.push_back({mi.vertexBase, mi.indexBase, mi.indexCount / 3u, 0u, 0u, 0u});
+            blas.push_back({mi.vertexBase, mi.indexBase, mi.indexCount / 3u, 0u, 0u, 0u, mi.vertexCount ? mi.vertexCount : ctx->vertexCount - mi.vertexBase});
             totalTris += mi.indexCount / 3u;
             if (!ctx->hostGeometrySource.empty()) bySource[ctx->hostGeometrySource[i]] = b;
             else byRange[key] = b;
@@ -713,6 +714,16 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_build_accel(vkrt_cuda_ctx* ctx, vkrt_cuda_bu
         instancedTris += mi.indexCount / 3u;
     }
     if (totalTris > 0xFFFFFFF0ull) return fail(ctx, VKRT_ERROR_INVALID_ARGUMENT, "too many triangles");
+    {   // every index must address a vertex of its geometry before any kernel dereferences it (one pass over the index buffer)
+        DevBuf<uint32_t> badIndex;
+        CU(badIndex.alloc(1));
+        CU(cudaMemsetAsync(badIndex.p, 0, sizeof(uint32_t), ctx->stream));
+        for (const BlasDesc& d : blas) launchValidateIndices(ctx->indices.p, d.indexBase, d.triCount * 3u, d.vertexLimit, badIndex.p, ctx->stream);
+        uint32_t bad = 0;
+        CU(cudaMemcpyAsync(&bad, badIndex.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (bad) return fail(ctx, VKRT_ERROR_INVALID_ARGUMENT, "index buffer addresses a vertex outside its geometry");
+    }
     // ---- single-level variant: one BVH over all instanced triangles in world space ------------------------------------------------
     // Instancing (shared BLASes under a TLAS) pays when geometry is reused many times; when it is not — a handful of instances, or many
     // overlapping meshes like the 16-mesh triangle soup, where a ray enters 9 BLASes — a flat BVH traverses far fewer nodes.

@@ -27,6 +27,7 @@ void launchPackTriangles(const ShaderVertex* vertices, const uint32_t* indices, 
                          ::float4* trianglesOut, uint32_t primBase, cudaStream_t st);
 void launchGeometryBounds(const ShaderVertex* vertices, const uint32_t* indices, uint32_t vertexBase, uint32_t indexBase, uint32_t triCount, int* bounds6,
                           cudaStream_t st);
+void launchValidateIndices(const uint32_t* indices, uint32_t indexBase, uint32_t indexCount, uint32_t vertexLimit, uint32_t* flag, cudaStream_t st);
 float orderedIntToFloatHost(int i);
 void launchFlatGatherTriangles(const uint2* flatPrims, const ::float4* src, uint32_t total, ::float4* dst, cudaStream_t st);
 void launchRelocateNodes(const Bvh8Node* src, Bvh8Node* dst, uint32_t count, uint32_t oldBase, uint32_t newBase, cudaStream_t st);

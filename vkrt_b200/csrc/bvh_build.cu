@@ -162,6 +162,16 @@ void launchGeometryBounds(const ShaderVertex* vertices, const uint32_t* indices,
     k_init_bounds<<<1, 32, 0, st>>>(bounds6);
     if (triCount) k_geometry_bounds<<<boundsGrid(triCount), 256, 0, st>>>(vertices, indices, vertexBase, indexBase, triCount, bounds6);
 }
+// Raises *flag when an index of the range does not address a vertex of its geometry (the ABI copies caller data in; an index past the
+// vertex buffer would otherwise become an out-of-bounds fetch in every later kernel).
+__global__ void k_validate_indices(const uint32_t* __restrict__ indices, uint32_t indexBase, uint32_t indexCount, uint32_t vertexLimit, uint32_t* flag) {
+    bool bad = false;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < indexCount; i += gridDim.x * blockDim.x) bad |= indices[indexBase + i] >= vertexLimit;
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
+}
+void launchValidateIndices(const uint32_t* indices, uint32_t indexBase, uint32_t indexCount, uint32_t vertexLimit, uint32_t* flag, cudaStream_t st) {
+    if (indexCount) k_validate_indices<<<boundsGrid(indexCount), 256, 0, st>>>(indices, indexBase, indexCount, vertexLimit, flag);
+}
 float orderedIntToFloatHost(int i) {
     int b = i >= 0 ? i : i ^ 0x7fffffff;
     float f;
