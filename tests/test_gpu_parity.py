@@ -375,6 +375,30 @@ def test_out_of_range_index_is_refused_at_build():
     g.close()
 
 
+def test_inconsistent_light_tables_are_refused():
+    """vkrt_cuda_set_lights checks every link of the alias / emissive tables (the light sampler follows them blindly), and a frame may
+    not name more emissive meshes than were uploaded."""
+    import copy
+    good = scenes.cornell(32, 32)
+    for field, value in (("triAliasIdx", 1 << 30), ("meshAliasIdx", 7)):
+        prep = copy.deepcopy(good)
+        prep["lights"][field] = prep["lights"][field].copy()
+        prep["lights"][field][0] = value
+        g = H.CudaBackend()
+        with pytest.raises(Exception, match="set_lights"):
+            g.upload(prep)
+        g.close()
+    g = H.CudaBackend()
+    g.upload(good)
+    g.resize(32, 32)
+    sd = good["sceneData"].copy()
+    sd["emissiveMeshCount"] = 5
+    with pytest.raises(Exception):
+        g.render(sd, frames=1)
+    g.render(good["sceneData"], frames=1)   # the consistent frame still renders
+    g.close()
+
+
 def test_dispersive_glass_hero_collapse():
     """Rough glass with an Abbe number: hero paths collapse to one wavelength on refraction (spectral_hero/transport.slang:77-87)."""
     w = h = 96

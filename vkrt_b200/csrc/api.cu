@@ -114,6 +114,7 @@ struct vkrt_cuda_ctx {
     std::vector<DevBuf<uint8_t>*> texturePixels;
     DevBuf<TextureView> textures;
     uint32_t textureCount = 0;
+    uint32_t lightMeshCount = 0;  // emissive meshes uploaded by vkrt_cuda_set_lights (SceneData.emissiveMeshCount may not exceed it)
     // environment-map importance sampling (extension, VKRT_CUDA_FLAG_ENV_IMPORTANCE): table of the texture it was built from
     DevBuf<float> envAliasQ, envPdfUv;
     DevBuf<uint32_t> envAliasIdx;
@@ -427,6 +428,7 @@ VKRT_Result enqueueFrame(vkrt_cuda_ctx* ctx, const SceneData* sceneData, uint32_
     const int mode = renderModeOf(sd);
     if (mode != 0 && !ctx->haveRgb2spec) return fail(ctx, VKRT_ERROR_OPERATION_FAILED, "spectral rendering needs vkrt_cuda_set_rgb2spec");
     if (sd.rrMaxDepth > 64u) sd.rrMaxDepth = 64u;
+    if (sd.emissiveMeshCount > ctx->lightMeshCount) return fail(ctx, VKRT_ERROR_INVALID_ARGUMENT, "render_frame: SceneData names %u emissive meshes, %u uploaded", sd.emissiveMeshCount, ctx->lightMeshCount);
     const uint32_t spp = std::max(sd.samplesPerPixel, 1u);
     sd.samplesPerPixel = spp;
     if ((ctx->flags & VKRT_CUDA_FLAG_ENV_IMPORTANCE) && sd.environmentTextureIndex < ctx->textureCount) {
@@ -623,7 +625,16 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_set_lights(vkrt_cuda_ctx* ctx, const Emissiv
     if (!ctx) return VKRT_ERROR_INVALID_ARGUMENT;
     if (meshCount && (!meshes || !meshAliasQ || !meshAliasIdx)) return VKRT_ERROR_INVALID_ARGUMENT;
     if (triangleCount && (!triangles || !triAliasQ || !triAliasIdx)) return VKRT_ERROR_INVALID_ARGUMENT;
+    // the tables are followed blindly by the light sampler (light_sampling.slang:9-37): every link must stay inside them
+    for (uint32_t m = 0; m < meshCount; m++) {
+        if (meshAliasIdx[m] >= meshCount) return fail(ctx, VKRT_ERROR_INVALID_ARGUMENT, "light tables: mesh alias %u out of range", m);
+        const EmissiveMesh& em = meshes[m];
+        if ((uint64_t)em.triOffset + em.triCount > triangleCount) return fail(ctx, VKRT_ERROR_INVALID_ARGUMENT, "light tables: emissive mesh %u triangle range out of bounds", m);
+        for (uint32_t k = 0; k < em.triCount; k++)
+            if (triAliasIdx[em.triOffset + k] >= em.triCount) return fail(ctx, VKRT_ERROR_INVALID_ARGUMENT, "light tables: triangle alias %u of mesh %u out of range", k, m);
+    }
     cudaSetDevice(ctx->device);
+    ctx->lightMeshCount = meshCount;
     CU(ctx->emissiveMeshes.upload(meshes, meshCount, ctx->stream));
     CU(ctx->emissiveTriangles.upload(triangles, triangleCount, ctx->stream));
     CU(ctx->meshAliasQ.upload(meshAliasQ, meshCount, ctx->stream));
