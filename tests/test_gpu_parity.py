@@ -399,6 +399,46 @@ def test_inconsistent_light_tables_are_refused():
     g.close()
 
 
+@ACCEL
+@pytest.mark.parametrize("bad", [np.nan, np.inf, 3.0e38], ids=["nan", "inf", "huge"])
+def test_triangles_with_non_finite_vertices_are_inactive(accel, bad):
+    """Vulkan acceleration structures (what the reference builds, accel/blas.c) treat a triangle with a NaN vertex as inactive; here every
+    triangle with a non-finite or overflowing coordinate collapses to a point inside the builder: it is never hit, everything else
+    renders exactly as if that triangle were degenerate, and the context survives (a NaN vertex used to fault the build kernels)."""
+    w = h = 64
+    good = scenes.cornell(w, h, spp=2)
+    tri = 40                                              # a triangle of the scene, made inactive through one of its vertices
+    mesh = next(m for m in good["meshInfos"] if m["indexBase"] <= 3 * tri < m["indexBase"] + m["indexCount"])   # indices are local to a geometry
+    first, last = int(mesh["indexBase"]) // 3, int(mesh["indexBase"] + mesh["indexCount"]) // 3
+    vi = int(good["indices"][3 * tri]) + int(mesh["vertexBase"])
+    films, ids = [], []
+    for variant in ("non_finite", "degenerate"):
+        prep = dict(good)
+        if variant == "non_finite":
+            v = good["vertices"].copy()
+            v["position"][vi, 1] = bad
+            prep["vertices"] = v
+        # reference image: the same triangles degenerate (all three corners on one vertex) in a scene without the bad value
+        idx = good["indices"].copy()
+        users = first + np.nonzero((idx.reshape(-1, 3)[first:last] == idx[3 * tri]).any(axis=1))[0]
+        if variant == "degenerate":
+            for t in users:
+                keep = [c for c in idx[3 * t:3 * t + 3] if c != idx[3 * tri]]
+                idx[3 * t:3 * t + 3] = keep[0] if keep else idx[3 * tri]
+            prep["indices"] = idx
+        g = H.CudaBackend(flags=accel)
+        g.upload(prep)
+        g.resize(w, h)
+        g.trace_primary(prep["sceneData"])
+        ids.append(g.read(H.AOV_HITID_CENTER).copy())
+        g.render(prep["sceneData"], frames=2)
+        films.append(g.read(H.AOV_ACCUM).copy())
+        g.close()
+    assert np.isfinite(films[0]).all()
+    assert np.array_equal(ids[0], ids[1])
+    assert np.array_equal(films[0].view(np.uint32), films[1].view(np.uint32))
+
+
 def test_dispersive_glass_hero_collapse():
     """Rough glass with an Abbe number: hero paths collapse to one wavelength on refraction (spectral_hero/transport.slang:77-87)."""
     w = h = 96

@@ -90,19 +90,30 @@ __device__ __forceinline__ void padBox(float3& lo, float3& hi) {
     hi = hi + float3(eps);
 }
 
+// A triangle with a non-finite (or absurdly large: extents and areas must not overflow) coordinate is INACTIVE, as in the Vulkan acceleration
+// structure the reference builds ("if the X component of a vertex is NaN the triangle is inactive"): it keeps its slot and its primitive
+// index but collapses to one finite point, so it is never hit and the builder only ever sees finite boxes.
+__device__ __forceinline__ bool finiteCoord(float x) { return fabsf(x) <= 1.0e18f; }  // false for NaN
+__device__ __forceinline__ bool finitePoint(float3 v) { return finiteCoord(v.x) && finiteCoord(v.y) && finiteCoord(v.z); }
+__device__ __forceinline__ void deactivateIfNonFinite(float3& a, float3& b, float3& c) {
+    if (finitePoint(a) && finitePoint(b) && finitePoint(c)) return;
+    const float3 p = finitePoint(a) ? a : (finitePoint(b) ? b : (finitePoint(c) ? c : float3(0.0f)));
+    a = b = c = p;
+}
+
 __global__ void k_triangle_bounds(const ShaderVertex* __restrict__ vertices, const uint32_t* __restrict__ indices, uint32_t vertexBase,
                                   uint32_t indexBase, uint32_t triCount, ::float4* __restrict__ primLo, ::float4* __restrict__ primHi,
                                   int* bounds) {
     float3 accLo(FLT_MAX), accHi(-FLT_MAX);
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < triCount; t += gridDim.x * blockDim.x) {
-        float3 lo(FLT_MAX), hi(-FLT_MAX);
+        float3 v[3];
         for (int k = 0; k < 3; k++) {
             uint32_t vi = indices[indexBase + t * 3u + k] + vertexBase;
             ::float4 p = *reinterpret_cast<const ::float4*>(vertices[vi].position);
-            float3 v(p.x, p.y, p.z);
-            lo = min(lo, v);
-            hi = max(hi, v);
+            v[k] = float3(p.x, p.y, p.z);
         }
+        deactivateIfNonFinite(v[0], v[1], v[2]);
+        float3 lo = min(min(v[0], v[1]), v[2]), hi = max(max(v[0], v[1]), v[2]);
         padBox(lo, hi);
         primLo[t] = make_float4(lo.x, lo.y, lo.z, 0.0f);
         primHi[t] = make_float4(hi.x, hi.y, hi.z, 0.0f);
@@ -147,13 +158,15 @@ __global__ void k_geometry_bounds(const ShaderVertex* __restrict__ vertices, con
                                   uint32_t triCount, int* bounds6) {
     float3 lo(FLT_MAX), hi(-FLT_MAX);
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < triCount; t += gridDim.x * blockDim.x) {
+        float3 v[3];
         for (int k = 0; k < 3; k++) {
             uint32_t vi = indices[indexBase + t * 3u + k] + vertexBase;
             ::float4 p = *reinterpret_cast<const ::float4*>(vertices[vi].position);
-            float3 v(p.x, p.y, p.z);
-            lo = min(lo, v);
-            hi = max(hi, v);
+            v[k] = float3(p.x, p.y, p.z);
         }
+        deactivateIfNonFinite(v[0], v[1], v[2]);
+        lo = min(lo, min(min(v[0], v[1]), v[2]));
+        hi = max(hi, max(max(v[0], v[1]), v[2]));
     }
     reduceBounds(lo, hi, bounds6);
 }
@@ -202,13 +215,19 @@ __global__ void k_flat_bounds(const ShaderVertex* __restrict__ vertices, const u
         const uint2 fp = flatIn[p];
         const uint4 inst = flatInstances[fp.x];
         const float* m = world3x4 + (size_t)fp.x * 12;
+        float3 o[3], w[3];
         for (int k = 0; k < 3; k++) {
             uint32_t vi = indices[inst.y + fp.y * 3u + k] + inst.x;
             ::float4 q = *reinterpret_cast<const ::float4*>(vertices[vi].position);
-            float3 w(m[0] * q.x + m[1] * q.y + m[2] * q.z + m[3], m[4] * q.x + m[5] * q.y + m[6] * q.z + m[7], m[8] * q.x + m[9] * q.y + m[10] * q.z + m[11]);
-            lo = min(lo, w);
-            hi = max(hi, w);
+            o[k] = float3(q.x, q.y, q.z);
         }
+        deactivateIfNonFinite(o[0], o[1], o[2]);  // the same object-space decision as the packed triangle record (k_pack_triangles)
+        for (int k = 0; k < 3; k++)
+            w[k] = float3(m[0] * o[k].x + m[1] * o[k].y + m[2] * o[k].z + m[3], m[4] * o[k].x + m[5] * o[k].y + m[6] * o[k].z + m[7],
+                          m[8] * o[k].x + m[9] * o[k].y + m[10] * o[k].z + m[11]);
+        if (!(finitePoint(w[0]) && finitePoint(w[1]) && finitePoint(w[2]))) w[0] = w[1] = w[2] = float3(0.0f);  // a transform that overflows
+        lo = min(min(w[0], w[1]), w[2]);
+        hi = max(max(w[0], w[1]), w[2]);
         padBox(lo, hi);
         padBox(lo, hi);
         primLo[p] = make_float4(lo.x, lo.y, lo.z, 0.0f);
@@ -227,6 +246,11 @@ __global__ void k_pack_triangles(const ShaderVertex* __restrict__ vertices, cons
     for (int k = 0; k < 3; k++) {
         uint32_t vi = indices[indexBase + t * 3u + k] + vertexBase;
         v[k] = *reinterpret_cast<const ::float4*>(vertices[vi].position);
+    }
+    {
+        float3 a(v[0].x, v[0].y, v[0].z), b(v[1].x, v[1].y, v[1].z), c(v[2].x, v[2].y, v[2].z);
+        deactivateIfNonFinite(a, b, c);   // an inactive triangle becomes a zero-area record: the watertight test rejects it (det == 0)
+        v[0] = make_float4(a.x, a.y, a.z, 0.0f); v[1] = make_float4(b.x, b.y, b.z, 0.0f); v[2] = make_float4(c.x, c.y, c.z, 0.0f);
     }
     v[0].w = __uint_as_float(t);
     v[1].w = 0.0f;
