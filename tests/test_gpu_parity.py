@@ -306,6 +306,29 @@ def test_deep_stack_kernel_is_bit_identical(accel):
     assert np.array_equal(films[0].view(np.uint32), films[1].view(np.uint32))
 
 
+@pytest.mark.parametrize("mode", ["rgb", "hero"])
+def test_converged_images_agree_across_sample_sets(mode):
+    """The other tests compare the two implementations on IDENTICAL samples. Here the sample sets are disjoint (the seed is a function of
+    pixel, frame and sample index: the oracle renders frames 1000..1015, the GPU frames 0..63), so agreement is statistical: the
+    converged images must coincide. Bounds: whole-image mean within 1 %, 8x8 block means within 4 % RMS of the mean."""
+    w, h = 96, 64
+    prep = scenes.cornell(w, h, spp=16)
+    spectral = mode != "rgb"
+    if spectral:
+        prep["sceneData"]["packedRenderSettings"] = H.hr.pack_render_settings(0, 1, 1)
+    o, g = scenes.both_backends(prep, w, h, spectral=spectral)
+    o.render(prep["sceneData"], frames=16, first_frame=1000)   # 256 spp on the CPU
+    g.render(prep["sceneData"], frames=64, first_frame=0)      # 1024 spp on the GPU
+    a, b = o.read(H.AOV_ACCUM)[..., :3].astype(np.float64), g.read(H.AOV_ACCUM)[..., :3].astype(np.float64)
+    assert np.isfinite(a).all() and np.isfinite(b).all()
+    ma, mb = a.mean(), b.mean()
+    assert abs(ma - mb) <= 0.01 * ma, (ma, mb)
+    ba, bb = _block_mean(a), _block_mean(b)
+    rms = np.sqrt(((ba - bb) ** 2).mean()) / ma
+    print("block-mean rRMS %.4f" % rms)
+    assert rms < 0.04, rms
+
+
 def _block_mean(img, b=8):
     h, w, c = img.shape
     return img[:h // b * b, :w // b * b].reshape(h // b, b, w // b, b, c).mean(axis=(1, 3))
