@@ -58,7 +58,15 @@ int main(int argc, char** argv) {
             ci.hostOnly = 1;
             ci.width = 64; ci.height = 64;
             if (VKRT_initWithCreateInfo(vkrt, &ci) != VKRT_SUCCESS) return 2;
-            if (VKRT_appLoadScene(vkrt, scratch) == VKRT_SUCCESS) loaded++; else rejected++;
+            if (VKRT_appLoadScene(vkrt, scratch) == VKRT_SUCCESS) {
+                /* the host half of the scene update: geometry packing, dedup, instance transforms, light tables, uniform */
+                VKRT_PreparedScene prepared;
+                memset(&prepared, 0, sizeof(prepared));
+                if (VKRT_updateScene(vkrt) == VKRT_SUCCESS) (void)VKRT_prepareScene(vkrt, &prepared);
+                loaded++;
+            } else {
+                rejected++;
+            }
             VKRT_destroy(vkrt);
             free(buf);
         }

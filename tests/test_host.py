@@ -196,3 +196,35 @@ def test_glb_with_an_out_of_range_index_fails_to_import(tmp_path):
     hs.import_mesh(os.path.join(H.ROOT, "assets", "models", "cube.glb"))   # the unmodified file still imports
     assert hs.mesh_count() == 1
     hs.close()
+
+
+@pytest.mark.parametrize("edit", ["negative_mesh_material", "fractional_material_index", "huge_material_index", "missing_mesh_material"])
+def test_scene_file_with_a_bad_material_reference_is_refused(tmp_path, edit):
+    """controller.c:368-377,905-927: material indices in a scene file must be non-negative integers below 2^32 and every mesh must carry one;
+    a negative index used to wrap to 4 billion and grow the material list until memory ran out. Indices past 2^20 are refused outright."""
+    import json
+    import shutil
+    from vkrt_b200 import host
+    doc = json.load(open(os.path.join(H.ROOT, "assets", "scenes", "prism.json")))
+    if edit == "negative_mesh_material":
+        doc["meshes"][0]["materialIndex"] = -2
+    elif edit == "fractional_material_index":
+        doc["materials"][0]["index"] = 1.5
+    elif edit == "huge_material_index":
+        doc["meshes"][0]["materialIndex"] = 4000000000
+    else:
+        del doc["meshes"][0]["materialIndex"]
+    (tmp_path / "scenes").mkdir()
+    shutil.copytree(os.path.join(H.ROOT, "assets", "models"), str(tmp_path / "models"))
+    bad = tmp_path / "scenes" / "bad.json"
+    bad.write_text(json.dumps(doc))
+    hs = host.Host(host_only=True, width=64, height=36)
+    with pytest.raises(Exception):
+        hs.load_scene(str(bad))
+    hs.close()
+    good = tmp_path / "scenes" / "good.json"
+    good.write_text(json.dumps(json.load(open(os.path.join(H.ROOT, "assets", "scenes", "prism.json")))))
+    hs = host.Host(host_only=True, width=64, height=36)
+    hs.load_scene(str(good))
+    assert hs.mesh_count() > 0
+    hs.close()

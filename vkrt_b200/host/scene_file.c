@@ -43,6 +43,21 @@ static void optIndex(const hj_value* o, const char* key, uint32_t* out) { /* num
     else if (v->type == HJ_NUMBER && v->number >= 0.0) *out = (uint32_t)v->number;
 }
 
+/* controller.c:368-377 jsonToUInt32: a JSON number that is a non-negative integer below 2^32, nothing else */
+static int jsonToUInt32(const hj_value* v, uint32_t* out) {
+    *out = 0u;
+    if (!v || v->type != HJ_NUMBER) return 0;
+    const double d = hj_number(v, -1.0);
+    if (!(d >= 0.0) || d > 4294967295.0) return 0;
+    const uint32_t c = (uint32_t)d;
+    if ((double)c != d) return 0;
+    *out = c;
+    return 1;
+}
+/* Slots a scene file may name. The reference grows its material list one VKRT_addMaterial at a time up to whatever index the file
+ * states (controller.c:933-945), i.e. until memory runs out for a corrupt index; here such a file is refused instead. */
+#define SCENE_MAX_MATERIAL_INDEX (1u << 20)
+
 static Material parseMaterialJson(const hj_value* o) {
     Material m = VKRT_materialDefault();
     optFloats(o, "baseColor", m.baseColor, 3);
@@ -201,7 +216,9 @@ VKRT_Result VKRT_appLoadScene(VKRT* vkrt, const char* scenePath) {
     /* 1b. standalone textures at their saved indices, then the environment map (controller.c:690-716,1274-1312) */
     const hj_value* texImports = hj_get(root, "textureImports");
     for (size_t k = 0; k < hj_count(texImports); k++) {
-        uint32_t saved = (uint32_t)hj_number(hj_get(hj_at(texImports, k), "index"), -1);
+        uint32_t saved = VKRT_INVALID_INDEX;
+        if (!jsonToUInt32(hj_get(hj_at(texImports, k), "index"), &saved)) saved = VKRT_INVALID_INDEX;
+        if (saved != VKRT_INVALID_INDEX && saved >= VKRT_MAX_BINDLESS_TEXTURES) { r = hostFail(vkrt, VKRT_ERROR_OPERATION_FAILED, "textureImports[%zu]: index %u out of range", k, saved); goto done; }
         if (saved != VKRT_INVALID_INDEX && saved + 1u > textureMapCount) textureMapCount = saved + 1u;
     }
     textureMap = (uint32_t*)malloc((textureMapCount ? textureMapCount : 1u) * sizeof(uint32_t));
@@ -238,7 +255,9 @@ VKRT_Result VKRT_appLoadScene(VKRT* vkrt, const char* scenePath) {
     unsigned char* keep = (unsigned char*)calloc(vkrt->meshCount ? vkrt->meshCount : 1, 1);
     for (size_t k = 0; k < nSaved; k++) {
         const hj_value* jm = hj_at(meshes, k);
-        uint32_t ii = (uint32_t)hj_number(hj_get(jm, "importIndex"), -1), li = (uint32_t)hj_number(hj_get(jm, "importLocalIndex"), -1);
+        uint32_t ii, li;
+        if (!jsonToUInt32(hj_get(jm, "importIndex"), &ii)) ii = VKRT_INVALID_INDEX;
+        if (!jsonToUInt32(hj_get(jm, "importLocalIndex"), &li)) li = VKRT_INVALID_INDEX;
         if (ii >= nImports || li >= importCount[ii]) { r = hostFail(vkrt, VKRT_ERROR_OPERATION_FAILED, "meshes[%zu]: bad import reference", k); break; }
         savedToLoaded[k] = importFirst[ii] + li;
         keep[savedToLoaded[k]] = 1;
@@ -257,18 +276,24 @@ VKRT_Result VKRT_appLoadScene(VKRT* vkrt, const char* scenePath) {
     /* 3. materials at their saved slots (slot 0 stays the default material) */
     const hj_value* mats = hj_get(root, "materials");
     uint32_t highest = 0;
+    /* controller.c:905-927: an explicit material index and every mesh's materialIndex must be valid unsigned integers */
     for (size_t k = 0; k < hj_count(mats); k++) {
-        uint32_t idx = (uint32_t)hj_number(hj_get(hj_at(mats, k), "index"), (double)k);
+        uint32_t idx = (uint32_t)k;
+        const hj_value* explicitIndex = hj_get(hj_at(mats, k), "index");
+        if (explicitIndex && !jsonToUInt32(explicitIndex, &idx)) { r = hostFail(vkrt, VKRT_ERROR_OPERATION_FAILED, "materials[%zu]: bad index", k); goto done; }
         if (idx > highest) highest = idx;
     }
     for (size_t k = 0; k < nSaved; k++) {
-        uint32_t idx = (uint32_t)hj_number(hj_get(hj_at(meshes, k), "materialIndex"), 0);
+        uint32_t idx;
+        if (!jsonToUInt32(hj_get(hj_at(meshes, k), "materialIndex"), &idx)) { r = hostFail(vkrt, VKRT_ERROR_OPERATION_FAILED, "meshes[%zu]: bad materialIndex", k); goto done; }
         if (idx > highest) highest = idx;
     }
+    if (highest > SCENE_MAX_MATERIAL_INDEX) { r = hostFail(vkrt, VKRT_ERROR_OPERATION_FAILED, "material index %u out of range", highest); goto done; }
     while (vkrt->materialCount < highest + 1u && r == VKRT_SUCCESS) r = VKRT_addMaterial(vkrt, NULL, NULL, NULL);
     for (size_t k = 0; k < hj_count(mats) && r == VKRT_SUCCESS; k++) {
         const hj_value* jm = hj_at(mats, k);
-        uint32_t idx = (uint32_t)hj_number(hj_get(jm, "index"), (double)k);
+        uint32_t idx = (uint32_t)k;
+        if (hj_get(jm, "index")) (void)jsonToUInt32(hj_get(jm, "index"), &idx);   /* validated above */
         const hj_value* body = hj_get(jm, "material");
         if (!body || body->type != HJ_OBJECT || !hj_string(hj_get(jm, "name"), NULL)) { r = hostFail(vkrt, VKRT_ERROR_OPERATION_FAILED, "materials[%zu] malformed", k); break; }
         Material m = parseMaterialJson(body);
@@ -285,7 +310,9 @@ VKRT_Result VKRT_appLoadScene(VKRT* vkrt, const char* scenePath) {
         uint32_t mi = savedToLoaded[k];
         VKRT_setMeshName(vkrt, mi, hj_string(hj_get(jm, "name"), "mesh"));
         int assigned = hj_bool(hj_get(jm, "hasMaterialAssignment"), 0);
-        r = assigned ? VKRT_setMeshMaterialIndex(vkrt, mi, (uint32_t)hj_number(hj_get(jm, "materialIndex"), 0)) : VKRT_clearMeshMaterialAssignment(vkrt, mi);
+        uint32_t meshMaterial = 0u;
+        (void)jsonToUInt32(hj_get(jm, "materialIndex"), &meshMaterial);   /* validated above */
+        r = assigned ? VKRT_setMeshMaterialIndex(vkrt, mi, meshMaterial) : VKRT_clearMeshMaterialAssignment(vkrt, mi);
         if (r == VKRT_SUCCESS) r = VKRT_setMeshOpacity(vkrt, mi, (float)hj_number(hj_get(jm, "opacity"), 1.0));
         if (r == VKRT_SUCCESS) r = VKRT_setMeshRenderBackfaces(vkrt, mi, hj_bool(hj_get(jm, "renderBackfaces"), 0) ? 1u : 0u);
     }
