@@ -73,6 +73,24 @@ int main(int argc, char** argv) {
                 (void)sink;
                 gltfImportFree(&imp);
                 imported++;
+                /* and through the host: import into a host-only handle, then the host half of the scene update (packing, dedup,
+                 * instance transforms, emissive / alias tables) */
+                VKRT* vkrt = NULL;
+                if (VKRT_create(&vkrt) == VKRT_SUCCESS) {
+                    VKRT_CreateInfo ci;
+                    VKRT_defaultCreateInfo(&ci);
+                    ci.hostOnly = 1;
+                    ci.width = 64; ci.height = 64;
+                    if (VKRT_initWithCreateInfo(vkrt, &ci) == VKRT_SUCCESS && VKRT_appImportMesh(vkrt, scratch, NULL, NULL) == VKRT_SUCCESS) {
+                        VKRT_PreparedScene prepared;
+                        memset(&prepared, 0, sizeof(prepared));
+                        if (VKRT_updateScene(vkrt) == VKRT_SUCCESS && VKRT_prepareScene(vkrt, &prepared) == VKRT_SUCCESS) {
+                            for (uint32_t k = 0; k < prepared.emissiveMeshCount; k++)
+                                if (prepared.meshAliasIdx[k] >= prepared.emissiveMeshCount) { fprintf(stderr, "mesh alias out of range\n"); abort(); }
+                        }
+                    }
+                    VKRT_destroy(vkrt);
+                }
             } else {
                 rejected++;
             }
