@@ -228,3 +228,36 @@ def test_scene_file_with_a_bad_material_reference_is_refused(tmp_path, edit):
     hs.load_scene(str(good))
     assert hs.mesh_count() > 0
     hs.close()
+
+
+@pytest.mark.parametrize("bad", [float("nan"), float("inf"), 3.0e38], ids=["nan", "inf", "huge"])
+def test_light_tables_stay_finite_with_a_non_finite_emissive_vertex(tmp_path, bad):
+    """An emissive triangle whose area is NaN / infinite (a non-finite vertex: the triangle is inactive in the acceleration structure)
+    is left out of the light tables like a zero-area one (lighting.c:302), so pmf, invTotalArea and MeshInfo.lightPdfArea stay finite
+    (they used to turn NaN and with them every emitter-hit MIS weight of that mesh)."""
+    import json
+    import struct
+    from vkrt_b200 import host
+    raw = open(os.path.join(H.ROOT, "assets", "models", "cube.glb"), "rb").read()
+    json_len = struct.unpack_from("<I", raw, 12)[0]
+    doc = json.loads(raw[20:20 + json_len].decode())
+    doc["materials"][0]["emissiveFactor"] = [1.0, 0.8, 0.6]
+    js = json.dumps(doc).encode()
+    js += b" " * ((4 - len(js) % 4) % 4)
+    bin_chunk = bytearray(raw[20 + json_len:])
+    struct.pack_into("<f", bin_chunk, 8, bad)          # x of the first POSITION (bufferView 0 starts the BIN payload)
+    out = bytearray(raw[:12]) + struct.pack("<I", len(js)) + b"JSON" + js + bin_chunk
+    struct.pack_into("<I", out, 8, len(out))
+    glb = tmp_path / "emissive_cube.glb"
+    glb.write_bytes(bytes(out))
+    hs = host.Host(host_only=True, width=64, height=36)
+    hs.import_mesh(str(glb))
+    p = hs.prepare_scene()
+    assert len(p["emissiveMeshes"]) == 1
+    em = p["emissiveMeshes"][0]
+    assert 0 < em["triCount"] < 12                      # the triangles of the bad vertex are left out, the rest still emit
+    for k in ("pmfMesh", "invTotalArea"):
+        assert np.isfinite(em[k]) and em[k] > 0
+    assert np.isfinite(np.asarray(p["triAliasQ"])).all() and np.asarray(p["triAliasIdx"]).max() < em["triCount"]
+    assert np.isfinite(p["meshInfos"]["lightPdfArea"]).all() and p["meshInfos"]["lightPdfArea"][0] > 0
+    hs.close()

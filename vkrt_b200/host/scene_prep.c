@@ -478,7 +478,7 @@ VKRT_Result hostRebuildLights(VKRT* vkrt) {
             for (int k = 0; k < 3; k++) { e1[k] = p1[k] - p0[k]; e2[k] = p2[k] - p0[k]; }
             h_cross3(e1, e2, cr);
             float area = 0.5f * h_norm3(cr);
-            if (area <= 0.0f) continue;
+            if (!(area > 0.0f) || !isfinite(area)) continue;   /* lighting.c:302 skips area <= 0; a NaN / infinite area (non-finite vertex: an inactive triangle) is skipped too */
             EmissiveTriangle* et = &vkrt->emissiveTriangles[nTri++];
             memset(et, 0, sizeof(*et));
             et->v0Area[0] = p0[0]; et->v0Area[1] = p0[1]; et->v0Area[2] = p0[2]; et->v0Area[3] = area;
@@ -488,7 +488,7 @@ VKRT_Result hostRebuildLights(VKRT* vkrt) {
         }
         uint32_t valid = nTri - triOffset;
         float selectionWeight = totalArea * ew;
-        if (selectionWeight <= 0.0f || valid == 0u) { nTri = triOffset; continue; }
+        if (!(selectionWeight > 0.0f) || !isfinite(selectionWeight) || valid == 0u) { nTri = triOffset; continue; }
         float invTotalArea = 1.0f / totalArea;
         for (uint32_t t = 0; t < valid; t++) pmf[t] = vkrt->emissiveTriangles[triOffset + t].v0Area[3] * invTotalArea;
         if (!hostBuildAliasTable(pmf, valid, vkrt->triAliasQ + triOffset, vkrt->triAliasIdx + triOffset)) { rc = hostFail(vkrt, VKRT_ERROR_OPERATION_FAILED, "triangle alias table"); break; }
