@@ -138,10 +138,29 @@ class ClockSampler:
 # CPU baseline / reference arm: the oracle (oracle/oracle.cpp, a line-by-line CPU restatement of the reference's shaders with a
 # BVH2 traverser) on the host cores. This is the only place bench.py touches oracle/.
 # ------------------------------------------------------------------------------------------------------------------------------
+def cpu_tag():
+    """Names this host's CPU (model + feature flags): the -march=native oracle build is per machine, and oracle/_build travels from the
+    build container to the GPU box."""
+    import hashlib
+    model, flags = "", ""
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name") and not model:
+                model = line.split(":", 1)[1].strip()
+            elif line.startswith("flags") and not flags:
+                flags = " ".join(sorted(line.split(":", 1)[1].split()))
+            if model and flags:
+                break
+    except OSError:
+        pass
+    return hashlib.sha1((model + "|" + flags).encode()).hexdigest()[:12]
+
+
 class OracleRunner:
     def __init__(self, prep, width, height, threads):
-        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "native"])
-        self.lib = C.CDLL(os.path.join(ROOT, "oracle", "_build", "liboracle_native.so"))
+        tag = cpu_tag()
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "native", "NATIVE_TAG=" + tag])
+        self.lib = C.CDLL(os.path.join(ROOT, "oracle", "_build", "liboracle_native_%s.so" % tag))
         self.ctx = C.c_void_p()
         assert self.lib.oracle_create(C.byref(self.ctx)) == 0
         self.threads = threads or self.lib.oracle_max_threads()
