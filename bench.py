@@ -389,8 +389,12 @@ def _run_ours(args, real_stdout):
     launches = trace_launches = 0
     trace_ms = shade_ms = frame_ms = 0.0
     ext = sh = local_paths = 0
-    for _ in range(args.warmup):
-        hs.draw()
+    for _ in range(args.warmup):   # warm-up steps are whole steps: draw + gather + device->host read (the first read into a fresh pinned
+        hs.draw()                  # buffer costs ~60 ms once)
+        if world > 1:
+            check(lib.vkrt_cuda_gather(ctx, C.byref(gather_ms)), "gather")
+        if rank == 0:
+            check(lib.vkrt_cuda_read_aov(ctx, C.c_int(0), pinned_ptr, C.c_size_t(w * h * 16)), "read_aov")
     barrier()
     t0 = time.time()
     tw0 = time.perf_counter()
