@@ -23,6 +23,7 @@
 
 #include "accel.h"
 #include "shading.h"
+#include "../include/vkrt_closure.h"
 
 namespace orc {
 
@@ -418,6 +419,16 @@ struct TraceCounters {
 // is order dependent when a segment crosses both glass and an opaque occluder. Pinned here (and in the CUDA kernel) as:
 // an accepted hit on a non-transmissive instance ends the search (OCCLUDED); accepted hits on transmissive instances only
 // raise sawTransmissive (-> UNSUPPORTED_TRANSMISSION if nothing opaque is found). Order independent.
+// Optional per-thread stand-in for the driver's any-hit stage (oracle/ref_slang/refshade_entry.cpp runs the reference's own any-hit
+// shaders through it); nullptr = the oracle's hashed stochastic alpha test above. `transmissiveInstance` reports which transmissive
+// instance a shadow ray met (the reference's shadow closest-hit shader wants an instance index).
+struct AnyHitHook {
+    bool (*accept)(void* user, uint32_t inst, uint32_t prim, float t, float u, float v) = nullptr;
+    void* user = nullptr;
+    uint32_t transmissiveInstance = 0xFFFFFFFFu;
+};
+static thread_local AnyHitHook* g_anyHitHook = nullptr;
+
 static void intersectInstance(const Ctx& c, uint32_t inst, const Ray& ray, uint32_t raySeed, bool anyHit, HitRecord& best, float& tBest,
                               bool& done, bool& sawTransmissive) {
     const Instance& I = c.instances[inst];
@@ -435,9 +446,18 @@ static void intersectInstance(const Ctx& c, uint32_t inst, const Ray& ray, uint3
         if (!watertightTriangle(o, sh, b.tri[(size_t)prim * 3], b.tri[(size_t)prim * 3 + 1], b.tri[(size_t)prim * 3 + 2], t, u, v)) return;
         if (!(t > ray.tMin)) return;
         if (!hitCloser(t, inst, prim, best, tBest)) return;
-        if (I.alphaTested && !alphaHitAccepted(c, inst, prim, float2(u, v), raySeed)) return;
+        if (I.alphaTested) {
+            const bool accepted = g_anyHitHook && g_anyHitHook->accept ? g_anyHitHook->accept(g_anyHitHook->user, inst, prim, t, u, v)
+                                                                       : alphaHitAccepted(c, inst, prim, float2(u, v), raySeed);
+            if (!accepted) return;
+        }
         if (anyHit) {
-            if (instanceTransmissive) { sawTransmissive = true; skipInstance = true; return; }
+            if (instanceTransmissive) {
+                sawTransmissive = true;
+                skipInstance = true;
+                if (g_anyHitHook) g_anyHitHook->transmissiveInstance = inst;
+                return;
+            }
             best.instance = inst;
             best.primitive = prim;
             done = true;
@@ -1520,6 +1540,45 @@ ORC_API void oracle_bsdf_eval_hero(oracle_ctx* c, const Material* m, const float
     float4 tp;
     float4 v = evalSpectralBSDF(C(c)->spectral, st, float3(wi[0], wi[1], wi[2]), wl, tp);
     out8[0] = v.x; out8[1] = v.y; out8[2] = v.z; out8[3] = v.w; out8[4] = tp.x; out8[5] = tp.y; out8[6] = tp.z; out8[7] = tp.w;
+}
+// Batched closure evaluation, record layout of include/vkrt_closure.h (shared with vkrt_cuda_eval_closures and refshade_eval_closures).
+ORC_API int oracle_eval_closures(oracle_ctx* c, const vkrt_closure_query* q, uint32_t count, vkrt_closure_result* out) {
+    if (!c || !q || !out) return -1;
+    const SpectralTables& T = C(c)->spectral;
+    for (uint32_t i = 0; i < count; i++) {
+        const vkrt_closure_query& Q = q[i];
+        vkrt_closure_result R = {};
+        BSDFMaterial bm(Q.material);
+        const float3 wo(Q.wo[0], Q.wo[1], Q.wo[2]), wi(Q.wi[0], Q.wi[1], Q.wi[2]);
+        const float4 wl(Q.wavelengths[0], Q.wavelengths[1], Q.wavelengths[2], Q.wavelengths[3]);
+        BSDFState st(bm, wo, Q.frontFace, Q.mode == 0u ? 0.0f : wl.x, Q.mode == 0u ? 0u : 1u);
+        ShadingBasis b;
+        b.tangent = float3(1, 0, 0); b.bitangent = float3(0, 1, 0); b.normal = float3(0, 0, 1);
+        uint32_t rng = Q.rng;
+        if (Q.mode == 2u) {
+            float4 tp(0.0f);
+            const float4 v = evalSpectralBSDF(T, st, wi, wl, tp);
+            R.evalValue[0] = v.x; R.evalValue[1] = v.y; R.evalValue[2] = v.z; R.evalValue[3] = v.w;
+            R.evalPdf[0] = tp.x; R.evalPdf[1] = tp.y; R.evalPdf[2] = tp.z; R.evalPdf[3] = tp.w;
+            const SpectralBSDFSample s = sampleSpectralBSDF(T, st, b, wl, rng);
+            R.sampleWi[0] = s.wi.x; R.sampleWi[1] = s.wi.y; R.sampleWi[2] = s.wi.z;
+            R.sampleWeight[0] = s.weight.x; R.sampleWeight[1] = s.weight.y; R.sampleWeight[2] = s.weight.z; R.sampleWeight[3] = s.weight.w;
+            R.samplePdf[0] = s.techniquePdf.x; R.samplePdf[1] = s.techniquePdf.y; R.samplePdf[2] = s.techniquePdf.z; R.samplePdf[3] = s.techniquePdf.w;
+            R.sampleFlags = (s.isUsable() ? 1u : 0u) | (s.isTransmission != 0u ? 2u : 0u);
+        } else {
+            const BSDFEval e = Q.mode == 0u ? evalBSDF(T, st, wi) : evalSingleWavelengthBSDF(T, st, wi);
+            R.evalValue[0] = e.value.x; R.evalValue[1] = e.value.y; R.evalValue[2] = e.value.z;
+            R.evalPdf[0] = e.pdf;
+            const BSDFSample s = sampleBSDF(T, st, b, rng);
+            R.sampleWi[0] = s.wi.x; R.sampleWi[1] = s.wi.y; R.sampleWi[2] = s.wi.z;
+            R.sampleWeight[0] = s.weight.x; R.sampleWeight[1] = s.weight.y; R.sampleWeight[2] = s.weight.z;
+            R.samplePdf[0] = s.pdf;
+            R.sampleFlags = (s.isUsable() ? 1u : 0u) | (s.isTransmission != 0u ? 2u : 0u);
+        }
+        R.rngAfter = rng;
+        out[i] = R;
+    }
+    return 0;
 }
 ORC_API int oracle_watertight(const float* org, const float* dir, const float* v0, const float* v1, const float* v2, float* tuv) {
     RayShear sh = makeRayShear(float3(dir[0], dir[1], dir[2]));

@@ -74,37 +74,40 @@ static inline void h_rotate(hmat4 m, float angle, const float* axis) {
         for (int row = 0; row < 4; row++) m[col][row] = a[0][row] * r[col][0] + a[1][row] * r[col][1] + a[2][row] * r[col][2];
 }
 
-/* General 4x4 inverse by cofactors (fp32). */
+/* General 4x4 inverse (fp32). The reference calls cglm's glm_mat4_inv (src/core/scene/camera.c:141-142), which on x86-64 is the SSE2
+ * routine glm_mat4_inv_sse2 (cglm simd/sse2/mat4.h, built without FMA): twelve 2x2 sub-determinants c1..c12 (product - product), the
+ * determinant as ((c2 c7 + c3 c10) + (c1 c8 + c4 c9)) - (c12 c5 + c11 c6), the sub-determinants scaled by 1 / det BEFORE the cofactor
+ * sums, each cofactor as (x cA - y cB) + z cC, signs applied by flipping the sign bit. This scalar code performs the same IEEE
+ * operations in the same order, lane by lane, so that viewInverse / projInverse -- and with them every primary ray -- are bit-identical
+ * to the reference's (tests/test_reference_pin.py::test_camera_matrices_are_bit_identical_to_the_reference). */
 static inline void h_mat4_inv(hmat4 mat, hmat4 dest) {
-    float a = mat[0][0], b = mat[0][1], c = mat[0][2], d = mat[0][3], e = mat[1][0], f = mat[1][1], g = mat[1][2], h = mat[1][3],
-          i = mat[2][0], j = mat[2][1], k = mat[2][2], l = mat[2][3], m = mat[3][0], n = mat[3][1], o = mat[3][2], p = mat[3][3];
-    float t[6];
+    const float a = mat[0][0], b = mat[0][1], c = mat[0][2], d = mat[0][3], e = mat[1][0], f = mat[1][1], g = mat[1][2], h = mat[1][3],
+                i = mat[2][0], j = mat[2][1], k = mat[2][2], l = mat[2][3], m = mat[3][0], n = mat[3][1], o = mat[3][2], p = mat[3][3];
+    float c1 = k * p - l * o, c2 = c * h - d * g, c3 = i * p - l * m, c4 = a * h - d * e;
+    float c5 = j * p - l * n, c6 = b * h - d * f, c11 = i * o - k * m, c12 = a * g - c * e;
+    float c7 = i * n - j * m, c8 = a * f - b * e, c9 = j * o - k * n, c10 = b * g - c * f;
+    const float det = ((c2 * c7 + c3 * c10) + (c1 * c8 + c4 * c9)) - (c12 * c5 + c11 * c6);
+    const float idt = 1.0f / det;
+    c1 *= idt; c2 *= idt; c3 *= idt; c4 *= idt; c5 *= idt; c6 *= idt;
+    c7 *= idt; c8 *= idt; c9 *= idt; c10 *= idt; c11 *= idt; c12 *= idt;
     hmat4 r;
-    t[0] = k * p - o * l; t[1] = j * p - n * l; t[2] = j * o - n * k;
-    t[3] = i * p - m * l; t[4] = i * o - m * k; t[5] = i * n - m * j;
-    r[0][0] = f * t[0] - g * t[1] + h * t[2];
-    r[1][0] = -(e * t[0] - g * t[3] + h * t[4]);
-    r[2][0] = e * t[1] - f * t[3] + h * t[5];
-    r[3][0] = -(e * t[2] - f * t[4] + g * t[5]);
-    r[0][1] = -(b * t[0] - c * t[1] + d * t[2]);
-    r[1][1] = a * t[0] - c * t[3] + d * t[4];
-    r[2][1] = -(a * t[1] - b * t[3] + d * t[5]);
-    r[3][1] = a * t[2] - b * t[4] + c * t[5];
-    t[0] = g * p - o * h; t[1] = f * p - n * h; t[2] = f * o - n * g;
-    t[3] = e * p - m * h; t[4] = e * o - m * g; t[5] = e * n - m * f;
-    r[0][2] = b * t[0] - c * t[1] + d * t[2];
-    r[1][2] = -(a * t[0] - c * t[3] + d * t[4]);
-    r[2][2] = a * t[1] - b * t[3] + d * t[5];
-    r[3][2] = -(a * t[2] - b * t[4] + c * t[5]);
-    t[0] = g * l - k * h; t[1] = f * l - j * h; t[2] = f * k - j * g;
-    t[3] = e * l - i * h; t[4] = e * k - i * g; t[5] = e * j - i * f;
-    r[0][3] = -(b * t[0] - c * t[1] + d * t[2]);
-    r[1][3] = a * t[0] - c * t[3] + d * t[4];
-    r[2][3] = -(a * t[1] - b * t[3] + d * t[5]);
-    r[3][3] = a * t[2] - b * t[4] + c * t[5];
-    float det = 1.0f / (a * r[0][0] + b * r[1][0] + c * r[2][0] + d * r[3][0]);
-    for (int col = 0; col < 4; col++)
-        for (int row = 0; row < 4; row++) dest[col][row] = r[col][row] * det;
+    r[0][0] = (f * c1 - g * c5) + h * c9;
+    r[0][1] = -((b * c1 - c * c5) + d * c9);
+    r[0][2] = (n * c2 - o * c6) + p * c10;
+    r[0][3] = -((j * c2 - k * c6) + l * c10);
+    r[1][0] = -((e * c1 - g * c3) + h * c11);
+    r[1][1] = (a * c1 - c * c3) + d * c11;
+    r[1][2] = -((m * c2 - o * c4) + p * c12);
+    r[1][3] = (i * c2 - k * c4) + l * c12;
+    r[2][0] = (e * c5 - f * c3) + h * c7;
+    r[2][1] = -((a * c5 - b * c3) + d * c7);
+    r[2][2] = (m * c6 - n * c4) + p * c8;
+    r[2][3] = -((i * c6 - j * c4) + l * c8);
+    r[3][0] = -((e * c9 - f * c11) + g * c7);
+    r[3][1] = (a * c9 - b * c11) + c * c7;
+    r[3][2] = -((m * c10 - n * c12) + o * c8);
+    r[3][3] = (i * c10 - j * c12) + k * c8;
+    memcpy(dest, r, sizeof(hmat4));
 }
 
 /* Right-handed look-at. */
