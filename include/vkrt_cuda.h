@@ -18,6 +18,7 @@
 #define VKRT_CUDA_H
 
 #include "vkrt_shared.h"
+#include "vkrt_closure.h"
 
 #ifdef __cplusplus
 extern "C" {
@@ -209,6 +210,13 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_read_accum_samples(vkrt_cuda_ctx* ctx, const
  * anyHit != 0 traces shadow-style (first accepted hit terminates; hits[i].instance = 1 occluded / 0 visible). */
 VKRT_CUDA_API VKRT_Result vkrt_cuda_trace_rays(vkrt_cuda_ctx* ctx, const float* rays, uint32_t rayCount, int anyHit,
                                                uint32_t* hits, float* outKernelMs);
+
+/* Test entry (no reference equivalent; vkrt_closure.h): evaluates and samples the layered closure for `count` independent queries on
+ * the device, through the same device functions the shading kernel calls, so that every lobe of src/shaders/bsdf can be compared
+ * call by call with the CPU oracle and with the reference's own shaders compiled for the CPU (tests/test_gpu_reference.py).
+ * queries / results are HOST arrays. Spectral modes need vkrt_cuda_set_rgb2spec. */
+VKRT_CUDA_API VKRT_Result vkrt_cuda_eval_closures(vkrt_cuda_ctx* ctx, const vkrt_closure_query* queries, uint32_t count,
+                                                  vkrt_closure_result* results);
 
 #ifdef __cplusplus
 }

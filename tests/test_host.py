@@ -198,6 +198,46 @@ def test_glb_with_an_out_of_range_index_fails_to_import(tmp_path):
     hs.close()
 
 
+@pytest.mark.parametrize("edit", ["count_2_pow_60", "negative_offset", "stride_below_element", "nan_count", "offset_past_end"])
+def test_glb_with_a_hostile_accessor_is_refused(tmp_path, edit):
+    """accessor count / byteStride / byteOffset arrive as JSON doubles; a count of 2^60 with stride 16 used to wrap the
+    bounds product, allocate 0 bytes and overflow the heap in the vertex loop. Every such file must fail to import, cleanly."""
+    import json
+    import struct
+    from vkrt_b200 import host
+    raw = open(os.path.join(H.ROOT, "assets", "models", "cube.glb"), "rb").read()
+    json_len = struct.unpack_from("<I", raw, 12)[0]
+    doc = json.loads(raw[20:20 + json_len].decode())
+    prim = doc["meshes"][0]["primitives"][0]
+    acc = doc["accessors"][prim["attributes"]["POSITION"]]
+    view = doc["bufferViews"][acc["bufferView"]]
+    if edit == "count_2_pow_60":
+        acc["count"] = 2 ** 60
+        view["byteStride"] = 16
+    elif edit == "negative_offset":
+        acc["byteOffset"] = -64
+    elif edit == "stride_below_element":
+        view["byteStride"] = 4
+    elif edit == "nan_count":
+        acc["count"] = 1e400     # json.dumps writes Infinity
+    else:
+        view["byteOffset"] = 2 ** 40
+    text = json.dumps(doc).encode()
+    text += b" " * (-len(text) % 4)
+    rest = raw[20 + json_len:]
+    out = bytearray(raw[:12]) + struct.pack("<I", len(text)) + b"JSON" + text + rest
+    struct.pack_into("<I", out, 8, len(out))
+    bad = tmp_path / (edit + ".glb")
+    bad.write_bytes(bytes(out))
+    hs = host.Host(host_only=True, width=64, height=36)
+    with pytest.raises(Exception):
+        hs.import_mesh(str(bad))
+    assert hs.mesh_count() == 0
+    hs.import_mesh(os.path.join(H.ROOT, "assets", "models", "cube.glb"))
+    assert hs.mesh_count() == 1
+    hs.close()
+
+
 @pytest.mark.parametrize("edit", ["negative_mesh_material", "fractional_material_index", "huge_material_index", "missing_mesh_material"])
 def test_scene_file_with_a_bad_material_reference_is_refused(tmp_path, edit):
     """controller.c:368-377,905-927: material indices in a scene file must be non-negative integers below 2^32 and every mesh must carry one;

@@ -68,6 +68,7 @@ EXPORTS = [
     "vkrt_cuda_render_frame", "vkrt_cuda_render_frame_async", "vkrt_cuda_sync", "vkrt_cuda_timer_begin", "vkrt_cuda_timer_end", "vkrt_cuda_nccl_unique_id",
     "vkrt_cuda_comm_init", "vkrt_cuda_gather", "vkrt_cuda_local_film", "vkrt_cuda_import_gathered",
     "vkrt_cuda_max_local_pixels", "vkrt_cuda_read_aov", "vkrt_cuda_read_accum_samples", "vkrt_cuda_trace_primary", "vkrt_cuda_trace_rays",
+    "vkrt_cuda_eval_closures",
 ]
 
 _lib = None
@@ -206,6 +207,13 @@ class CudaContext:
         ms = C.c_float()
         self._check(self.lib.vkrt_cuda_trace_rays(self.ctx, _ptr(r), C.c_uint32(len(r)), C.c_int(1 if any_hit else 0), _ptr(hits), C.byref(ms)), "trace_rays")
         return hits, ms.value
+
+    def eval_closures(self, queries, result_dtype):
+        """Test entry (include/vkrt_closure.h): `queries` is a structured array of vkrt_closure_query records."""
+        q = np.ascontiguousarray(queries)
+        out = np.zeros(len(q), dtype=result_dtype)
+        self._check(self.lib.vkrt_cuda_eval_closures(self.ctx, _ptr(q), C.c_uint32(len(q)), _ptr(out)), "eval_closures")
+        return out
 
     def comm_init(self, unique_id: bytes):
         buf = C.create_string_buffer(unique_id, 128)

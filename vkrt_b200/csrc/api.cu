@@ -20,6 +20,7 @@
 #include "build.h"
 #include "tiles.h"
 #include "wavefront.cuh"
+#include "../../include/vkrt_closure.h"
 
 namespace vk {
 void launchRaygen(int mode, const FrameParams& fp, int grid, cudaStream_t st);
@@ -34,6 +35,7 @@ void launchPackRgb2spec(const float* table, uint32_t dataOffset, size_t cellCoun
 void launchPrimaryStore(const FrameParams& fp, int grid, cudaStream_t st);
 void launchUntile(const void* src, void* dst, const TileMap& tm, const uint32_t* l2g, uint32_t words, int grid, cudaStream_t st);
 void launchMeshTrig(const MeshInfo* infos, MeshTrig* out, uint32_t count, cudaStream_t st);
+void launchEvalClosures(const SceneView& sc, const vkrt_closure_query* queries, uint32_t count, vkrt_closure_result* results, cudaStream_t st);
 int traceBlocksPerSm(bool count);
 int shadeBlocksPerSm(int mode);
 }  // namespace vk
@@ -985,9 +987,18 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_resize(vkrt_cuda_ctx* ctx, uint32_t width, u
     tm.localTileCount = lay.localTileCount;
     tm.localPixelCount = lay.localTileCount * lay.tileW * lay.tileH;
     tm.localToGlobalTile = ctx->l2g.p;
-    if (tm.localPixelCount == 0) return fail(ctx, VKRT_ERROR_INVALID_ARGUMENT, "rank %u owns no tiles of a %ux%u image", ctx->rank, width, height);
+    if (tm.localPixelCount == 0) {
+        // leave the context "not resized": a later render_frame must fail on its width guard, not divide by a zero pixel count
+        ctx->width = ctx->height = 0;
+        ctx->tiles = {};
+        return fail(ctx, VKRT_ERROR_INVALID_ARGUMENT, "rank %u owns no tiles of a %ux%u image (%u ranks, %ux%u tiles): use fewer ranks or smaller tiles",
+                    ctx->rank, width, height, ctx->worldSize, lay.tileW, lay.tileH);
+    }
     VKRT_Result r = allocateWavefront(ctx);
-    if (r != VKRT_SUCCESS) return r;
+    if (r != VKRT_SUCCESS) {
+        ctx->width = ctx->height = 0;
+        return r;
+    }
     ctx->readIndex = 0;
     r = resetAccumulation(ctx);
     if (r != VKRT_SUCCESS) return r;
@@ -1212,6 +1223,26 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_trace_rays(vkrt_cuda_ctx* ctx, const float* 
             memcpy(&hits[i * 5 + 4], &b[i], 4);
         }
     }
+    return VKRT_SUCCESS;
+}
+
+// Test entry (include/vkrt_closure.h): closures evaluated on the device by the functions k_shade uses.
+VKRT_CUDA_API VKRT_Result vkrt_cuda_eval_closures(vkrt_cuda_ctx* ctx, const vkrt_closure_query* queries, uint32_t count, vkrt_closure_result* results) {
+    if (!ctx || (count && (!queries || !results))) return VKRT_ERROR_INVALID_ARGUMENT;
+    for (uint32_t i = 0; i < count; i++)
+        if (queries[i].mode > 2u) return fail(ctx, VKRT_ERROR_INVALID_ARGUMENT, "eval_closures: query %u has mode %u", i, queries[i].mode);
+    bool spectral = false;
+    for (uint32_t i = 0; i < count; i++) spectral |= queries[i].mode != 0u;
+    if (spectral && !ctx->haveRgb2spec) return fail(ctx, VKRT_ERROR_OPERATION_FAILED, "eval_closures: spectral queries need vkrt_cuda_set_rgb2spec");
+    cudaSetDevice(ctx->device);
+    DevBuf<vkrt_closure_query> q;
+    DevBuf<vkrt_closure_result> r;
+    CU(q.upload(queries, count, ctx->stream));
+    CU(r.alloc(count));
+    launchEvalClosures(makeSceneView(ctx), q.p, count, r.p, ctx->stream);
+    CU(cudaGetLastError());
+    if (count) CU(cudaMemcpyAsync(results, r.p, sizeof(vkrt_closure_result) * count, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
     return VKRT_SUCCESS;
 }
 

@@ -9,6 +9,7 @@
 #include <cooperative_groups.h>
 
 #include "wavefront.cuh"
+#include "../../include/vkrt_closure.h"
 
 namespace cg = cooperative_groups;
 
@@ -265,7 +266,9 @@ static __device__ __noinline__ DirectLightSurfaceSample sampleEnvironmentLight(c
     s.shadowDistance = s.pdfSolidAngle = 0.0f;
     const uint32_t n = E.width * E.height;
     const uint64_t hi = (uint64_t)(rand(rng) * 16777216.0f), lo = (uint64_t)(rand(rng) * 16777216.0f);
-    uint32_t texel = (uint32_t)((((hi << 24) | lo) * (uint64_t)n) >> 48);
+    // 48 random bits x n needs a 128-bit product: in 64 bits it wraps as soon as n > 65536 texels, and every map larger than 256 x 256
+    // would then start in its first 65536 texels only. High half of (bits << 16) * n = floor(bits * n / 2^48).
+    uint32_t texel = (uint32_t)__umul64hi(((hi << 24) | lo) << 16, (uint64_t)n);
     texel = min(texel, n - 1u);
     if (!(rand(rng) < __ldg(E.aliasQ + texel))) texel = __ldg(E.aliasIdx + texel);
     const uint32_t ty = texel / E.width, tx = texel - ty * E.width;
@@ -1057,6 +1060,62 @@ __global__ void __launch_bounds__(256) k_probe_accum(const ::float4* __restrict_
 }
 void launchProbeAccum(const ::float4* accum, const TileMap& tm, const uint32_t* l2g, const ::uint2* xy, uint32_t count, ::float4* out, cudaStream_t st) {
     k_probe_accum<<<(count + 255) / 256, 256, 0, st>>>(accum, tm, l2g, xy, count, out);
+}
+
+// ----------------------------------------------------------------------------------------------------------------------
+// Per-call closure evaluation (TEST ENTRY, include/vkrt_closure.h): one thread per query through the SAME device functions, compiled
+// in this translation unit with the same flags, that k_shade calls: BSDFMaterial / BSDFState construction, evalBSDF /
+// evalSingleWavelengthBSDF / evalSpectralBSDF (the NEE path) and sampleBSDF / sampleSpectralBSDF (the continuation), with the rgb2spec
+// scale axis staged in shared memory as in k_shade. Lets every lobe be compared call by call with the reference's own shaders.
+// ----------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_eval_closures(const SceneView sc, const vkrt_closure_query* __restrict__ queries, uint32_t count,
+                                                       vkrt_closure_result* __restrict__ results) {
+    __shared__ float sScale[RGB2SPEC_SMEM_RES];
+    SpectralTables T = sc.spectral;
+    if (T.info.res <= RGB2SPEC_SMEM_RES && T.info.res > 0u) {
+        if (threadIdx.x < T.info.res) sScale[threadIdx.x] = T.scale[threadIdx.x];
+        T.scale = sScale;
+        __syncthreads();
+    }
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const vkrt_closure_query& Q = queries[i];
+    vkrt_closure_result R = {};
+    const Material material = loadMaterial(&Q.material);
+    const BSDFMaterial bm(material);
+    const float3 wo(Q.wo[0], Q.wo[1], Q.wo[2]), wi(Q.wi[0], Q.wi[1], Q.wi[2]);
+    const float4 wl(Q.wavelengths[0], Q.wavelengths[1], Q.wavelengths[2], Q.wavelengths[3]);
+    const BSDFState st(bm, wo, Q.frontFace, Q.mode == 0u ? 0.0f : wl.x, Q.mode == 0u ? 0u : 1u);
+    ShadingBasis basis;
+    basis.tangent = float3(1.0f, 0.0f, 0.0f);
+    basis.bitangent = float3(0.0f, 1.0f, 0.0f);
+    basis.normal = float3(0.0f, 0.0f, 1.0f);
+    uint rng = Q.rng;
+    if (Q.mode == 2u) {
+        float4 tp(0.0f);
+        const float4 v = evalSpectralBSDF(T, st, wi, wl, tp);
+        R.evalValue[0] = v.x; R.evalValue[1] = v.y; R.evalValue[2] = v.z; R.evalValue[3] = v.w;
+        R.evalPdf[0] = tp.x; R.evalPdf[1] = tp.y; R.evalPdf[2] = tp.z; R.evalPdf[3] = tp.w;
+        const SpectralBSDFSample s = sampleSpectralBSDF(T, st, basis, wl, rng);
+        R.sampleWi[0] = s.wi.x; R.sampleWi[1] = s.wi.y; R.sampleWi[2] = s.wi.z;
+        R.sampleWeight[0] = s.weight.x; R.sampleWeight[1] = s.weight.y; R.sampleWeight[2] = s.weight.z; R.sampleWeight[3] = s.weight.w;
+        R.samplePdf[0] = s.techniquePdf.x; R.samplePdf[1] = s.techniquePdf.y; R.samplePdf[2] = s.techniquePdf.z; R.samplePdf[3] = s.techniquePdf.w;
+        R.sampleFlags = (s.isUsable() ? 1u : 0u) | (s.isTransmission != 0u ? 2u : 0u);
+    } else {
+        const BSDFEval e = Q.mode == 0u ? evalBSDF(T, st, wi) : evalSingleWavelengthBSDF(T, st, wi);
+        R.evalValue[0] = e.value.x; R.evalValue[1] = e.value.y; R.evalValue[2] = e.value.z;
+        R.evalPdf[0] = e.pdf;
+        const BSDFSample s = sampleBSDF(T, st, basis, rng);
+        R.sampleWi[0] = s.wi.x; R.sampleWi[1] = s.wi.y; R.sampleWi[2] = s.wi.z;
+        R.sampleWeight[0] = s.weight.x; R.sampleWeight[1] = s.weight.y; R.sampleWeight[2] = s.weight.z;
+        R.samplePdf[0] = s.pdf;
+        R.sampleFlags = (s.isUsable() ? 1u : 0u) | (s.isTransmission != 0u ? 2u : 0u);
+    }
+    R.rngAfter = rng;
+    results[i] = R;
+}
+void launchEvalClosures(const SceneView& sc, const vkrt_closure_query* queries, uint32_t count, vkrt_closure_result* results, cudaStream_t st) {
+    if (count) k_eval_closures<<<(count + 127u) / 128u, 128, 0, st>>>(sc, queries, count, results);
 }
 
 // One thread per mesh: the rotation trig the shade kernel would otherwise re-evaluate per hit (see MeshTrig).

@@ -74,16 +74,29 @@ static int openAccessor(ImportCtx* c, int index, Accessor* a) {
     if ((int)hj_number(hj_get(bv, "buffer"), 0) != 0) return fail(c, "glTF: only the embedded GLB buffer is supported");
     a->componentType = (int)hj_number(hj_get(acc, "componentType"), 0);
     a->components = typeComponents(hj_string(hj_get(acc, "type"), NULL));
-    a->count = (size_t)hj_number(hj_get(acc, "count"), 0);
     a->normalized = hj_bool(hj_get(acc, "normalized"), 0);
     size_t cs = componentSize(a->componentType);
     if (!cs || !a->components) return fail(c, "glTF: unsupported accessor type");
     size_t elem = cs * (size_t)a->components;
-    a->stride = (size_t)hj_number(hj_get(bv, "byteStride"), 0);
+    /* every number below comes from the file as a double: reject anything that is not a small non-negative integer BEFORE it is cast
+     * (a count of 2^60 used to wrap the bounds product and pass; the reference relied on cgltf_validate) */
+    const double countD = hj_number(hj_get(acc, "count"), 0), strideD = hj_number(hj_get(bv, "byteStride"), 0);
+    const double viewOffD = hj_number(hj_get(bv, "byteOffset"), 0), accOffD = hj_number(hj_get(acc, "byteOffset"), 0);
+    const double limit = 4294967295.0;
+    if (!(countD >= 0.0 && countD <= limit) || !(strideD >= 0.0 && strideD <= 252.0) || !(viewOffD >= 0.0 && viewOffD <= limit) ||
+        !(accOffD >= 0.0 && accOffD <= limit))
+        return fail(c, "glTF: accessor count / stride / offset out of range");
+    a->count = (size_t)countD;
+    a->stride = (size_t)strideD;
     if (!a->stride) a->stride = elem;
-    size_t start = (size_t)hj_number(hj_get(bv, "byteOffset"), 0) + (size_t)hj_number(hj_get(acc, "byteOffset"), 0);
-    if (a->count && start + (a->count - 1) * a->stride + elem > c->binSize) return fail(c, "glTF: accessor exceeds the binary chunk");
-    a->base = c->bin + start;
+    if (a->stride < elem) return fail(c, "glTF: byteStride smaller than the element");
+    const size_t start = (size_t)viewOffD + (size_t)accOffD;
+    if (start > c->binSize || elem > c->binSize - start) {
+        if (a->count) return fail(c, "glTF: accessor exceeds the binary chunk");
+    } else if (a->count && a->count - 1 > (c->binSize - start - elem) / a->stride) {
+        return fail(c, "glTF: accessor exceeds the binary chunk");
+    }
+    a->base = c->bin + (start <= c->binSize ? start : 0);
     return 1;
 }
 static float readComponent(const Accessor* a, size_t i, int k) {
