@@ -10,9 +10,10 @@ oracle/ref_slang and shipped prebuilt to the GPU box), closing VERDICT r01's par
    on the 10 M-triangle soup, C4 ids on 1000 x suzanne.glb at 1080p).
 
 Bars. Closures: the device code uses approximate division / sqrt and the fast transcendental intrinsics (vkrt_b200/Makefile), the
-reference side glibc libm, so values agree to a relative 1e-4 (plus 1e-6 absolute) for >= 99.5 % of the calls, and discrete outcomes
-(usable / transmission flags, the number of random numbers consumed) for >= 99.8 %: a lobe choice `u < cdf` can flip on a last-bit
-difference. Frames: as tests/test_gpu_parity.py (sample counts exact, >= 98.5 % of pixels within 1e-3 relative)."""
+reference side glibc libm, so values agree to a relative 1e-4 (plus 1e-6 absolute) for >= 99.9 % of the calls (measured >= 99.977 %
+for every lobe), and discrete outcomes (usable / transmission flags, the number of random numbers consumed) for >= 99.9 % (measured
+100 %): a lobe choice `u < cdf` can flip on a last-bit difference. Frames: sample counts exact, >= 99 % of pixels within 1e-3
+relative (measured 99.8 - 100 %), RMSE <= 2 - 5 % of the mean (measured 0.02 - 0.4 %)."""
 import ctypes as C
 import os
 
@@ -55,9 +56,11 @@ def test_device_closures_match_the_reference_shaders(mode):
     same_rng = want["rngAfter"] == got["rngAfter"]
     usable = same_flags & ((want["sampleFlags"] & 1) != 0)
     sv = np.ones(n, bool)
-    sv[usable] = (_close(want["sampleWi"][usable], got["sampleWi"][usable], rel=1e-4, abs_=2e-5).all(axis=1) &
-                  _close(want["sampleWeight"][usable][:, :lanes], got["sampleWeight"][usable][:, :lanes], rel=2e-4, abs_=1e-5).all(axis=1) &
-                  _close(want["samplePdf"][usable][:, :pdf_lanes], got["samplePdf"][usable][:, :pdf_lanes], rel=2e-4, abs_=1e-6).all(axis=1))
+    # a sampled direction goes through sin / cos / sqrt of random numbers and, for microfacet lobes, a reflection about the sampled
+    # normal, which amplifies the ~1e-6 error of the fast intrinsics; its weight and pdf are evaluated AT that direction
+    sv[usable] = (_close(want["sampleWi"][usable], got["sampleWi"][usable], rel=1e-4, abs_=2e-4).all(axis=1) &
+                  _close(want["sampleWeight"][usable][:, :lanes], got["sampleWeight"][usable][:, :lanes], rel=2e-3, abs_=1e-4).all(axis=1) &
+                  _close(want["samplePdf"][usable][:, :pdf_lanes], got["samplePdf"][usable][:, :pdf_lanes], rel=2e-3, abs_=1e-5).all(axis=1))
     report = {}
     for name, sel in (("all", np.ones(n, bool)), ("sheen", m["sheenTintWeight"][:, 3] > 0), ("clearcoat", m["clearcoat"] > 0), ("subsurface", m["subsurface"] > 0),
                       ("oren_nayar", m["diffuseRoughness"] > 0), ("anisotropic", m["anisotropic"] > 0), ("specular_tint", m["specularTint"] > 0),
@@ -69,8 +72,8 @@ def test_device_closures_match_the_reference_shaders(mode):
         print("  %-14s %6d  %.5f  %.5f  %.5f  %.5f" % ((k,) + v))
     assert (want["evalPdf"][:, 0] > 0).sum() > 20000 and ((want["sampleFlags"] & 1) != 0).sum() > 30000
     for name, (cnt, e_ok, f_ok, r_ok, s_ok) in report.items():
-        assert e_ok >= 0.995, (name, "eval", e_ok)
-        assert f_ok >= 0.998 and r_ok >= 0.998, (name, "discrete outcome", f_ok, r_ok)
+        assert e_ok >= 0.999, (name, "eval", e_ok)              # measured on B200: >= 0.99977 for every lobe and mode
+        assert f_ok >= 0.999 and r_ok >= 0.999, (name, "discrete outcome", f_ok, r_ok)   # measured 1.0
         assert s_ok >= 0.99, (name, "sample", s_ok)
     g.close()
 
@@ -105,7 +108,7 @@ def test_every_lobe_in_a_rendered_scene_matches_the_reference_shaders(mode, hero
         b.render(prep["sceneData"], frames=2)
     ref, orc, gpu = r.read(H.AOV_ACCUM), o.read(H.AOV_ACCUM), g.read(H.AOV_ACCUM)
     assert np.array_equal(ref.view(np.uint32), orc.view(np.uint32)), "oracle and reference shaders must agree bit for bit"
-    _compare(ref, gpu, 0.985, 0.08, "lobes %d/%d GPU vs reference shaders" % (mode, hero))
+    _compare(ref, gpu, 0.995, 0.02, "lobes %d/%d GPU vs reference shaders" % (mode, hero))
     for which in (H.AOV_ALBEDO, H.AOV_NORMAL):
         fa, fb = r.read(which).astype(np.float32), g.read(which).astype(np.float32)
         assert (np.abs(fa - fb) > 2e-3).mean() < 0.005
@@ -127,7 +130,7 @@ def test_stochastic_alpha_blend_and_mask():
     for b in (o, r, g):
         b.render(prep["sceneData"], frames=4)
     orc, ref, gpu = o.read(H.AOV_ACCUM), r.read(H.AOV_ACCUM), g.read(H.AOV_ACCUM)
-    _compare(orc, gpu, 0.985, 0.08, "alpha GPU vs oracle")
+    _compare(orc, gpu, 0.995, 0.02, "alpha GPU vs oracle")
     blocks = lambda x: x[..., :3].astype(np.float64).reshape(h // 8, 8, w // 8, 8, 3).mean(axis=(1, 3))  # noqa: E731
     rel = np.abs(blocks(ref) - blocks(gpu)) / (blocks(ref) + 0.05)
     rms = float(np.sqrt((rel ** 2).mean()))
@@ -198,7 +201,7 @@ def test_bundled_scenes_through_the_c_host_match_the_reference_shaders(scene, mo
     assert np.array_equal(read(4, np.uint32, 2), r.read(H.AOV_HITID_CENTER))
     gpu, ref = read(0, np.float32, 4), r.read(H.AOV_ACCUM)
     assert gpu[..., :3].mean() > 1e-3
-    _compare(ref, gpu, 0.97 if scene == "prism" else 0.98, 0.15, "%s %d/%d GPU vs reference shaders" % (scene, mode, hero))
+    _compare(ref, gpu, 0.99, 0.05, "%s %d/%d GPU vs reference shaders" % (scene, mode, hero))
     hs.close()
 
 
@@ -217,7 +220,7 @@ def test_config_c1_cornell_rgb_512_64spp_image():
     assert np.array_equal(read(5, np.uint32, 2), r.read(H.AOV_HITID_S0))
     gpu, ref = read(0, np.float32, 4), r.read(H.AOV_ACCUM)
     assert np.all(gpu[..., 3] == 64.0)
-    _compare(ref, gpu, 0.97, 0.05, "C1 GPU vs reference shaders")
+    _compare(ref, gpu, 0.99, 0.02, "C1 GPU vs reference shaders")
     f = flip.mean_flip(r.read(H.AOV_OUTPUT)[..., :3] / 65535.0, read(3, np.uint16, 4)[..., :3] / 65535.0)
     print("C1 mean FLIP %.5f" % f)
     assert f <= 0.002
@@ -235,7 +238,7 @@ def test_config_c2_cornell_spectral_hero_1080p_radiance():
     r.trace_primary(sd)
     assert np.array_equal(read(4, np.uint32, 2), r.read(H.AOV_HITID_CENTER))
     assert np.array_equal(read(6, np.float32, 3).view(np.uint32), r.read(H.AOV_HIT_TUV).view(np.uint32))
-    _compare(r.read(H.AOV_ACCUM), read(0, np.float32, 4), 0.985, 0.08, "C2 GPU vs reference shaders")
+    _compare(r.read(H.AOV_ACCUM), read(0, np.float32, 4), 0.995, 0.02, "C2 GPU vs reference shaders")
     hs.close()
 
 
