@@ -157,10 +157,25 @@ def cpu_tag():
 
 
 class OracleRunner:
+    """The CPU arm. kind = "reference": the reference's own shaders (src/shaders/**/*.slang, transliterated to C++ by oracle/ref_slang when
+    `make -C oracle ref` ran where the reference checkout exists; oracle/_ref/shaders_gen.inc travels to the GPU box) over the oracle's
+    BVH2 traversal and texture sampler, which stand in for the Vulkan driver the reference gets them from. kind = "port": the oracle's
+    restatement of the same shaders, used only when oracle/_ref is absent. Both are rebuilt -O3 -march=native for the machine they run on."""
+
     def __init__(self, prep, width, height, threads):
         tag = cpu_tag()
-        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "native", "NATIVE_TAG=" + tag])
-        self.lib = C.CDLL(os.path.join(ROOT, "oracle", "_build", "liboracle_native_%s.so" % tag))
+        odir = os.path.join(ROOT, "oracle")
+        self.kind = "port"
+        if os.path.exists(os.path.join(odir, "_ref", "shaders_gen.inc")):
+            try:
+                subprocess.check_call(["make", "-s", "-C", odir, "refnative", "NATIVE_TAG=" + tag])
+                self.lib = C.CDLL(os.path.join(odir, "_ref", "libvkrt_refshade_native_%s.so" % tag))
+                self.kind = "reference"
+            except (subprocess.CalledProcessError, OSError) as e:
+                print("bench.py: reference-shader library unavailable (%s); falling back to the oracle port" % e, file=sys.stderr)
+        if self.kind == "port":
+            subprocess.check_call(["make", "-s", "-C", odir, "native", "NATIVE_TAG=" + tag])
+            self.lib = C.CDLL(os.path.join(odir, "_build", "liboracle_native_%s.so" % tag))
         self.ctx = C.c_void_p()
         assert self.lib.oracle_create(C.byref(self.ctx)) == 0
         self.threads = threads or self.lib.oracle_max_threads()
@@ -213,10 +228,21 @@ class OracleRunner:
         for b in range(bands):
             y0 = int((b + 0.5) * self.height / bands - rows_per_band / 2)
             y0 = max(0, min(self.height - rows_per_band, y0))
-            rc = self.lib.oracle_render_frame_rows(self.ctx, sd.ctypes.data_as(C.c_void_p), C.c_uint32(y0), C.c_uint32(y0 + rows_per_band), rays)
-            assert rc == 0, "oracle render failed"
+            if self.kind == "reference":
+                rc = self.lib.refshade_render_frame_rows(self.ctx, sd.ctypes.data_as(C.c_void_p), C.c_uint32(y0), C.c_uint32(y0 + rows_per_band))
+            else:
+                rc = self.lib.oracle_render_frame_rows(self.ctx, sd.ctypes.data_as(C.c_void_p), C.c_uint32(y0), C.c_uint32(y0 + rows_per_band), rays)
+            assert rc == 0, "CPU render failed"
             paths += rows_per_band * self.width * spp
         return paths, time.perf_counter() - t0
+
+
+CPU_NOTE = {
+    "reference": "the reference's own Slang shaders (raygen / hit / miss / any-hit, BSDF, NEE, MIS, film) transliterated to C++ and compiled -O3 "
+                 "-march=native (oracle/ref_slang), std::thread over rows; BVH2 traversal + bilinear sampler are the oracle's stand-ins for the "
+                 "Vulkan driver (the reference repository holds no traversal code); lavapipe itself is not installable here",
+    "port": "CPU oracle restatement of the reference shaders (oracle/oracle.cpp, BVH2, std::thread over rows); oracle/_ref was not available",
+}
 
 
 def make_oracle(width, height, threads):
@@ -233,9 +259,9 @@ def make_oracle(width, height, threads):
 
 
 def cpu_sample(orc, sd, budget_s, frame=0):
-    """Bounded sample: 4 bands x (2 rows per thread) x 1 spp at a time until `budget_s` seconds of CPU work have been done."""
+    """Bounded sample: 4 bands x (8 rows per thread) x 1 spp at a time until `budget_s` seconds of CPU work have been done."""
     paths, secs, n = 0, 0.0, 0
-    rows = min(2 * orc.threads, orc.height // 4)
+    rows = min(8 * orc.threads, orc.height // 4)
     while secs < budget_s:
         p, s = orc.render_bands(sd, frame + n, 1, 4, rows)
         paths, secs, n = paths + p, secs + s, n + 1
@@ -261,8 +287,8 @@ def run_reference(args):
             "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "impl": "reference",
             "config": {"workload": "cornell.json (bunny) 1920x1080 spectral hero, procedural HDR sky, depth 4..8, NEE+MIS; each step = a bounded sample of that frame",
-                       "note": "CPU oracle restatement of the reference shaders (oracle/oracle.cpp, BVH2, std::thread over rows); the reference itself needs Vulkan+slangc+meson and cannot be built here"},
-            "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": orc.threads, "kind": "port", "sample": "per step: " + sample},
+                       "note": CPU_NOTE[orc.kind]},
+            "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": orc.threads, "kind": orc.kind, "sample": "per step: " + sample},
             "e2e": {"value": value, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
     return 0
@@ -471,7 +497,7 @@ def _run_ours(args, real_stdout):
             orc, osd = make_oracle(w, h, 0)
             cpu_sample(orc, osd, 1.0)
             p, s, sample = cpu_sample(orc, osd, args.cpu_seconds, frame=10)
-            cpu_base = {"value": p / s / 1e6, "unit": "Mpaths/s", "cores": orc.threads, "kind": "port", "sample": sample}
+            cpu_base = {"value": p / s / 1e6, "unit": "Mpaths/s", "cores": orc.threads, "kind": orc.kind, "sample": sample, "note": CPU_NOTE[orc.kind]}
 
     if rank == 0:
         line = {

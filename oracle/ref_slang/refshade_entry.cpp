@@ -190,8 +190,12 @@ static void bindResources(orc::Ctx& c, const ::SceneData& sd, int writeIndex) {
     triAliasIdx.data = c.triAliasIdx.data();
     rgb2specSRGBTable.data = c.rgb2spec.data();
     selection.data = &g_selectionSlot;
-    for (uint i = 0; i < VKRT_MAX_BINDLESS_TEXTURES; i++) sceneTextures[i].index = i;
-    for (uint i = 0; i < uint(sizeof(textureSamplers) / sizeof(textureSamplers[0])); i++) textureSamplers[i].variant = i;
+    static bool tablesBound = false;   // slot i of the bindless arrays is texture i / sampler variant i, once and for all
+    if (!tablesBound) {
+        for (uint i = 0; i < VKRT_MAX_BINDLESS_TEXTURES; i++) sceneTextures[i].index = i;
+        for (uint i = 0; i < uint(sizeof(textureSamplers) / sizeof(textureSamplers[0])); i++) textureSamplers[i].variant = i;
+        tablesBound = true;
+    }
     const int r = c.readIndex, w = writeIndex;
     accumulationReadImage = {c.accum[r].data(), c.width, IMG_RGBA32F};
     accumulationWriteImage = {c.accum[w].data(), c.width, IMG_RGBA32F};

@@ -1,4 +1,4 @@
-"""bench.py's JSON contract, checked on the CPU: the reference arm (the oracle restatement on the host cores) prints one line with the
+"""bench.py's JSON contract, checked on the CPU: the reference arm (the reference's shaders from oracle/_ref on the host cores) prints one line with the
 keys the driver reads, and our own arm refuses to run without a CUDA device instead of falling back to anything."""
 import json
 import os
@@ -22,7 +22,9 @@ def test_reference_arm_prints_the_contract_line():
     assert d["value"] > 0 and d["ms_per_step"] > 0 and d["vs_baseline"] is None
     assert "workload" in d["config"] and "model" not in d["config"]
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["sample"] and cb["value"] == pytest.approx(d["value"])
+    # "reference" = the reference's own shaders from oracle/_ref (built wherever the reference checkout or its transliterated unit exists), else the port
+    want_kind = "reference" if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "shaders_gen.inc")) else "port"
+    assert cb["kind"] == want_kind and cb["cores"] >= 1 and cb["sample"] and cb["value"] == pytest.approx(d["value"])
     e = d["e2e"]
     assert e["value"] == pytest.approx(d["value"]) and e["unit"] == d["unit"] and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
 
