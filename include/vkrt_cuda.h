@@ -64,6 +64,11 @@ enum {
     VKRT_CUDA_FLAG_FORCE_TWO_LEVEL = 1u << 3, /* always build BLAS per unique geometry + TLAS (default: chosen from the instancing ratio) */
     VKRT_CUDA_FLAG_FORCE_FLAT = 1u << 4,      /* always build one BVH over all instanced triangles */
     VKRT_CUDA_FLAG_DEEP_STACK = 1u << 5,      /* always traverse with the deep-tree kernel (default: chosen from the depth of the built trees) */
+    VKRT_CUDA_FLAG_LBVH = 1u << 7,            /* build every hierarchy as a Karras radix tree over the Morton codes only (fastest build). Default: also
+                                                 build the PLOC tree (bottom-up clustering by surface area over the same Morton order) and keep, per
+                                                 BVH, the one with the lower surface-area cost: the counterpart of the PREFER_FAST_TRACE the
+                                                 reference asks its driver for (src/core/render/accel/blas.c:39, tlas.c:188) */
+    VKRT_CUDA_FLAG_PLOC = 1u << 8,            /* PLOC only (A/B measurements) */
     VKRT_CUDA_FLAG_ENV_IMPORTANCE = 1u << 6   /* EXTENSION (not in the reference, which reads the environment map on a miss only:
                                                  src/shaders/light/environment.slang:16-27): next-event estimation also samples the
                                                  lat-long environment texture by luminance x sin(theta), MIS-combined with BSDF sampling.
@@ -81,7 +86,7 @@ typedef struct vkrt_cuda_build_stats {
     uint64_t bvh8NodeCount;
     uint64_t accelBytes;       /* nodes + repacked triangles + instance records */
     uint32_t flat;             /* 1 = single-level BVH over instanced triangles was built, 0 = BLAS per geometry + TLAS */
-    uint32_t reserved;
+    uint32_t plocHierarchies;  /* how many of the built BVHs kept the PLOC hierarchy (the others the radix tree; VKRT_CUDA_FLAG_LBVH) */
 } vkrt_cuda_build_stats;
 
 typedef struct vkrt_cuda_frame_stats {

@@ -43,7 +43,7 @@ class CreateInfo(C.Structure):
 class BuildStats(C.Structure):
     _fields_ = [("buildMs", C.c_float), ("blasMs", C.c_float), ("tlasMs", C.c_float), ("uniqueGeometries", C.c_uint32),
                 ("instanceCount", C.c_uint32), ("triangleCount", C.c_uint64), ("instancedTriangleCount", C.c_uint64),
-                ("bvh8NodeCount", C.c_uint64), ("accelBytes", C.c_uint64), ("flat", C.c_uint32), ("reserved", C.c_uint32)]
+                ("bvh8NodeCount", C.c_uint64), ("accelBytes", C.c_uint64), ("flat", C.c_uint32), ("plocHierarchies", C.c_uint32)]
 
 
 class FrameStats(C.Structure):

@@ -537,6 +537,7 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_create(const vkrt_cuda_create_info* info, vk
         delete ctx;
         return VKRT_ERROR_INVALID_ARGUMENT;
     }
+    ctx->builder.mode = (ctx->flags & VKRT_CUDA_FLAG_LBVH) ? AccelBuilder::BUILD_LBVH : ((ctx->flags & VKRT_CUDA_FLAG_PLOC) ? AccelBuilder::BUILD_PLOC : AccelBuilder::BUILD_BEST);
     if (cudaSetDevice(dev) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&ctx->evA) != cudaSuccess || cudaEventCreate(&ctx->evB) != cudaSuccess) {
         delete ctx;
@@ -694,6 +695,7 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_build_accel(vkrt_cuda_ctx* ctx, vkrt_cuda_bu
     if (!ctx) return VKRT_ERROR_INVALID_ARGUMENT;
     cudaSetDevice(ctx->device);
     const uint32_t n = (uint32_t)ctx->hostMeshInfos.size();
+    uint32_t plocKept = 0;
     // --- unique geometries (geometry.c:166-210 decides sharing on the host; here it arrives as geometrySource) ---
     struct BlasDesc { uint32_t vertexBase, indexBase, triCount, nodeBase, primBase, nodeCount, vertexLimit; };
     std::vector<BlasDesc> blas;
@@ -837,6 +839,7 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_build_accel(vkrt_cuda_ctx* ctx, vkrt_cuda_bu
             return fail(ctx, VKRT_ERROR_OPERATION_FAILED, "flat BVH build failed: %s", ctx->builder.err);
         if (primCount != total) return fail(ctx, VKRT_ERROR_OPERATION_FAILED, "flat BVH emitted %u of %u triangles", primCount, total);
         // one parked node group per level (+ margin): the traversal kernel is chosen by this bound, deeper trees are refused
+        plocKept += ctx->builder.lastBuilder;
         ctx->stackNeed = ctx->builder.lastLevels + 2u;
         if (ctx->stackNeed > (uint32_t)TRACE_STACK_DEEP)
             return fail(ctx, VKRT_ERROR_OPERATION_FAILED, "flat BVH has %u levels: deeper than the traversal stack (%d)", ctx->builder.lastLevels, TRACE_STACK_DEEP);
@@ -862,6 +865,7 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_build_accel(vkrt_cuda_ctx* ctx, vkrt_cuda_bu
         s.bvh8NodeCount = nodeCount;
         s.accelBytes = (uint64_t)nodeCount * sizeof(Bvh8Node) + totalTris * 48ull + instancedTris * 8ull + (uint64_t)n * sizeof(InstanceRecord);
         s.flat = 1;
+        s.plocHierarchies = plocKept;
         if (outStats) *outStats = s;
         return VKRT_SUCCESS;
     }
@@ -892,6 +896,7 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_build_accel(vkrt_cuda_ctx* ctx, vkrt_cuda_bu
         if (primCount != d.triCount) return fail(ctx, VKRT_ERROR_OPERATION_FAILED, "BLAS %zu emitted %u of %u triangles", b, primCount, d.triCount);
         d.nodeCount = nodeCount;
         maxBlasLevels = std::max(maxBlasLevels, ctx->builder.lastLevels);
+        plocKept += ctx->builder.lastBuilder;
         primBase += d.triCount;
     }
     CU(cudaEventRecord(ctx->evB, st));
@@ -941,6 +946,7 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_build_accel(vkrt_cuda_ctx* ctx, vkrt_cuda_bu
         }
         launchRelocateNodes(scratchNodes.p + tlasNodeBase, ctx->nodes.p + ctx->tlasRoot, tlasNodes, tlasNodeBase, ctx->tlasRoot, st);
         tlasLevels = ctx->builder.lastLevels;
+        plocKept += ctx->builder.lastBuilder;
     }
     // one parked node group per level, two entries parked when a ray enters an instance (+ margin)
     ctx->stackNeed = tlasLevels + 2u + maxBlasLevels + 2u;
@@ -967,6 +973,7 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_build_accel(vkrt_cuda_ctx* ctx, vkrt_cuda_bu
     s.bvh8NodeCount = finalNodes + tlasNodes;
     s.accelBytes = s.bvh8NodeCount * sizeof(Bvh8Node) + totalTris * 48ull + (uint64_t)n * sizeof(InstanceRecord);
     s.flat = 0;
+    s.plocHierarchies = plocKept;
     if (outStats) *outStats = s;
     return VKRT_SUCCESS;
 }

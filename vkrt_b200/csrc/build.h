@@ -49,9 +49,16 @@ public:
                    uint32_t instanceCount, const float* world3x4, uint32_t totalPrims, uint2* flatScratch, Bvh8Node* nodesOut, uint32_t nodeBase,
                    uint2* flatOut, uint32_t* outNodeCount, uint32_t* outPrimCount);
     char err[512] = {0};
+    enum Mode { BUILD_BEST = 0, BUILD_LBVH = 1, BUILD_PLOC = 2 };
+    // BEST: build the Karras radix tree AND the PLOC tree and keep the one with the lower surface-area cost (PREFER_FAST_TRACE);
+    // LBVH: radix tree only (fastest build); PLOC: PLOC only (A/B measurements)
+    Mode mode = BUILD_BEST;
+    uint32_t lastBuilder = 0;           // hierarchy the most recent build kept: 0 = radix tree, 1 = PLOC
+    double lastCost[2] = {0.0, 0.0};    // sum of internal-node half-areas of the two hierarchies (BEST mode)
     uint32_t lastLevels = 0;  // BVH8 levels of the most recent build (number of collapse rounds)
 
 private:
+    bool buildPloc(cudaStream_t st, uint32_t n);
     bool buildFromBoxes(cudaStream_t st, uint32_t n, const BuildTarget& tgt, uint32_t* outNodeCount, uint32_t* outPrimCount);
     uint32_t capacity = 0;
     ::float4 *primLo = nullptr, *primHi = nullptr;
@@ -63,6 +70,11 @@ private:
     uint2* work[2] = {nullptr, nullptr};
     uint32_t* counters = nullptr;
     int* bounds = nullptr;
+    void* plocState = nullptr;
+    ::float4 *nodeLoB = nullptr, *nodeHiB = nullptr;      // PLOC's hierarchy (the radix tree lives in nodeLo / nodeHi)
+    const ::float4 *treeLo = nullptr, *treeHi = nullptr;  // the hierarchy the collapse reads
+    uint32_t *plocClusters = nullptr, *plocNN = nullptr;
+    double* treeCost = nullptr;
     const uint32_t* sortedVals = nullptr;
 };
 

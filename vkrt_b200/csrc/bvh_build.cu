@@ -559,6 +559,256 @@ __global__ void k_refit(uint32_t n, ::float4* nodeLo, ::float4* nodeHi, const ui
     }
 }
 
+
+// ---- PLOC hierarchy (Meister & Bittner 2018, "Parallel Locally-Ordered Clustering for Bounding Volume Hierarchy Construction") ----
+// The reference asks its driver for PREFER_FAST_TRACE acceleration structures (src/core/render/accel/blas.c:39, tlas.c:188). A Karras
+// radix tree follows the Morton code alone: ten wall-sized triangles among 70 k small ones end up deep inside it (the flat BVH over the
+// cornell box cost 1.7x the node visits of the two-level one, profiles/r01_notes.md). PLOC keeps the Morton ORDER but builds the tree
+// bottom-up by surface area: every cluster looks `PLOC_RADIUS` neighbours to each side for the partner whose merged box is smallest, and
+// mutually-nearest pairs merge; surviving clusters are compacted in order and the search repeats. Large boxes find no cheap partner and
+// stay near the root. Each iteration = neighbour search + flags (k_ploc_search), one block-level scan (k_ploc_scan), merge + compaction
+// (k_ploc_apply); the last <= PLOC_TAIL clusters are finished by one block in shared memory (k_ploc_tail).
+// Node numbering as k_hierarchy's: leaves at (n-1)+k, internal nodes 0..n-2 with the ROOT AT 0 (ids are handed out from n-2 downwards,
+// and a binary tree over n leaves has exactly n-1 merges).
+constexpr int PLOC_RADIUS = 10;
+constexpr int PLOC_THREADS = 256;
+constexpr int PLOC_TAIL = 512;
+
+struct PlocState {          // device-resident
+    uint32_t count, merged, iterations;   // clusters alive, merges so far (= internal nodes created), iterations run
+    uint32_t prevCount, prevMerged;       // the same two before the iteration in flight (k_ploc_apply works on those)
+    uint32_t pad[3];
+};
+
+__device__ __forceinline__ float mergedHalfArea(float3 alo, float3 ahi, float3 blo, float3 bhi) {
+    const float ex = fmaxf(ahi.x, bhi.x) - fminf(alo.x, blo.x), ey = fmaxf(ahi.y, bhi.y) - fminf(alo.y, blo.y), ez = fmaxf(ahi.z, bhi.z) - fminf(alo.z, blo.z);
+    return ex * ey + ey * ez + ez * ex;
+}
+// Candidate j beats the current best for cluster i. Ties (identical boxes are common: instanced or degenerate triangles) are broken by
+// distance in the order and then towards the partner i ^ 1, so that runs of equal boxes pair up (0,1)(2,3)... instead of forming a chain
+// in which only one pair per iteration is mutual.
+__device__ __forceinline__ bool plocBetter(float cost, int i, int j, float bestCost, int bestJ) {
+    if (cost != bestCost) return cost < bestCost;
+    const int dj = j > i ? j - i : i - j, db = bestJ > i ? bestJ - i : i - bestJ;
+    if (dj != db) return dj < db;
+    return j == (i ^ 1);
+}
+
+// Nearest neighbour of every cluster of this block's tile (and of the halo, so that "mutual" can be decided without another pass),
+// the survival / merge flags, their block sums, and nn[] for k_ploc_apply.
+__global__ void __launch_bounds__(PLOC_THREADS) k_ploc_search(const PlocState* __restrict__ state, const uint32_t* __restrict__ clusters,
+                                                                const ::float4* __restrict__ nodeLo, const ::float4* __restrict__ nodeHi,
+                                                                uint32_t* __restrict__ nn, uint2* __restrict__ blockCounts, uint32_t forcePairs) {
+    constexpr int R = PLOC_RADIUS, T = PLOC_THREADS, W = T + 4 * R;
+    __shared__ float sLx[W], sLy[W], sLz[W], sHx[W], sHy[W], sHz[W];
+    __shared__ int sNN[T + 2 * R];
+    __shared__ uint32_t sKeep[T / 32], sMerge[T / 32];
+    const int c = (int)state->count;
+    const int tile0 = blockIdx.x * T;
+    if (tile0 >= c) return;
+    const int base = tile0 - 2 * R;   // global index of sLo[0]
+    for (int k = threadIdx.x; k < W; k += T) {
+        const int g = base + k;
+        if (g >= 0 && g < c) {
+            const uint32_t node = clusters[g];
+            const ::float4 lo = __ldg(nodeLo + node), hi = __ldg(nodeHi + node);
+            sLx[k] = lo.x; sLy[k] = lo.y; sLz[k] = lo.z;
+            sHx[k] = hi.x; sHy[k] = hi.y; sHz[k] = hi.z;
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < T + 2 * R; k += T) {   // element g = tile0 - R + k
+        const int g = tile0 - R + k;
+        int best = -1;
+        if (g >= 0 && g < c) {
+            if (forcePairs) {
+                best = (g ^ 1) < c ? (g ^ 1) : -1;
+            } else {
+                float bestCost = FLT_MAX;
+                const int s = k + R;   // index of g in sLo
+                const float3 alo(sLx[s], sLy[s], sLz[s]), ahi(sHx[s], sHy[s], sHz[s]);
+                for (int d = -R; d <= R; d++) {
+                    const int j = g + d;
+                    if (d == 0 || j < 0 || j >= c) continue;
+                    const float cost = mergedHalfArea(alo, ahi, float3(sLx[s + d], sLy[s + d], sLz[s + d]), float3(sHx[s + d], sHy[s + d], sHz[s + d]));
+                    if (best < 0 || plocBetter(cost, g, j, bestCost, best)) { bestCost = cost; best = j; }
+                }
+            }
+        }
+        sNN[k] = best;
+    }
+    __syncthreads();
+    const int g = tile0 + threadIdx.x;
+    bool keep = false, merge = false;
+    if (g < c) {
+        const int j = sNN[threadIdx.x + R];
+        nn[g] = (uint32_t)j;
+        const bool mutual = j >= 0 && sNN[j - (tile0 - R)] == g;
+        merge = mutual && g < j;
+        keep = !(mutual && g > j);
+    }
+    const unsigned km = __ballot_sync(0xffffffffu, keep), mm = __ballot_sync(0xffffffffu, merge);
+    if ((threadIdx.x & 31) == 0) { sKeep[threadIdx.x >> 5] = __popc(km); sMerge[threadIdx.x >> 5] = __popc(mm); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t a = 0, b = 0;
+        for (int w = 0; w < T / 32; w++) { a += sKeep[w]; b += sMerge[w]; }
+        blockCounts[blockIdx.x] = make_uint2(a, b);
+    }
+}
+
+// Exclusive scan of the per-block {survivors, merges} (one block; <= n / PLOC_THREADS entries), new cluster count and merge total.
+__global__ void __launch_bounds__(1024) k_ploc_scan(PlocState* __restrict__ state, uint2* __restrict__ blockCounts, uint2* __restrict__ blockOffsets) {
+    __shared__ uint32_t sA[1024], sB[1024];
+    __shared__ uint32_t carryA, carryB;
+    const uint32_t c = state->count;
+    const uint32_t blocks = (c + PLOC_THREADS - 1) / PLOC_THREADS;
+    if (threadIdx.x == 0) { carryA = 0; carryB = 0; }
+    __syncthreads();
+    for (uint32_t base = 0; base < blocks; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint2 v = i < blocks ? blockCounts[i] : make_uint2(0u, 0u);
+        sA[threadIdx.x] = v.x; sB[threadIdx.x] = v.y;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            const uint32_t a = threadIdx.x >= (uint32_t)o ? sA[threadIdx.x - o] : 0u, b = threadIdx.x >= (uint32_t)o ? sB[threadIdx.x - o] : 0u;
+            __syncthreads();
+            sA[threadIdx.x] += a; sB[threadIdx.x] += b;
+            __syncthreads();
+        }
+        if (i < blocks) blockOffsets[i] = make_uint2(carryA + sA[threadIdx.x] - v.x, carryB + sB[threadIdx.x] - v.y);
+        __syncthreads();
+        if (threadIdx.x == 1023) { carryA += sA[1023]; carryB += sB[1023]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        state->prevCount = c;
+        state->prevMerged = state->merged;
+        state->count = carryA;
+        state->merged += carryB;
+        state->iterations++;
+    }
+}
+
+// Creates the merged nodes and writes the surviving clusters, in order, to clustersOut.
+__global__ void __launch_bounds__(PLOC_THREADS) k_ploc_apply(const PlocState* __restrict__ state, const uint32_t* __restrict__ clusters,
+                                                               uint32_t* __restrict__ clustersOut, const uint32_t* __restrict__ nn,
+                                                               const uint2* __restrict__ blockOffsets, ::float4* __restrict__ nodeLo, ::float4* __restrict__ nodeHi, uint32_t* __restrict__ subCount, uint32_t n) {
+    __shared__ uint32_t sKeep[PLOC_THREADS / 32], sMerge[PLOC_THREADS / 32];
+    const uint32_t T = PLOC_THREADS;
+    const uint32_t oldCount = state->prevCount, mergedBefore = state->prevMerged;
+    const uint32_t g = blockIdx.x * T + threadIdx.x;
+    if (blockIdx.x * T >= oldCount) return;
+    bool keep = false, merge = false;
+    uint32_t j = 0xFFFFFFFFu;
+    if (g < oldCount) {
+        j = nn[g];
+        const bool mutual = j != 0xFFFFFFFFu && nn[j] == g;
+        merge = mutual && g < j;
+        keep = !(mutual && g > j);
+    }
+    const unsigned km = __ballot_sync(0xffffffffu, keep), mm = __ballot_sync(0xffffffffu, merge);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { sKeep[warp] = __popc(km); sMerge[warp] = __popc(mm); }
+    __syncthreads();
+    uint32_t keepBase = 0, mergeBase = 0;
+    for (int w = 0; w < warp; w++) { keepBase += sKeep[w]; mergeBase += sMerge[w]; }
+    const uint2 off = blockOffsets[blockIdx.x];
+    const uint32_t pos = off.x + keepBase + __popc(km & ((1u << lane) - 1u));
+    const uint32_t mrank = mergedBefore + off.y + mergeBase + __popc(mm & ((1u << lane) - 1u));
+    if (merge) {
+        const uint32_t a = clusters[g], b = clusters[j];
+        const uint32_t id = (n - 2u) - mrank;
+        const ::float4 alo = nodeLo[a], ahi = nodeHi[a], blo = nodeLo[b], bhi = nodeHi[b];
+        nodeLo[id] = make_float4(fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), __uint_as_float(a));
+        nodeHi[id] = make_float4(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), __uint_as_float(b));
+        subCount[id] = 2u;   // "not leaf-like" for the collapse (one primitive per leaf slot)
+        clustersOut[pos] = id;
+    } else if (keep) {
+        clustersOut[pos] = clusters[g];
+    }
+}
+
+// The last <= PLOC_TAIL clusters: every iteration in shared memory, one block, no host round trips.
+__global__ void __launch_bounds__(PLOC_TAIL) k_ploc_tail(PlocState* __restrict__ state, const uint32_t* __restrict__ clusters, ::float4* __restrict__ nodeLo,
+                                                           ::float4* __restrict__ nodeHi, uint32_t* __restrict__ subCount, uint32_t n) {
+    constexpr int R = PLOC_RADIUS;
+    __shared__ float sB[2][6][PLOC_TAIL];   // boxes, ping-pong: lo.xyz, hi.xyz
+    __shared__ uint32_t sNode[2][PLOC_TAIL];
+    __shared__ int sNN[PLOC_TAIL];
+    __shared__ uint32_t sScanA[PLOC_TAIL], sScanB[PLOC_TAIL];
+    __shared__ uint32_t sCount, sMerged;
+    const int t = threadIdx.x;
+    int c = (int)state->count;
+    if (c > PLOC_TAIL) return;   // not yet: the host keeps iterating globally
+    if (t < c) {
+        const uint32_t node = clusters[t];
+        const ::float4 lo = nodeLo[node], hi = nodeHi[node];
+        sB[0][0][t] = lo.x; sB[0][1][t] = lo.y; sB[0][2][t] = lo.z;
+        sB[0][3][t] = hi.x; sB[0][4][t] = hi.y; sB[0][5][t] = hi.z;
+        sNode[0][t] = node;
+    }
+    if (t == 0) { sCount = (uint32_t)c; sMerged = state->merged; }
+    __syncthreads();
+    int cur = 0;
+    uint32_t iterations = 0;
+    while (c > 1) {
+        int best = -1;
+        if (t < c) {
+            float bestCost = FLT_MAX;
+            const float3 alo(sB[cur][0][t], sB[cur][1][t], sB[cur][2][t]), ahi(sB[cur][3][t], sB[cur][4][t], sB[cur][5][t]);
+            for (int d = -R; d <= R; d++) {
+                const int j = t + d;
+                if (d == 0 || j < 0 || j >= c) continue;
+                const float cost = mergedHalfArea(alo, ahi, float3(sB[cur][0][j], sB[cur][1][j], sB[cur][2][j]), float3(sB[cur][3][j], sB[cur][4][j], sB[cur][5][j]));
+                if (best < 0 || plocBetter(cost, t, j, bestCost, best)) { bestCost = cost; best = j; }
+            }
+        }
+        sNN[t] = best;
+        __syncthreads();
+        bool keep = false, merge = false;
+        if (t < c) {
+            const bool mutual = best >= 0 && sNN[best] == t;
+            merge = mutual && t < best;
+            keep = !(mutual && t > best);
+        }
+        sScanA[t] = keep ? 1u : 0u;
+        sScanB[t] = merge ? 1u : 0u;
+        __syncthreads();
+        for (int o = 1; o < PLOC_TAIL; o <<= 1) {
+            const uint32_t a = t >= o ? sScanA[t - o] : 0u, b = t >= o ? sScanB[t - o] : 0u;
+            __syncthreads();
+            sScanA[t] += a; sScanB[t] += b;
+            __syncthreads();
+        }
+        const uint32_t mergedBefore = sMerged;
+        const int nxt = 1 - cur;
+        if (merge) {
+            const uint32_t pos = sScanA[t] - 1u, id = (n - 2u) - (mergedBefore + sScanB[t] - 1u);
+            const uint32_t a = sNode[cur][t], b = sNode[cur][best];
+            float box[6];
+            for (int k = 0; k < 3; k++) box[k] = fminf(sB[cur][k][t], sB[cur][k][best]);
+            for (int k = 3; k < 6; k++) box[k] = fmaxf(sB[cur][k][t], sB[cur][k][best]);
+            nodeLo[id] = make_float4(box[0], box[1], box[2], __uint_as_float(a));
+            nodeHi[id] = make_float4(box[3], box[4], box[5], __uint_as_float(b));
+            subCount[id] = 2u;
+            for (int k = 0; k < 6; k++) sB[nxt][k][pos] = box[k];
+            sNode[nxt][pos] = id;
+        } else if (keep) {
+            const uint32_t pos = sScanA[t] - 1u;
+            for (int k = 0; k < 6; k++) sB[nxt][k][pos] = sB[cur][k][t];
+            sNode[nxt][pos] = sNode[cur][t];
+        }
+        __syncthreads();
+        if (t == 0) { sCount = sScanA[PLOC_TAIL - 1]; sMerged = mergedBefore + sScanB[PLOC_TAIL - 1]; }
+        __syncthreads();
+        c = (int)sCount;
+        cur = nxt;
+        iterations++;
+    }
+    if (t == 0) { state->count = (uint32_t)c; state->merged = sMerged; state->iterations += iterations; }
+}
+
 // ---- collapse to compressed 8-wide nodes -----------------------------------------------------------------------------
 struct CollapseParams {
     const ::float4* nodeLo;
@@ -770,6 +1020,32 @@ void launchRelocateNodes(const Bvh8Node* src, Bvh8Node* dst, uint32_t count, uin
 // ----------------------------------------------------------------------------------------------------------------------
 // Host driver
 // ----------------------------------------------------------------------------------------------------------------------
+// Sum of the half-areas of the internal nodes of a binary hierarchy: with the leaves fixed, the surface-area-heuristic cost of two trees
+// over the same primitives differs only in this sum.
+__global__ void __launch_bounds__(256) k_tree_cost(const ::float4* __restrict__ nodeLo, const ::float4* __restrict__ nodeHi, uint32_t internalCount, double* __restrict__ out) {
+    __shared__ double sSum[8];
+    double acc = 0.0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < internalCount; i += gridDim.x * blockDim.x) {
+        const ::float4 lo = nodeLo[i], hi = nodeHi[i];
+        const float ex = hi.x - lo.x, ey = hi.y - lo.y, ez = hi.z - lo.z;
+        const float a = ex * ey + ey * ez + ez * ex;
+        if (a == a && a < 3.0e38f) acc += (double)a;
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) sSum[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; w++) t += sSum[w];
+        atomicAdd(out, t);
+    }
+}
+
+__global__ void k_ploc_init(uint32_t* __restrict__ clusters, uint32_t n) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) clusters[k] = n - 1u + k;   // leaf k of the Morton order
+}
+
 static uint32_t ceilLog2(uint32_t v) {
     uint32_t r = 0;
     while ((1ull << r) < v) r++;
@@ -779,7 +1055,12 @@ static uint32_t ceilLog2(uint32_t v) {
 void AccelBuilder::release() {
     auto F = [](void* p) { if (p) cudaFree(p); };
     F(primLo); F(primHi); F(keys[0]); F(keys[1]); F(vals[0]); F(vals[1]); F(tileHist); F(digitTotals); F(nodeLo); F(nodeHi);
-    F(parent); F(arrival); F(subFirst); F(subCount); F(work[0]); F(work[1]); F(counters); F(bounds);
+    F(parent); F(arrival); F(subFirst); F(subCount); F(work[0]); F(work[1]); F(counters); F(bounds); F(plocState);
+    F(nodeLoB); F(nodeHiB); F(plocClusters); F(plocNN); F(treeCost);
+    plocState = nullptr;
+    nodeLoB = nodeHiB = nullptr;
+    plocClusters = plocNN = nullptr;
+    treeCost = nullptr;
     primLo = primHi = nodeLo = nodeHi = nullptr;
     keys[0] = keys[1] = nullptr;
     vals[0] = vals[1] = nullptr;
@@ -811,6 +1092,12 @@ bool AccelBuilder::reserve(uint32_t n) {
     CK(cudaMalloc(&subCount, sizeof(uint32_t) * 2 * cap));
     CK(cudaMalloc(&counters, sizeof(uint32_t) * 4));
     CK(cudaMalloc(&bounds, sizeof(int) * 8));
+    CK(cudaMalloc(&plocState, 64));
+    CK(cudaMalloc(&nodeLoB, sizeof(::float4) * 2 * cap));
+    CK(cudaMalloc(&nodeHiB, sizeof(::float4) * 2 * cap));
+    CK(cudaMalloc(&plocClusters, sizeof(uint32_t) * 2 * cap));
+    CK(cudaMalloc(&plocNN, sizeof(uint32_t) * cap));
+    CK(cudaMalloc(&treeCost, sizeof(double) * 2));
     capacity = cap;
     return true;
 }
@@ -834,14 +1121,43 @@ bool AccelBuilder::buildFromBoxes(cudaStream_t st, uint32_t n, const BuildTarget
     }
     sortedVals = vals[cur];
     k_leaves<<<grid, TB, 0, st>>>(primLo, primHi, vals[cur], n, nodeLo, nodeHi, subFirst, subCount, parent);
+    treeLo = nodeLo;
+    treeHi = nodeHi;
+    lastBuilder = 0;
     if (n > 1) {
-        k_hierarchy<<<grid, TB, 0, st>>>(keys[cur], n, nodeLo, nodeHi, parent, subFirst, subCount);
-        CK(cudaMemsetAsync(arrival, 0, sizeof(uint32_t) * n, st));
-        k_refit<<<grid, TB, 0, st>>>(n, nodeLo, nodeHi, parent, arrival);
+        const bool wantLbvh = mode != BUILD_PLOC, wantPloc = mode != BUILD_LBVH;
+        if (wantPloc) {
+            // PLOC works on its own copy of the leaves (nodeLoB / nodeHiB) so that both hierarchies exist side by side
+            CK(cudaMemcpyAsync(nodeLoB + (n - 1), nodeLo + (n - 1), sizeof(::float4) * n, cudaMemcpyDeviceToDevice, st));
+            CK(cudaMemcpyAsync(nodeHiB + (n - 1), nodeHi + (n - 1), sizeof(::float4) * n, cudaMemcpyDeviceToDevice, st));
+        }
+        if (wantLbvh) {
+            k_hierarchy<<<grid, TB, 0, st>>>(keys[cur], n, nodeLo, nodeHi, parent, subFirst, subCount);
+            CK(cudaMemsetAsync(arrival, 0, sizeof(uint32_t) * n, st));
+            k_refit<<<grid, TB, 0, st>>>(n, nodeLo, nodeHi, parent, arrival);
+        }
+        if (wantPloc && !buildPloc(st, n)) return false;
+        if (wantLbvh && wantPloc) {
+            // PREFER_FAST_TRACE: keep the hierarchy with the lower surface-area cost. A radix tree follows the regular cell structure of
+            // the Morton code, which is close to optimal for uniformly distributed primitives (10 M-triangle soup: 20.9 node visits per
+            // ray against PLOC's 24.0); PLOC wins wherever primitive sizes or densities vary (flat cornell: 6.2 against 9.3).
+            CK(cudaMemsetAsync(treeCost, 0, sizeof(double) * 2, st));
+            const int cg = (int)std::min<uint32_t>((n + 255u) / 256u, 2048u);
+            k_tree_cost<<<cg, 256, 0, st>>>(nodeLo, nodeHi, n - 1, treeCost);
+            k_tree_cost<<<cg, 256, 0, st>>>(nodeLoB, nodeHiB, n - 1, treeCost + 1);
+            double host[2];
+            CK(cudaMemcpyAsync(host, treeCost, sizeof(host), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            lastCost[0] = host[0];
+            lastCost[1] = host[1];
+            if (host[1] < host[0]) { treeLo = nodeLoB; treeHi = nodeHiB; lastBuilder = 1; }
+        } else if (wantPloc) {
+            treeLo = nodeLoB; treeHi = nodeHiB; lastBuilder = 1;
+        }
     }
     // collapse
     CollapseParams P = {};
-    P.nodeLo = nodeLo; P.nodeHi = nodeHi; P.subFirst = subFirst; P.subCount = subCount; P.sortedVals = vals[cur];
+    P.nodeLo = treeLo; P.nodeHi = treeHi; P.subFirst = subFirst; P.subCount = subCount; P.sortedVals = vals[cur];
     P.primCount = n;
     // One primitive per leaf slot. A watertight triangle test costs ~4 child-box tests and runs at half their lane efficiency, so a
     // slot box that culls a single triangle pays for itself: 3 -> 1 triangles per slot took the 10 M-triangle soup from 13.4 to 4.5
@@ -876,6 +1192,42 @@ bool AccelBuilder::buildFromBoxes(cudaStream_t st, uint32_t n, const BuildTarget
     return true;
 }
 
+// PLOC over the Morton-sorted leaves in nodeLoB / nodeHiB[(n-1)+k]. Scratch: plocClusters (ping-pong cluster lists), plocNN (nearest
+// neighbours), `tileHist` (per-block counts and offsets; free once the sort is done).
+bool AccelBuilder::buildPloc(cudaStream_t st, uint32_t n) {
+    uint32_t* cl[2] = {plocClusters, plocClusters + capacity};
+    uint2* blockCounts = reinterpret_cast<uint2*>(tileHist);
+    const uint32_t maxBlocks = (n + PLOC_THREADS - 1) / PLOC_THREADS;
+    uint2* blockOffsets = blockCounts + maxBlocks + 1;
+    PlocState* state = reinterpret_cast<PlocState*>(plocState);
+    PlocState init = {};
+    init.count = n;
+    CK(cudaMemcpyAsync(state, &init, sizeof(init), cudaMemcpyHostToDevice, st));
+    k_ploc_init<<<(n + 255) / 256, 256, 0, st>>>(cl[0], n);
+    uint32_t upper = n;       // host-side upper bound of the cluster count (refreshed every few iterations)
+    int cur = 0;
+    uint32_t iterations = 0;
+    const uint32_t maxIterations = 64u + 8u * ceilLog2(n);
+    while (upper > (uint32_t)PLOC_TAIL) {
+        const uint32_t force = iterations >= maxIterations ? 1u : 0u;   // pathological input: finish by pairing neighbours (halves the count)
+        for (int k = 0; k < 4 && upper > (uint32_t)PLOC_TAIL; k++) {
+            const uint32_t blocks = (upper + PLOC_THREADS - 1) / PLOC_THREADS;
+            k_ploc_search<<<blocks, PLOC_THREADS, 0, st>>>(state, cl[cur], nodeLoB, nodeHiB, plocNN, blockCounts, force);
+            k_ploc_scan<<<1, 1024, 0, st>>>(state, blockCounts, blockOffsets);
+            k_ploc_apply<<<blocks, PLOC_THREADS, 0, st>>>(state, cl[cur], cl[1 - cur], plocNN, blockOffsets, nodeLoB, nodeHiB, subCount, n);
+            cur = 1 - cur;
+            iterations++;
+        }
+        PlocState host;
+        CK(cudaMemcpyAsync(&host, state, sizeof(host), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        upper = host.count;
+    }
+    k_ploc_tail<<<1, PLOC_TAIL, 0, st>>>(state, cl[cur], nodeLoB, nodeHiB, subCount, n);
+    CK(cudaGetLastError());
+    return true;
+}
+
 bool AccelBuilder::buildBlas(cudaStream_t st, const ShaderVertex* vertices, const uint32_t* indices, uint32_t vertexBase, uint32_t indexBase,
                              uint32_t triCount, Bvh8Node* nodesOut, uint32_t nodeBase, ::float4* trianglesOut, uint32_t primBase,
                              ::float4* blasBoundsOut, uint32_t* outNodeCount, uint32_t* outPrimCount) {
@@ -887,8 +1239,8 @@ bool AccelBuilder::buildBlas(cudaStream_t st, const ShaderVertex* vertices, cons
     tgt.vertexBase = vertexBase; tgt.indexBase = indexBase; tgt.trianglesOut = trianglesOut; tgt.primBase = primBase;
     if (!buildFromBoxes(st, triCount, tgt, outNodeCount, outPrimCount)) return false;
     // BLAS root box (LBVH node 0 after refit; for a single triangle node 0 is that leaf)
-    CK(cudaMemcpyAsync(blasBoundsOut, nodeLo, sizeof(::float4), cudaMemcpyDeviceToDevice, st));
-    CK(cudaMemcpyAsync(blasBoundsOut + 1, nodeHi, sizeof(::float4), cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(blasBoundsOut, treeLo, sizeof(::float4), cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(blasBoundsOut + 1, treeHi, sizeof(::float4), cudaMemcpyDeviceToDevice, st));
     return true;
 }
 

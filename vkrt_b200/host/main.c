@@ -23,7 +23,9 @@ static void printHelp(void) {
     printf("  --render-width <px>       Offline render width (default: 3840)\n");
     printf("  --render-height <px>      Offline render height (default: 2160)\n");
     printf("  --render-samples <n>      Offline render target samples (default: 16384)\n");
-    printf("  --render-spp <n>          Samples per pixel per frame (default: 16; the reference auto-tunes this by wall clock)\n");
+    printf("  --render-spp <n>          Samples per pixel per frame (default: as many as fit the wavefront pool, at most 64: the reference\n"
+           "                            auto-tunes this by wall clock, an offline render here fills the GPU instead)\n");
+    printf("  --builder <best|lbvh|ploc> BVH hierarchy: lower surface-area cost of radix tree and PLOC (default), radix tree only, PLOC only\n");
     printf("  --render-output <path>    Save the image after completion (.exr linear, .png tone-mapped 16-bit)\n");
     printf("  --spectral <0|1|2>        Override render mode: 0 RGB, 1 spectral single wavelength, 2 spectral hero\n");
     printf("  --rgb2spec <path>         rgb2spec coefficient table (default: assets/rgb2spec/srgb.coeff)\n");
@@ -34,7 +36,7 @@ static void printHelp(void) {
 
 int main(int argc, char** argv) {
     const char* scene = NULL; const char* import = NULL; const char* output = NULL; const char* instancedGlb = NULL; const char* rgb2spec = "assets/rgb2spec/srgb.coeff";
-    uint32_t width = 3840, height = 2160, samples = 16384, spp = 16, soup = 0, instanced = 0;
+    uint32_t width = 3840, height = 2160, samples = 16384, spp = 0, soup = 0, instanced = 0, builderFlags = 0;
     int device = -1, emptyScene = 0, spectral = -1, envImportance = 0;
     for (int i = 1; i < argc; i++) {
         const char* a = argv[i];
@@ -56,6 +58,10 @@ int main(int argc, char** argv) {
         else if (!strcmp(a, "--spectral")) spectral = atoi(NEXT());
         else if (!strcmp(a, "--rgb2spec")) rgb2spec = NEXT();
         else if (!strcmp(a, "--env-importance")) envImportance = 1;
+        else if (!strcmp(a, "--builder")) {
+            const char* b = NEXT();
+            builderFlags = !strcmp(b, "lbvh") ? VKRT_CUDA_FLAG_LBVH : (!strcmp(b, "ploc") ? VKRT_CUDA_FLAG_PLOC : 0u);
+        }
         else { fprintf(stderr, "unknown option %s (see --help)\n", a); return 2; }
     }
     VKRT* vkrt = NULL;
@@ -64,6 +70,21 @@ int main(int argc, char** argv) {
     VKRT_defaultCreateInfo(&ci);
     ci.width = width; ci.height = height; ci.preferredDeviceIndex = device;
     if (envImportance) ci.cudaFlags |= VKRT_CUDA_FLAG_ENV_IMPORTANCE;
+    ci.cudaFlags |= builderFlags;
+    {   /* an offline render fills the GPU: one frame = as many samples per pixel as a 64 Mi-path wavefront pool holds (~28 GB of the 180 GB
+           of HBM; a 512 x 512 frame at 8 spp is launch-bound), at most 64. The reference auto-tunes spp per frame by wall clock instead. */
+        const uint64_t pixels = (width && height) ? (uint64_t)width * height : 1;
+        if (spp == 0) {
+            spp = (uint32_t)((64ull << 20) / pixels);
+            if (spp < 1) spp = 1;
+            if (spp > 64) spp = 64;
+            if (spp > samples) spp = samples ? samples : 1;
+        }
+        uint64_t pool = pixels * spp + 65536;
+        if (pool > (64ull << 20) + 65536) pool = (64ull << 20) + 65536;
+        if (pool < (16ull << 20)) pool = 16ull << 20;
+        ci.maxPathsInFlight = (uint32_t)pool;
+    }
     if (VKRT_initWithCreateInfo(vkrt, &ci) != VKRT_SUCCESS) { fprintf(stderr, "init failed: %s\n", VKRT_lastError(vkrt)); VKRT_destroy(vkrt); return 1; }
     VKRT_Result r = VKRT_SUCCESS;
     if (soup) r = VKRT_appGenerateSoup(vkrt, soup, 0);
@@ -89,7 +110,8 @@ int main(int argc, char** argv) {
     {   /* the first build of a process also pays for scratch allocation and module loading: time a rebuild of the same scene */
         vkrt_cuda_build_stats again;
         if (vkrt_cuda_build_accel(VKRT_cudaContext(vkrt), &again) == VKRT_SUCCESS)
-            printf("Acceleration structure rebuild: %.3f ms (%.1f M triangles/s)\n", again.buildMs, again.buildMs > 0 ? (double)again.triangleCount / again.buildMs / 1e3 : 0.0);
+            printf("Acceleration structure rebuild: %.3f ms (%.1f M triangles/s), %u of %u hierarchies kept PLOC\n", again.buildMs,
+                   again.buildMs > 0 ? (double)again.triangleCount / again.buildMs / 1e3 : 0.0, again.plocHierarchies, again.flat ? 1u : again.uniqueGeometries + 1u);
     }
     printf("Offline render complete: %.3f s, %.2f samples/s, %.3f ms/sample, %u spp/frame, actual %llu samples\n", res.seconds, res.samplesPerSecond,
            res.samples ? res.seconds * 1000.0 / (double)res.samples : 0.0, res.samplesPerFrame, (unsigned long long)res.samples);
