@@ -245,6 +245,50 @@ CPU_NOTE = {
 }
 
 
+def measure_c3(host_mod, device, triangles):
+    """BASELINE.json configs[2] in the same run: the C host's procedural triangle soup, BVH build time (second build: the first one of a
+    process also allocates the builder's scratch), traversal rate of RGB frames at 1080p with CUDA events around the k_trace launches,
+    and the visit counts of one instrumented frame."""
+    w, h, spp = 1920, 1080, 8
+    out = {"triangles": triangles, "frame": "%dx%d RGB, %d spp per frame, depth 4..8, NEE+MIS" % (w, h, spp)}
+    hs = host_mod.Host(width=w, height=h, device=device, max_paths=w * h * spp + 65536, cuda_flags=FLAG_STAGE_TIMING)
+    hs.generate_soup(triangles, 1)
+    hs.set_render_mode(0)
+    hs.set_samples_per_pixel(spp)
+    hs.start_render(w, h, 0xFFFFFFFF)
+    hs.draw()                      # upload + first build + one warm-up frame
+    import vkrt_b200
+    lib = vkrt_b200.load_library()
+    again = vkrt_b200.BuildStats()
+    lib.vkrt_cuda_invalidate_accel(C.c_void_p(hs.cuda_context()))
+    assert lib.vkrt_cuda_build_accel(C.c_void_p(hs.cuda_context()), C.byref(again)) == 0
+    out.update({"bvh_build_ms": again.buildMs, "build_Mtris_per_s": again.triangleCount / max(again.buildMs, 1e-6) / 1e3, "bvh8_nodes": int(again.bvh8NodeCount),
+                "accel_MB": again.accelBytes / 1e6, "hierarchy": "PLOC" if again.plocHierarchies else "radix tree (lower surface-area cost than PLOC)"})
+    rays = tms = fms = paths = 0.0
+    for _ in range(3):
+        hs.draw()
+        st = hs.last_frame_stats()
+        rays += st.extensionRays + st.shadowRays
+        tms += st.traceMs
+        fms += st.frameMs
+        paths += st.paths
+    out.update({"mrays_per_s_trace": rays / max(tms, 1e-9) / 1e3, "mpaths_per_s": paths / max(fms, 1e-9) / 1e3, "trace_share_of_frame": tms / max(fms, 1e-9)})
+    hs.close()
+    hc = host_mod.Host(width=w, height=h, device=device, max_paths=w * h * 2 + 65536, cuda_flags=FLAG_COUNT_RAYS)
+    hc.generate_soup(triangles, 1)
+    hc.set_render_mode(0)
+    hc.set_samples_per_pixel(2)
+    hc.start_render(w, h, 0xFFFFFFFF)
+    hc.draw()
+    cs = hc.last_frame_stats()
+    r = max(cs.extensionRays + cs.shadowRays, 1)
+    out["visits"] = {"nodes_per_ray": cs.nodesVisited / r, "triangles_per_ray": cs.trianglesTested / r}
+    out["achieved_GBps_algorithmic"] = out["mrays_per_s_trace"] * 1e6 * (0.58 * B_EXT_RAY + 0.42 * B_SHADOW_RAY + out["visits"]["nodes_per_ray"] * B_NODE +
+                                                                          out["visits"]["triangles_per_ray"] * B_TRI) / 1e9
+    hc.close()
+    return out
+
+
 def make_oracle(width, height, threads):
     from vkrt_b200 import host
     hs = setup_scene(host, width, height, 1, host_only=True)   # the C host prepares the scene; no device involved
@@ -412,8 +456,8 @@ def _run_ours(args, real_stdout):
     hs.lib.VKRT_invalidateAccumulation(hs.h)
     pinned = torch.empty((h, w, 4), dtype=torch.float32, pin_memory=True)
     pinned_ptr = C.c_void_p(pinned.data_ptr())
-    launches = trace_launches = 0
-    trace_ms = shade_ms = frame_ms = 0.0
+    launches = trace_launches = shade_launches_proper = 0
+    trace_ms = shade_ms = frame_ms = shade_kernel_ms = 0.0
     ext = sh = local_paths = 0
     for _ in range(args.warmup):   # warm-up steps are whole steps: draw + gather + device->host read (the first read into a fresh pinned
         hs.draw()                  # buffer costs ~60 ms once)
@@ -431,6 +475,8 @@ def _run_ours(args, real_stdout):
         trace_launches += st.traceLaunches
         trace_ms += st.traceMs
         shade_ms += st.shadeMs
+        shade_kernel_ms += st.shadeKernelMs
+        shade_launches_proper += st.shadeLaunches
         frame_ms += st.frameMs
         ext += st.extensionRays
         sh += st.shadowRays
@@ -452,7 +498,32 @@ def _run_ours(args, real_stdout):
     all_launches = int(sum_over_ranks(float(launches)))
 
     # ---- roofline of the dominant kernel (by measured time), from the per-launch events of the e2e region on rank 0 ----
-    roofline = cpu_base = kernels = None
+    # ---- strong scaling (N > 1): the SAME 32-spp step split over the N GPUs' tiles, device-timed like `value` ----
+    strong = None
+    if world > 1:
+        hs.lib.VKRT_invalidateAccumulation(hs.h)
+        sd_strong = sd.copy()
+        sd_strong[132:136] = np.frombuffer(np.uint32(args.spp).tobytes(), np.uint8)
+
+        def enqueue_strong():
+            sd_strong[128:132] = np.frombuffer(np.uint32(frame_counter[0]).tobytes(), np.uint8)
+            frame_counter[0] += 1
+            check(lib.vkrt_cuda_render_frame_async(ctx, sd_strong.ctypes.data_as(C.c_void_p)), "render_frame_async")
+        for _ in range(args.warmup):
+            enqueue_strong()
+        barrier()
+        check(lib.vkrt_cuda_timer_begin(ctx), "timer_begin")
+        for _ in range(args.steps):
+            enqueue_strong()
+        check(lib.vkrt_cuda_gather(ctx, C.byref(gather_ms)), "gather")
+        ms2 = C.c_float()
+        check(lib.vkrt_cuda_timer_end(ctx, C.byref(ms2)), "timer_end")
+        barrier()
+        strong_ms = max_over_ranks(float(ms2.value))
+        strong = {"value": float(w) * h * args.spp * args.steps / (strong_ms * 1e-3) / 1e6, "unit": "Mpaths/s", "ms_per_step": strong_ms / args.steps,
+                  "spp_per_step": args.spp, "note": "total work fixed: every GPU renders its interleaved tiles of the same %d-spp 1080p step; one NCCL gather inside the timed region" % args.spp}
+
+    roofline = cpu_base = kernels = c3 = None
     if rank == 0:
         peaks = {}
         try:
@@ -469,8 +540,8 @@ def _run_ours(args, real_stdout):
             r = max(cs.extensionRays + cs.shadowRays, 1)
             visits = {"nodes_per_ray": cs.nodesVisited / r, "triangles_per_ray": cs.trianglesTested / r, "instances_per_ray": cs.instancesEntered / r}
             hc.close()
-        shade_launches = launches - trace_launches   # raygen + shade + film
-        n_shade = args.steps * 8                     # k_shade launches proper (rrMaxDepth = 8)
+        other_launches = launches - trace_launches - shade_launches_proper   # raygen, material sort, film
+        n_shade = shade_launches_proper              # k_shade launches proper, counted by the library (one per depth and sample chunk)
         shade_bytes = (ext * (B_SHADE_READ_HERO + B_SHADE_SURFACE) - local_paths * B_SHADE_READ_FRESH + max(ext - local_paths, 0) * B_SHADE_WRITE_PATH_HERO +
                        sh * B_SHADE_WRITE_SHADOW + local_paths * B_SHADE_FEATURES)
         trace_bytes = ext * B_EXT_RAY + sh * B_SHADOW_RAY
@@ -482,17 +553,21 @@ def _run_ours(args, real_stdout):
         except (OSError, ValueError):
             pass
         kernels = {
-            "k_shade<hero>": {"launches": n_shade, "ms_total": shade_ms, "note": "shadeMs also contains raygen + film (%d launches)" % (shade_launches - n_shade),
-                              "algorithmic_GB": shade_bytes / 1e9, "achieved_GBps": shade_bytes / 1e9 / max(shade_ms * 1e-3, 1e-9)},
+            "k_shade<hero>": {"launches": n_shade, "ms_total": shade_kernel_ms,
+                              "note": "CUDA events around the k_shade launches alone; raygen + material sort + film (%d launches) took %.2f ms more" % (
+                                  other_launches, shade_ms - shade_kernel_ms),
+                              "algorithmic_GB": shade_bytes / 1e9, "achieved_GBps": shade_bytes / 1e9 / max(shade_kernel_ms * 1e-3, 1e-9)},
             "k_trace": {"launches": trace_launches, "ms_total": trace_ms, "algorithmic_GB": trace_bytes / 1e9, "achieved_GBps": trace_bytes / 1e9 / max(trace_ms * 1e-3, 1e-9),
                         "Mrays_per_s": (ext + sh) / max(trace_ms * 1e-3, 1e-9) / 1e6, "visits": visits},
         }
-        dom = "k_shade<hero>" if shade_ms >= trace_ms else "k_trace"
+        dom = "k_shade<hero>" if shade_kernel_ms >= trace_ms else "k_trace"
         kd = kernels[dom]
         roofline = {"bound": "hbm", "kernel": dom, "achieved": kd["achieved_GBps"], "peak": peak, "unit": "GB/s", "frac": kd["achieved_GBps"] / peak,
-                    "traffic": traffic.get(dom), "peak_source": peak_src, "avg_launch_ms": kd["ms_total"] / max(kd["launches"], 1),
+                    "traffic": traffic.get(dom), "traffic_source": traffic.get("_source"), "peak_source": peak_src, "avg_launch_ms": kd["ms_total"] / max(kd["launches"], 1),
                     "algorithmic_bytes_per_launch": kd["algorithmic_GB"] * 1e9 / max(kd["launches"], 1),
                     "share_of_step": kd["ms_total"] / max(frame_ms, 1e-9)}
+        if world == 1 and not args.no_c3:
+            c3 = measure_c3(host, local_rank, args.c3_triangles)
         if world == 1 and not args.no_cpu_baseline:
             orc, osd = make_oracle(w, h, 0)
             cpu_sample(orc, osd, 1.0)
@@ -514,6 +589,10 @@ def _run_ours(args, real_stdout):
         }
         if cpu_base:
             line["cpu_baseline"] = cpu_base
+        if c3:
+            line["config"]["c3"] = c3
+        if strong:
+            line["config"]["strong"] = strong
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
     hs.close()
     if world > 1:
@@ -535,6 +614,8 @@ def main():
     ap.add_argument("--ref-step-seconds", type=float, default=3.0, help="CPU work per step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-visit-counts", action="store_true")
+    ap.add_argument("--no-c3", action="store_true", help="skip the 10 M-triangle traversal block (config.c3)")
+    ap.add_argument("--c3-triangles", type=int, default=10_000_000)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

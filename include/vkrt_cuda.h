@@ -65,9 +65,9 @@ enum {
     VKRT_CUDA_FLAG_FORCE_FLAT = 1u << 4,      /* always build one BVH over all instanced triangles */
     VKRT_CUDA_FLAG_DEEP_STACK = 1u << 5,      /* always traverse with the deep-tree kernel (default: chosen from the depth of the built trees) */
     VKRT_CUDA_FLAG_LBVH = 1u << 7,            /* build every hierarchy as a Karras radix tree over the Morton codes only (fastest build). Default: also
-                                                 build the PLOC tree (bottom-up clustering by surface area over the same Morton order) and keep, per
-                                                 BVH, the one with the lower surface-area cost: the counterpart of the PREFER_FAST_TRACE the
-                                                 reference asks its driver for (src/core/render/accel/blas.c:39, tlas.c:188) */
+                                                 build the PLOC tree (bottom-up clustering by surface area over the same Morton order) and keep it, per
+                                                 BVH, when it lowers the surface-area cost by more than 20 %: the counterpart of the
+                                                 PREFER_FAST_TRACE the reference asks its driver for (src/core/render/accel/blas.c:39, tlas.c:188) */
     VKRT_CUDA_FLAG_PLOC = 1u << 8,            /* PLOC only (A/B measurements) */
     VKRT_CUDA_FLAG_ENV_IMPORTANCE = 1u << 6   /* EXTENSION (not in the reference, which reads the environment map on a miss only:
                                                  src/shaders/light/environment.slang:16-27): next-event estimation also samples the
@@ -95,12 +95,15 @@ typedef struct vkrt_cuda_frame_stats {
     float shadeMs;       /* device time inside raygen + shading + film kernels; needs VKRT_CUDA_FLAG_STAGE_TIMING */
     uint32_t kernelLaunches;
     uint32_t traceLaunches; /* traversal launches among kernelLaunches */
+    uint32_t shadeLaunches; /* shading-kernel launches proper among kernelLaunches (one per depth and sample chunk) */
     uint64_t paths;      /* camera paths started = local pixels * spp */
     uint64_t extensionRays; /* closest-hit rays traced */
     uint64_t shadowRays;    /* any-hit rays traced */
     uint64_t nodesVisited;  /* only with VKRT_CUDA_FLAG_COUNT_RAYS */
     uint64_t trianglesTested;
     uint64_t instancesEntered;
+    float shadeKernelMs;    /* device time inside the shading kernels alone (part of shadeMs); needs VKRT_CUDA_FLAG_STAGE_TIMING */
+    uint32_t reserved;
 } vkrt_cuda_frame_stats;
 
 /* reference: VKRT_TextureUpload, src/core/api/vkrt_types.h:70-77 */
@@ -160,6 +163,10 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_set_rgb2spec(vkrt_cuda_ctx* ctx, const float
 /* Replaces recordBottomLevelAccelerationStructureBuilds (blas.c:222-262) + recordTopLevelAccelerationStructureBuilds
  * (tlas.c:535-559): LBVH build + collapse to compressed 8-wide nodes, one BLAS per unique geometry, TLAS over instances. */
 VKRT_CUDA_API VKRT_Result vkrt_cuda_build_accel(vkrt_cuda_ctx* ctx, vkrt_cuda_build_stats* outStats);
+/* vkrt_cuda_build_accel returns the previous build when nothing it depends on changed (geometry, instance matrices / sharing / any-hit
+ * flags, the "transmits" bit of a material): like the reference, which rebuilds a BLAS only when blasBuildPending is set
+ * (src/core/render/accel/blas.c:222-262). This forces the next call to build (build-time measurements). */
+VKRT_CUDA_API VKRT_Result vkrt_cuda_invalidate_accel(vkrt_cuda_ctx* ctx);
 
 /* Replaces createGPUImages (src/core/runtime/images.c:260-320): (re)allocates film images for the FULL image size;
  * this rank stores only its own tiles. Resets accumulation. */

@@ -233,6 +233,7 @@ VKRT_HOST_API VKRT_Result VKRT_removeTexture(VKRT* vkrt, uint32_t textureIndex);
 VKRT_HOST_API VKRT_Result VKRT_addTexturesBatch(VKRT* vkrt, const VKRT_TextureUpload* uploads, size_t uploadCount, uint32_t* outTextureIndices); /* vkrt.h:88-93 */
 VKRT_HOST_API VKRT_Result VKRT_setMaterialTexture(VKRT* vkrt, uint32_t materialIndex, uint32_t textureSlot, uint32_t textureIndex);
 VKRT_HOST_API VKRT_Result VKRT_addMaterial(VKRT* vkrt, const Material* material, const char* name, uint32_t* outMaterialIndex);
+VKRT_HOST_API VKRT_Result VKRT_removeMaterial(VKRT* vkrt, uint32_t materialIndex); /* vkrt.h:96 */
 VKRT_HOST_API VKRT_Result VKRT_setMaterialName(VKRT* vkrt, uint32_t materialIndex, const char* name);
 VKRT_HOST_API VKRT_Result VKRT_setMaterial(VKRT* vkrt, uint32_t materialIndex, const Material* material);
 VKRT_HOST_API VKRT_Result VKRT_setMeshMaterialIndex(VKRT* vkrt, uint32_t meshIndex, uint32_t materialIndex);

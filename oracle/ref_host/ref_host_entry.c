@@ -172,6 +172,8 @@ REFHOST_API void refhost_material_default(Material* out) { *out = VKRT_materialD
 /* ---- scene through the reference's own API ------------------------------------------------------------------------------------------ */
 REFHOST_API int refhost_add_material(void* h, const Material* material, uint32_t* outIndex) { return VKRT_addMaterial((VKRT*)h, material, "m", outIndex); }
 REFHOST_API int refhost_set_material(void* h, uint32_t index, const Material* material) { return VKRT_setMaterial((VKRT*)h, index, material); }
+REFHOST_API int refhost_remove_material(void* h, uint32_t index) { return VKRT_removeMaterial((VKRT*)h, index); }
+REFHOST_API uint32_t refhost_material_count(void* h) { return ((VKRT*)h)->core.materialCount; }
 REFHOST_API int refhost_get_material(void* h, uint32_t index, Material* out) {
     const Material* m = vkrtGetSceneMaterialData((VKRT*)h, index);
     if (!m) return VKRT_ERROR_INVALID_ARGUMENT;

@@ -274,16 +274,37 @@ def test_cornell_spectral(sampling):
 
 
 def test_default_accel_choice():
-    """Stacked, non-shared meshes (the 16-mesh soup: overlap depth 16) -> one flat BVH; separated instances (cornell) keep
-    BLAS per geometry + TLAS (vkrt_cuda_build_accel heuristic)."""
+    """vkrt_cuda_build_accel: with the default builder (radix tree and PLOC, lower surface-area cost kept) every scene whose instanced
+    triangles fit without multiplying memory gets ONE flat BVH (cornell included: its wall-sized triangles make the cost comparison
+    keep the PLOC hierarchy); heavily instanced scenes keep BLAS per geometry + TLAS. With the radix tree alone (flag 128) separated
+    instances (cornell) keep their own BLASes and only stacked meshes (the 16-mesh soup, overlap depth 16) are flattened."""
     g = H.CudaBackend()
     g.upload(scenes.cornell(32, 32))
-    assert g.build_stats.flat == 0
+    assert g.build_stats.flat == 1 and g.build_stats.plocHierarchies == 1
     g.close()
     g = H.CudaBackend()
+    g.upload(scenes.instanced(32, 32, count=1000))      # 1000 x 576 triangles = 0.6 M instanced triangles: below the 4 Mi flattening limit
+    assert g.build_stats.flat == 1                       # (1000 x suzanne.glb = 63 M stays two-level: tests/test_gpu_reference.py, config C4)
+    g.close()
+    g = H.CudaBackend(flags=128)
+    g.upload(scenes.cornell(32, 32))
+    assert g.build_stats.flat == 0 and g.build_stats.plocHierarchies == 0
+    g.close()
+    g = H.CudaBackend(flags=128)
     g.upload(scenes.soup(20000, 32, 32))
     assert g.build_stats.flat == 1
     g.close()
+
+
+@pytest.mark.parametrize("builder", [0, 128, 256], ids=["best", "lbvh", "ploc"])
+@ACCEL
+def test_every_builder_gives_the_same_hits(builder, accel):
+    """The accepted hit does not depend on the hierarchy (closest hit with id tie-break): radix tree, PLOC and best-of-two must return the
+    oracle's ids and t/u/v bits on a scene with wall-sized and tiny triangles, on instances and on a soup."""
+    for prep, w, h in ((scenes.cornell(96, 96, spp=1), 96, 96), (scenes.instanced(96, 64, count=64, spp=1), 96, 64), (scenes.soup(30000, 96, 64, spp=1), 96, 64)):
+        o, g = scenes.both_backends(prep, w, h, flags=accel | builder)
+        _check_ids(o, g, prep["sceneData"])
+        g.close()
 
 
 @pytest.mark.parametrize("accel", [8, 16])
@@ -489,3 +510,30 @@ def test_spectral_without_table_fails():
     g.resize(w, h)
     with pytest.raises(Exception):
         g.render(prep["sceneData"], frames=1)
+
+
+def test_material_edits_keep_the_bvh_unless_it_depends_on_them():
+    """a colour / roughness edit must not pay a BVH rebuild. vkrt_cuda_build_accel returns the previous build unless geometry,
+    instance matrices / sharing / any-hit flags or a material's "transmits" bit changed; the frame after the edit still matches the
+    oracle with the same edit."""
+    w = h = 64
+    prep = scenes.cornell(w, h, spp=2)
+    o, g = scenes.both_backends(prep, w, h)
+    first = g.build_stats.buildMs
+    mats = prep["materials"].copy()
+    mats[3]["baseColor"] = (0.1, 0.9, 0.2)
+    mats[3]["roughness"] = 0.2
+    for b in (o, g):
+        m = np.ascontiguousarray(mats)
+        b.check(b.f("set_materials")(b.ctx, m.ctypes.data_as(H.C.c_void_p), H.C.c_uint32(len(m))), "set_materials")
+        b.build_accel()
+    assert g.build_stats.buildMs == first, "a colour edit rebuilt the BVH"
+    o.render(prep["sceneData"], frames=2)
+    g.render(prep["sceneData"], frames=2)
+    _check_images(o, g)
+    mats[3]["transmission"] = 1.0          # now shadow rays must treat that instance as transmissive: the instance records change
+    m = np.ascontiguousarray(mats)
+    g.check(g.f("set_materials")(g.ctx, m.ctypes.data_as(H.C.c_void_p), H.C.c_uint32(len(m))), "set_materials")
+    g.build_accel()
+    assert g.build_stats.buildMs != first, "a transmission edit must rebuild the instance records"
+    g.close()

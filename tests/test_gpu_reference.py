@@ -282,3 +282,77 @@ def test_config_c4_thousand_suzannes_1080p_ids():
     assert np.array_equal(read(6, np.float32, 3).view(np.uint32), o.read(H.AOV_HIT_TUV).view(np.uint32))
     assert len(np.unique(ids_g[..., 0])) > 300
     hs.close()
+
+
+def _read_exr_rgba32f(path):
+    """Minimal reader for what host/export.c writes: single-part scanline OpenEXR, NO_COMPRESSION, four FLOAT channels A, B, G, R."""
+    import struct
+    raw = open(path, "rb").read()
+    assert struct.unpack_from("<I", raw, 0)[0] == 20000630
+    pos = 8
+    attrs = {}
+    while True:
+        end = raw.index(b"\0", pos)
+        name = raw[pos:end].decode()
+        pos = end + 1
+        if not name:
+            break
+        end = raw.index(b"\0", pos)
+        typ = raw[pos:end].decode()
+        pos = end + 1
+        size = struct.unpack_from("<i", raw, pos)[0]
+        pos += 4
+        attrs[name] = (typ, raw[pos:pos + size])
+        pos += size
+    x0, y0, x1, y1 = struct.unpack("<4i", attrs["dataWindow"][1])
+    w, h = x1 - x0 + 1, y1 - y0 + 1
+    assert attrs["compression"][1] == b"\0"
+    offsets = struct.unpack_from("<%dQ" % h, raw, pos)
+    img = np.zeros((h, w, 4), np.float32)
+    for y in range(h):
+        yy, nbytes = struct.unpack_from("<ii", raw, offsets[y])
+        assert nbytes == w * 16
+        row = np.frombuffer(raw, "<f4", w * 4, offsets[y] + 8).reshape(4, w)   # A, B, G, R
+        img[yy - y0, :, 3], img[yy - y0, :, 2], img[yy - y0, :, 1], img[yy - y0, :, 0] = row[0], row[1], row[2], row[3]
+    return img
+
+
+@pytest.mark.parametrize("mode,hero", [(0, 0), (1, 1)], ids=["rgb", "hero"])
+def test_saved_render_images_match_the_reference_shaders(tmp_path, mode, hero):
+    """VKRT_saveRenderImageEx through the whole product path (C host -> C ABI -> CUDA -> film read-back -> file writers): the .exr holds
+    the accumulation in linear sRGB (spectral: XYZ under an equal-energy white, Bradford-adapted to D65 and converted, src/core/utility/
+    export/image.c:907-1016), the .png the tone-mapped 16-bit display image; both against the reference shaders' film."""
+    from vkrt_b200 import host
+    w, h, spp, frames = 128, 80, 8, 2
+    hs, prep, read = _host_scene(w, h, lambda x: x.load_scene(os.path.join(ASSETS, "scenes", "cornell.json")), mode, hero, spp, frames)
+    exr, png = str(tmp_path / "out.exr"), str(tmp_path / "out.png")
+    hs.save_render_image(exr)
+    hs.save_render_image(png)
+    r, sd = _cpu_backend(refpin.RefShadeBackend, prep, w, h)
+    sd["samplesPerPixel"] = spp
+    r.render(sd, frames=frames)
+    acc = r.read(H.AOV_ACCUM)[..., :3].astype(np.float32)
+    if mode == 1:   # export/image.c:932-937 restated in numpy fp32
+        f32 = np.float32
+        bradford = np.array([[0.8951, 0.2664, -0.1614], [-0.7502, 1.7135, 0.0367], [0.0389, -0.0685, 1.0296]], f32)
+        inverse = np.array([[0.9869929, -0.1470543, 0.1599627], [0.4323053, 0.5183603, 0.0492912], [-0.0085287, 0.0400428, 0.9684867]], f32)
+        scale = np.array([0.9413344, 1.0404175, 1.0895327], f32)
+        to_srgb = np.array([[3.2404542, -1.5371385, -0.4985314], [-0.9692660, 1.8760108, 0.0415560], [0.0556434, -0.2040259, 1.0572252]], f32)
+        acc = (((acc @ bradford.T) * scale) @ inverse.T) @ to_srgb.T
+    got = _read_exr_rgba32f(exr)
+    assert got.shape == (h, w, 4) and np.all(got[..., 3] == 1.0)
+    c = H.compare_images(acc, got[..., :3])
+    print("saved EXR vs reference shaders: within 1e-3 %.4f, rmse/mean %.4f" % (1.0 - c["frac_rel_gt_1e3"], c["rmse"] / max(abs(c["mean_a"]), 1e-6)))
+    assert 1.0 - c["frac_rel_gt_1e3"] >= 0.98 and c["rmse"] <= 0.03 * max(abs(c["mean_a"]), 1e-6), c
+    # PNG: 16-bit RGBA of the display image, decoded by the host's own reader (tests/test_images.py covers the reader itself)
+    class Loaded(C.Structure):
+        _fields_ = [("pixels", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32), ("format", C.c_uint32), ("colorSpace", C.c_uint32)]
+    lib = host.load_host_library()
+    img = Loaded()
+    assert lib.vkrtLoadImageFromFile(png.encode(), C.c_uint32(1), C.byref(img)) == 1
+    assert (img.width, img.height) == (w, h)
+    want = r.read(H.AOV_OUTPUT).astype(np.int64)
+    gpu_out = read(3, np.uint16, 4).astype(np.int64)
+    assert (np.abs(want - gpu_out) > 64).mean() < 0.01
+    lib.vkrtFreeLoadedImage(C.byref(img))
+    hs.close()

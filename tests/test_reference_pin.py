@@ -531,3 +531,58 @@ def test_render_setting_clamps_match_the_reference():
     finally:
         ref.refhost_destroy(C.c_void_p(h))
         mine.close()
+
+
+def test_remove_material_matches_the_reference():
+    """VKRT_removeMaterial (src/core/api/mesh.c:296-342,449-459): the default material cannot be removed, meshes fall back to it, later
+    indices shift down; a random sequence of add / remove / assign calls leaves both hosts with the same materials and mesh indices."""
+    ref = refpin.refhost_lib()
+    host = _host()
+    ref.refhost_material_count.restype = C.c_uint32
+    rng = np.random.default_rng(12)
+    h = ref.refhost_create(C.c_uint32(64), C.c_uint32(64))
+    mine = host.Host(width=64, height=64, host_only=True)
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+
+    class Snapshot(C.Structure):
+        _fields_ = [("material", C.c_uint8 * 272), ("useCount", C.c_uint32), ("name", C.c_char * 256), ("_tail", C.c_uint8 * 12)]
+    try:
+        quad = hr.quad_mesh("q", 1.0)
+        v, ix = np.ascontiguousarray(quad.vertices), np.ascontiguousarray(quad.indices, dtype=np.uint32)
+        idx = C.c_uint32()
+        for k in range(6):
+            m = hr.default_material()
+            m["baseColor"] = rng.random(3)
+            m["roughness"] = float(rng.random())
+            m = np.ascontiguousarray(m)
+            assert ref.refhost_add_material(C.c_void_p(h), ptr(m), C.byref(idx)) == 0
+            assert mine.lib.VKRT_addMaterial(mine.h, ptr(m), b"m", C.byref(idx)) == 0
+        for k in range(8):
+            assert ref.refhost_add_mesh(C.c_void_p(h), ptr(v), C.c_uint32(len(v)), ptr(ix), C.c_uint32(len(ix)), C.c_uint32(1 + k % 6)) == 0
+            assert mine.lib.VKRT_uploadMeshData(mine.h, ptr(v), C.c_size_t(len(v)), ptr(ix), C.c_size_t(len(ix))) == 0
+            assert mine.lib.VKRT_setMeshMaterialIndex(mine.h, C.c_uint32(k), C.c_uint32(1 + k % 6)) == 0
+        for victim in (0, 3, 99, 1, 5, 1, 1, 1, 1, 1):
+            ra = ref.refhost_remove_material(C.c_void_p(h), C.c_uint32(victim))
+            rb = mine.lib.VKRT_removeMaterial(mine.h, C.c_uint32(victim))
+            assert ra == rb, (victim, ra, rb)
+            n_ref = ref.refhost_material_count(C.c_void_p(h))
+            n_mine = C.c_uint32()
+            mine.lib.VKRT_getMaterialCount(mine.h, C.byref(n_mine))
+            assert n_ref == n_mine.value
+            out = np.zeros(1, hr.MATERIAL)
+            snap = Snapshot()
+            for i in range(n_ref):
+                assert ref.refhost_get_material(C.c_void_p(h), C.c_uint32(i), ptr(out)) == 0
+                assert mine.lib.VKRT_getMaterialSnapshot(mine.h, C.c_uint32(i), C.byref(snap)) == 0
+                assert out.tobytes() == bytes(snap.material), (victim, i)
+            info = np.zeros(1, hr.MESH_INFO)
+            world = np.zeros(12, np.float32)
+            mine.start_render(64, 64, 1)
+            mine.update_scene()
+            prep = mine.prepare_scene()
+            for k in range(8):
+                assert ref.refhost_get_mesh(C.c_void_p(h), C.c_uint32(k), ptr(info), ptr(world)) == 0
+                assert int(info["materialIndex"][0]) == int(prep["meshInfos"][k]["materialIndex"]), (victim, k)
+    finally:
+        ref.refhost_destroy(C.c_void_p(h))
+        mine.close()

@@ -48,8 +48,8 @@ class BuildStats(C.Structure):
 
 class FrameStats(C.Structure):
     _fields_ = [("frameMs", C.c_float), ("traceMs", C.c_float), ("shadeMs", C.c_float), ("kernelLaunches", C.c_uint32),
-                ("traceLaunches", C.c_uint32), ("paths", C.c_uint64), ("extensionRays", C.c_uint64), ("shadowRays", C.c_uint64), ("nodesVisited", C.c_uint64),
-                ("trianglesTested", C.c_uint64), ("instancesEntered", C.c_uint64)]
+                ("traceLaunches", C.c_uint32), ("shadeLaunches", C.c_uint32), ("paths", C.c_uint64), ("extensionRays", C.c_uint64), ("shadowRays", C.c_uint64), ("nodesVisited", C.c_uint64),
+                ("trianglesTested", C.c_uint64), ("instancesEntered", C.c_uint64), ("shadeKernelMs", C.c_float), ("reserved", C.c_uint32)]
 
 
 class RGB2SpecInfo(C.Structure):
@@ -68,7 +68,7 @@ EXPORTS = [
     "vkrt_cuda_render_frame", "vkrt_cuda_render_frame_async", "vkrt_cuda_sync", "vkrt_cuda_timer_begin", "vkrt_cuda_timer_end", "vkrt_cuda_nccl_unique_id",
     "vkrt_cuda_comm_init", "vkrt_cuda_gather", "vkrt_cuda_local_film", "vkrt_cuda_import_gathered",
     "vkrt_cuda_max_local_pixels", "vkrt_cuda_read_aov", "vkrt_cuda_read_accum_samples", "vkrt_cuda_trace_primary", "vkrt_cuda_trace_rays",
-    "vkrt_cuda_eval_closures",
+    "vkrt_cuda_eval_closures", "vkrt_cuda_invalidate_accel",
 ]
 
 _lib = None

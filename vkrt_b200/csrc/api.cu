@@ -157,6 +157,7 @@ struct vkrt_cuda_ctx {
     SceneData lastScene = {};
     bool haveScene = false;
     int traceGrid = 0, shadeGrid[3] = {0, 0, 0};
+    bool splitShadowTrace = false;
     DevBuf<uint8_t> staging;  // full-frame un-tiled image for read_aov
     DevBuf<uint8_t> gathered; // rank 0: concatenated tile-compact buffers of all ranks
     bool filmIsFullFrame[8] = {false};
@@ -291,7 +292,7 @@ VKRT_Result allocateWavefront(vkrt_cuda_ctx* ctx) {
           (film.frameFollow = F32(lpc)) && (film.debugColor = F4(lpc)) && (film.bounceCount = U32(lpc)) && (film.hitId = U2(lpc)) &&
           (film.hitTuv = F4(lpc));
     if (!ok) return fail(ctx, VKRT_ERROR_OUT_OF_MEMORY, "wavefront allocation failed (capacity %u paths, %u local pixels)", cap, lpc);
-    if (ctx->counters.alloc(MAX_DEPTH_SLOTS * 3) != cudaSuccess || ctx->stats.alloc(4) != cudaSuccess)
+    if (ctx->counters.alloc(MAX_DEPTH_SLOTS * 4) != cudaSuccess || ctx->stats.alloc(4) != cudaSuccess)
         return fail(ctx, VKRT_ERROR_OUT_OF_MEMORY, "counter allocation failed");
     if (ctx->shadeOrder.alloc(cap) != cudaSuccess || ctx->sortBins.alloc(512) != cudaSuccess)
         return fail(ctx, VKRT_ERROR_OUT_OF_MEMORY, "sort buffer allocation failed");
@@ -465,16 +466,24 @@ VKRT_Result enqueueFrame(vkrt_cuda_ctx* ctx, const SceneData* sceneData, uint32_
     for (uint32_t s0 = 0; s0 < spp; s0 += samplesPerChunk) {
         fp.chunkFirstSample = s0;
         fp.chunkSamples = std::min(samplesPerChunk, spp - s0);
-        CU(cudaMemsetAsync(ctx->counters.p, 0, sizeof(uint32_t) * MAX_DEPTH_SLOTS * 3, st));
+        CU(cudaMemsetAsync(ctx->counters.p, 0, sizeof(uint32_t) * MAX_DEPTH_SLOTS * 4, st));
         launchRaygen(mode, fp, ctx->shadeGrid[mode] * 2, st);
         nl++;
         mark(0);
         for (uint32_t d = 0; d < sd.rrMaxDepth; d++) {
-            launchTrace(makeTraceParams(ctx, d, true, d > 0), count, ctx->traceGrid, st);
+            if (ctx->splitShadowTrace && d > 0) {   // A/B knob (VKRT_TRACE_SPLIT=1): closest-hit and any-hit rays in separate launches
+                launchTrace(makeTraceParams(ctx, d, true, false), count, ctx->traceGrid, st);
+                TraceParams sp = makeTraceParams(ctx, d, false, true);
+                sp.workCounter = ctx->counters.p + 3 * MAX_DEPTH_SLOTS + d;
+                launchTrace(sp, count, ctx->traceGrid, st);
+                nl++;
+            } else {
+                launchTrace(makeTraceParams(ctx, d, true, d > 0), count, ctx->traceGrid, st);
+            }
             mark(1);
-            if (fp.shadeOrder) { launchShadeSort(fp, d, ctx->smCount, st); nl += 3; }
+            if (fp.shadeOrder) { launchShadeSort(fp, d, ctx->smCount, st); nl += 3; mark(0); }
             launchShade(mode, fp, d, ctx->shadeGrid[mode], st);
-            mark(0);
+            mark(2);
             nl += 2;
         }
         if (sd.rrMaxDepth > 0) {
@@ -537,6 +546,7 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_create(const vkrt_cuda_create_info* info, vk
         delete ctx;
         return VKRT_ERROR_INVALID_ARGUMENT;
     }
+    ctx->splitShadowTrace = getenv("VKRT_TRACE_SPLIT") && atoi(getenv("VKRT_TRACE_SPLIT")) != 0;
     ctx->builder.mode = (ctx->flags & VKRT_CUDA_FLAG_LBVH) ? AccelBuilder::BUILD_LBVH : ((ctx->flags & VKRT_CUDA_FLAG_PLOC) ? AccelBuilder::BUILD_PLOC : AccelBuilder::BUILD_BEST);
     if (cudaSetDevice(dev) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&ctx->evA) != cudaSuccess || cudaEventCreate(&ctx->evB) != cudaSuccess) {
@@ -597,6 +607,20 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_set_instances(vkrt_cuda_ctx* ctx, const Mesh
                                                   const uint8_t* alphaTested, uint32_t instanceCount) {
     if (!ctx || (instanceCount && (!infos || !world3x4))) return VKRT_ERROR_INVALID_ARGUMENT;
     cudaSetDevice(ctx->device);
+    // The acceleration structure depends on: which geometry each instance shares, its world matrix, its any-hit flag and whether its
+    // material transmits. An update that changes none of these (material index between two opaque materials, lightPdfArea after a
+    // light edit, opacity above the any-hit threshold ...) keeps the built BVH: interactive edits must not pay a rebuild.
+    auto transmissive = [&](uint32_t materialIndex) { return materialIndex < ctx->hostMaterials.size() && ctx->hostMaterials[materialIndex].transmission > 0.0f; };
+    bool same = ctx->accelValid && ctx->hostMeshInfos.size() == instanceCount && ctx->hostWorld.size() == (size_t)instanceCount * 12 &&
+                (instanceCount == 0 || memcmp(ctx->hostWorld.data(), world3x4, sizeof(float) * 12 * instanceCount) == 0) &&
+                (geometrySource ? (ctx->hostGeometrySource.size() == instanceCount && memcmp(ctx->hostGeometrySource.data(), geometrySource, sizeof(uint32_t) * instanceCount) == 0)
+                                : ctx->hostGeometrySource.empty());
+    for (uint32_t i = 0; same && i < instanceCount; i++) {
+        const MeshInfo &a = ctx->hostMeshInfos[i], &b = infos[i];
+        same = a.vertexBase == b.vertexBase && a.vertexCount == b.vertexCount && a.indexBase == b.indexBase && a.indexCount == b.indexCount &&
+               transmissive(a.materialIndex) == transmissive(b.materialIndex) && b.materialIndex < std::max<size_t>(ctx->hostMaterials.size(), 1) &&
+               ctx->hostAlpha[i] == (alphaTested ? alphaTested[i] : 0);
+    }
     ctx->hostMeshInfos.assign(infos, infos + instanceCount);
     ctx->hostWorld.assign(world3x4, world3x4 + (size_t)instanceCount * 12);
     if (geometrySource) ctx->hostGeometrySource.assign(geometrySource, geometrySource + instanceCount);
@@ -608,17 +632,21 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_set_instances(vkrt_cuda_ctx* ctx, const Mesh
     launchMeshTrig(ctx->meshInfos.p, ctx->meshTrig.p, instanceCount, ctx->stream);
     CU(ctx->world3x4.upload(world3x4, (size_t)instanceCount * 12, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    ctx->accelValid = false;
+    if (!same) ctx->accelValid = false;
     return VKRT_SUCCESS;
 }
 
 VKRT_CUDA_API VKRT_Result vkrt_cuda_set_materials(vkrt_cuda_ctx* ctx, const Material* materials, uint32_t materialCount) {
     if (!ctx || (materialCount && !materials)) return VKRT_ERROR_INVALID_ARGUMENT;
     cudaSetDevice(ctx->device);
+    // the instance records carry one bit per material: "transmits" (shadow rays: unsupported transmission). Only a change of that bit,
+    // or of the material count the instances were validated against, invalidates the built BVH.
+    bool same = ctx->accelValid && ctx->hostMaterials.size() == materialCount;
+    for (uint32_t i = 0; same && i < materialCount; i++) same = (ctx->hostMaterials[i].transmission > 0.0f) == (materials[i].transmission > 0.0f);
     ctx->hostMaterials.assign(materials, materials + materialCount);
     CU(ctx->materials.upload(materials, materialCount, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    ctx->accelValid = false;  // instance flags (transmissive) depend on materials
+    if (!same) ctx->accelValid = false;
     return VKRT_SUCCESS;
 }
 
@@ -694,6 +722,10 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_set_rgb2spec(vkrt_cuda_ctx* ctx, const float
 VKRT_CUDA_API VKRT_Result vkrt_cuda_build_accel(vkrt_cuda_ctx* ctx, vkrt_cuda_build_stats* outStats) {
     if (!ctx) return VKRT_ERROR_INVALID_ARGUMENT;
     cudaSetDevice(ctx->device);
+    if (ctx->accelValid) {   // nothing the BVH depends on changed since the last build (see vkrt_cuda_set_instances / set_materials)
+        if (outStats) *outStats = ctx->buildStats;
+        return VKRT_SUCCESS;
+    }
     const uint32_t n = (uint32_t)ctx->hostMeshInfos.size();
     uint32_t plocKept = 0;
     // --- unique geometries (geometry.c:166-210 decides sharing on the host; here it arrives as geometrySource) ---
@@ -742,7 +774,7 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_build_accel(vkrt_cuda_ctx* ctx, vkrt_cuda_bu
     // ---- single-level variant: one BVH over all instanced triangles in world space ------------------------------------------------
     // Instancing (shared BLASes under a TLAS) pays when geometry is reused many times; when it is not — a handful of instances, or many
     // overlapping meshes like the 16-mesh triangle soup, where a ray enters 9 BLASes — a flat BVH traverses far fewer nodes.
-    // Decision: average overlap depth of the instances' world boxes = sum of box volumes / volume of their union box. Separated
+    // Decision (radix-tree builder): average overlap depth of the instances' world boxes = sum of box volumes / volume of their union box. Separated
     // instances (cornell: depth < 1) keep their own well-fitting BLASes — mixing ten wall-sized triangles into one Morton-ordered
     // tree with 70 k small ones costs 1.7x the node visits; stacked instances (soup: depth 16) are flattened. Flattening is also
     // limited to scenes where it does not multiply memory (instanced <= 2 x unique triangles, or <= 4 Mi triangles in total).
@@ -789,6 +821,11 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_build_accel(vkrt_cuda_ctx* ctx, vkrt_cuda_bu
             sumVol += v;
         }
         flat = unionVol > 0.0 && sumVol / unionVol > 2.0;
+        // With the surface-area driven hierarchy (PLOC, picked per BVH by cost) large triangles stay near the root, so one BVH over all
+        // instanced triangles beats BLAS + TLAS even for separated instances (cornell: 32.7 against 33.7 ms of traversal per 16-spp
+        // 1080p frame, 0.95 against 1.61 instance transforms per ray): flatten whenever it does not multiply memory. A radix tree alone
+        // needs the overlap test above (flat cornell: 9.3 node visits per ray against 5.5).
+        if (ctx->builder.mode != AccelBuilder::BUILD_LBVH) flat = true;
     }
     if (ctx->flags & VKRT_CUDA_FLAG_FORCE_TWO_LEVEL) flat = false;
     if ((ctx->flags & VKRT_CUDA_FLAG_FORCE_FLAT) && instancedTris > 0 && instancedTris < 0x7FFFFFF0ull) flat = true;
@@ -978,6 +1015,12 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_build_accel(vkrt_cuda_ctx* ctx, vkrt_cuda_bu
     return VKRT_SUCCESS;
 }
 
+VKRT_CUDA_API VKRT_Result vkrt_cuda_invalidate_accel(vkrt_cuda_ctx* ctx) {
+    if (!ctx) return VKRT_ERROR_INVALID_ARGUMENT;
+    ctx->accelValid = false;
+    return VKRT_SUCCESS;
+}
+
 VKRT_CUDA_API VKRT_Result vkrt_cuda_resize(vkrt_cuda_ctx* ctx, uint32_t width, uint32_t height) {
     if (!ctx || width == 0 || height == 0 || width > 16384 || height > 16384) return VKRT_ERROR_INVALID_ARGUMENT;  // render.c:252-253
     cudaSetDevice(ctx->device);
@@ -1071,6 +1114,7 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_render_frame(vkrt_cuda_ctx* ctx, const Scene
             if (cudaEventElapsedTime(&ms, ctx->stageEvents[k - 1], ctx->stageEvents[k]) != cudaSuccess) continue;
             if (ctx->stageKinds[k] == 1) { outStats->traceMs += ms; outStats->traceLaunches++; }
             else outStats->shadeMs += ms;
+            if (ctx->stageKinds[k] == 2) { outStats->shadeKernelMs += ms; outStats->shadeLaunches++; }
         }
         const uint32_t spp = std::max(sceneData->samplesPerPixel, 1u);
         // counters hold the LAST chunk only; ray totals are exact when the frame fits one chunk (the common case)

@@ -50,11 +50,12 @@ public:
                    uint2* flatOut, uint32_t* outNodeCount, uint32_t* outPrimCount);
     char err[512] = {0};
     enum Mode { BUILD_BEST = 0, BUILD_LBVH = 1, BUILD_PLOC = 2 };
-    // BEST: build the Karras radix tree AND the PLOC tree and keep the one with the lower surface-area cost (PREFER_FAST_TRACE);
+    // BEST: build the Karras radix tree AND the PLOC tree; PLOC is kept when its surface-area cost is below 0.8 x the radix tree's
+    // (PREFER_FAST_TRACE; see buildFromBoxes);
     // LBVH: radix tree only (fastest build); PLOC: PLOC only (A/B measurements)
     Mode mode = BUILD_BEST;
     uint32_t lastBuilder = 0;           // hierarchy the most recent build kept: 0 = radix tree, 1 = PLOC
-    double lastCost[2] = {0.0, 0.0};    // sum of internal-node half-areas of the two hierarchies (BEST mode)
+    double lastCost[2] = {0.0, 0.0};       // sum of internal-node half-areas of the two binary hierarchies (BEST mode)
     uint32_t lastLevels = 0;  // BVH8 levels of the most recent build (number of collapse rounds)
 
 private:

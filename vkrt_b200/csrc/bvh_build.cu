@@ -877,7 +877,6 @@ __global__ void __launch_bounds__(64) k_collapse(CollapseParams P, const uint2* 
 
     // node frame
     ::float4 nlo = P.nodeLo[b2], nhi = P.nodeHi[b2];
-    if (nc == 1 && child[0] == b2) { /* single leaf-like root: frame is its own box */ }
     float3 center((nlo.x + nhi.x) * 0.5f, (nlo.y + nhi.y) * 0.5f, (nlo.z + nhi.z) * 0.5f);
 
     // greedy slot assignment: slot bit set = child on the positive side of that axis (x: bit0, y: bit1, z: bit2)
@@ -1138,9 +1137,7 @@ bool AccelBuilder::buildFromBoxes(cudaStream_t st, uint32_t n, const BuildTarget
         }
         if (wantPloc && !buildPloc(st, n)) return false;
         if (wantLbvh && wantPloc) {
-            // PREFER_FAST_TRACE: keep the hierarchy with the lower surface-area cost. A radix tree follows the regular cell structure of
-            // the Morton code, which is close to optimal for uniformly distributed primitives (10 M-triangle soup: 20.9 node visits per
-            // ray against PLOC's 24.0); PLOC wins wherever primitive sizes or densities vary (flat cornell: 6.2 against 9.3).
+            // surface-area cost of the two BINARY trees (sum of internal half-areas), kept for the build statistics
             CK(cudaMemsetAsync(treeCost, 0, sizeof(double) * 2, st));
             const int cg = (int)std::min<uint32_t>((n + 255u) / 256u, 2048u);
             k_tree_cost<<<cg, 256, 0, st>>>(nodeLo, nodeHi, n - 1, treeCost);
@@ -1150,7 +1147,16 @@ bool AccelBuilder::buildFromBoxes(cudaStream_t st, uint32_t n, const BuildTarget
             CK(cudaStreamSynchronize(st));
             lastCost[0] = host[0];
             lastCost[1] = host[1];
-            if (host[1] < host[0]) { treeLo = nodeLoB; treeHi = nodeHiB; lastBuilder = 1; }
+            // PREFER_FAST_TRACE: PLOC is kept when it lowers the surface-area cost of the binary tree by more than 20 %. Measured on B200
+            // (profiles/r02_notes.md): flat cornell 0.47 of the radix tree's cost -> 9.3 to 6.2 node visits per ray; 1000 instances
+            // 0.65; the C4 TLAS 0.53; caustics 0.13. Near parity the radix tree is the better one although its cost is a few percent
+            // higher (bunny 0.93, suzanne 0.90, 10 M-triangle soup 0.94 -> 20.9 against PLOC's 24.0 visits): its children sit in the
+            // octants of their parent, which is what the octant-ordered front-to-back traversal of the 8-wide nodes assumes, and the
+            // surface-area cost -- of the binary tree or of the collapsed wide tree, both were tried -- does not see traversal order.
+            if (host[1] < 0.8 * host[0]) { treeLo = nodeLoB; treeHi = nodeHiB; lastBuilder = 1; }
+            if (getenv("VKRT_BUILD_VERBOSE"))
+                fprintf(stderr, "[vkrt build] n=%u surface-area cost: radix tree %.6g, PLOC %.6g (ratio %.3f) -> %s\n", n, host[0], host[1],
+                        host[0] > 0.0 ? host[1] / host[0] : 0.0, lastBuilder ? "PLOC" : "radix tree");
         } else if (wantPloc) {
             treeLo = nodeLoB; treeHi = nodeHiB; lastBuilder = 1;
         }
@@ -1168,24 +1174,28 @@ bool AccelBuilder::buildFromBoxes(cudaStream_t st, uint32_t n, const BuildTarget
     P.trianglesOut = tgt.trianglesOut; P.primBase = tgt.primBase;
     P.instanceRecords = tgt.instanceRecords; P.instancesOut = tgt.instancesOut;
     P.flatIn = tgt.flatIn; P.flatInstances = tgt.flatInstances; P.flatOut = tgt.flatOut;
-    uint32_t initCounters[4] = {0u, 1u, 0u, 0u};  // node 0 (root) is pre-allocated
-    CK(cudaMemcpyAsync(counters, initCounters, sizeof(initCounters), cudaMemcpyHostToDevice, st));
-    uint2 rootWork = make_uint2(0u, 0u);  // bvh2 node 0 (for n == 1 that is the single leaf) -> local bvh8 node 0
-    CK(cudaMemcpyAsync(work[0], &rootWork, sizeof(uint2), cudaMemcpyHostToDevice, st));
-    uint32_t workCount = 1;
-    int wq = 0;
-    uint32_t hostCounters[4];
-    lastLevels = 0;
-    while (workCount > 0) {
-        lastLevels++;
-        k_collapse<<<(workCount + 63) / 64, 64, 0, st>>>(P, work[wq], workCount, work[1 - wq]);
-        CK(cudaMemcpyAsync(hostCounters, counters, sizeof(hostCounters), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        workCount = hostCounters[0];
-        uint32_t zero = 0;
-        CK(cudaMemcpyAsync(counters, &zero, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-        wq = 1 - wq;
-    }
+    uint32_t hostCounters[4] = {0u, 0u, 0u, 0u};
+    auto runCollapse = [&](CollapseParams cp, uint32_t* levels) -> bool {
+        uint32_t initCounters[4] = {0u, 1u, 0u, 0u};  // node 0 (root) is pre-allocated
+        CK(cudaMemcpyAsync(counters, initCounters, sizeof(initCounters), cudaMemcpyHostToDevice, st));
+        uint2 rootWork = make_uint2(0u, 0u);  // bvh2 node 0 (for n == 1 that is the single leaf) -> local bvh8 node 0
+        CK(cudaMemcpyAsync(work[0], &rootWork, sizeof(uint2), cudaMemcpyHostToDevice, st));
+        uint32_t workCount = 1;
+        int wq = 0;
+        *levels = 0;
+        while (workCount > 0) {
+            (*levels)++;
+            k_collapse<<<(workCount + 63) / 64, 64, 0, st>>>(cp, work[wq], workCount, work[1 - wq]);
+            CK(cudaMemcpyAsync(hostCounters, counters, sizeof(hostCounters), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            workCount = hostCounters[0];
+            uint32_t zero = 0;
+            CK(cudaMemcpyAsync(counters, &zero, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+            wq = 1 - wq;
+        }
+        return true;
+    };
+    if (!runCollapse(P, &lastLevels)) return false;
     *outNodeCount = hostCounters[1];
     *outPrimCount = hostCounters[2];
     CK(cudaGetLastError());

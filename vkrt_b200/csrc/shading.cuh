@@ -858,6 +858,7 @@ VK_NOINLINE float sheenDirectionalAlbedo(float cosT, float sheenRoughness) {
     return sheenLtcLookup(cosT, clamp(sheenRoughness, 1e-3f, 1.0f), 2u);
 }
 VK_D float sheenLayerAttenuation(float sheenWeight, float cosT, float sheenRoughness) {
+    if (sheenWeight <= 0.0f) return 1.0f;   // saturate(1 - 0 * albedo) without the LTC lookup (three per vertex for a material without sheen)
     return saturate(1.0f - sheenWeight * sheenDirectionalAlbedo(cosT, sheenRoughness));
 }
 VK_NOINLINE BSDFEval evalSheen(float3 sheenColor, float sheenRoughness, float3 wo, float3 wi) {
@@ -1165,6 +1166,11 @@ struct BSDFState {
     float wavelengthNm = 0.0f;
     uint spectralMode = 0u;
     BSDFBranchWeights sampleWeights;
+    // Hero mode evaluates the closure twice per vertex with the same (material, wo): once for the light sample, once for the sampled
+    // direction. The two spectral upsamplings that do not depend on wi are kept from the first evaluation (the state lives in the
+    // kernel's local frame; each lookup is ~100 instructions and 8 gathered 128-bit loads).
+    mutable float4 cachedDiffuse4, cachedVd4;
+    mutable uint cachedMask = 0u;   // bit 0: cachedDiffuse4 valid, bit 1: cachedVd4 valid
     __device__ BSDFState() {}
     __device__ BSDFState(const BSDFMaterial& m, float3 wo_, uint ff, float wl, uint sm)
         : material(m), wo(wo_), frontFace(ff), wavelengthNm(wl), spectralMode(sm) {
@@ -1278,7 +1284,11 @@ VK_D float4 evalSpectralReflectionStack(const SpectralTables& t, const BSDFState
         techniquePdf += s.sampleWeights.dielectric * dp;
     }
     if (s.sampleWeights.diffuse > 0.0f || s.sampleWeights.subsurface > 0.0f) {
-        float4 diffuseColor = spectralScalarFromLinearSrgb4(t, saturate(bsdfDiffuseColor(m)), wl);
+        if (!(s.cachedMask & 1u)) {
+            s.cachedDiffuse4 = spectralScalarFromLinearSrgb4(t, saturate(bsdfDiffuseColor(m)), wl);
+            s.cachedMask |= 1u;
+        }
+        const float4 diffuseColor = s.cachedDiffuse4;
         if (s.sampleWeights.diffuse > 0.0f) {
             float ds = (1.0f - m.transmission) * (1.0f - m.subsurface);
             BSDFEval d = m.diffuseRoughness <= 0.0f ? evalLambertian(float3(ds), wi) : evalOrenNayar(float3(ds), m.diffuseRoughness, s.wo, wi);
@@ -1297,8 +1307,12 @@ VK_D float4 evalSpectralReflectionStack(const SpectralTables& t, const BSDFState
         return m.metallic * metalValue + nonMetal * dielectricValue;
     }
     float vc = coatDirectionalAttenuation(m, s.wo);
-    float4 vs = saturate(1.0f - sheenColor * sheenDirectionalAlbedo(cosTheta(s.wo), m.sheenRoughness));
-    float4 vd = spectralScalarFromLinearSrgb4(t, saturate(dielectricDirectionalAttenuation(m, s.wo)), wl);
+    const float4 vs = anyGreater(sheenColor, 0.0f) ? saturate(1.0f - sheenColor * sheenDirectionalAlbedo(cosTheta(s.wo), m.sheenRoughness)) : float4(1.0f);
+    if (!(s.cachedMask & 2u)) {
+        s.cachedVd4 = spectralScalarFromLinearSrgb4(t, saturate(dielectricDirectionalAttenuation(m, s.wo)), wl);
+        s.cachedMask |= 2u;
+    }
+    const float4 vd = s.cachedVd4;
     float nonMetal = 1.0f - m.metallic;
     float ra = reflectionStackAttenuation(m, vc, wi);
     float4 baseValue = float4(coatValue) + ra * (m.metallic * metalValue + nonMetal * (dielectricValue + vd * substrateValue));

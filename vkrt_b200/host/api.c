@@ -645,6 +645,39 @@ VKRT_Result VKRT_addMaterial(VKRT* v, const Material* material, const char* name
     if (outIndex) *outIndex = idx;
     return VKRT_SUCCESS;
 }
+/* api/mesh.c:296-342,449-459: the default material (index 0) cannot be removed; meshes that used the removed material fall back to it
+ * and lose their assignment, later material indices shift down by one, and textures only the removed material referenced are dropped. */
+VKRT_Result VKRT_removeMaterial(VKRT* v, uint32_t materialIndex) {
+    VKRT_Result ready = requireReady(v);
+    if (ready != VKRT_SUCCESS) return ready;
+    if (materialIndex >= v->materialCount) return VKRT_ERROR_INVALID_ARGUMENT;
+    if (materialIndex == 0u) return VKRT_ERROR_OPERATION_FAILED;
+    const Material removed = v->materials[materialIndex].material;
+    for (uint32_t i = 0; i < v->meshCount; i++) {
+        if (v->meshes[i].info.materialIndex == materialIndex) {
+            v->meshes[i].info.materialIndex = 0u;
+            v->meshes[i].hasMaterialAssignment = 0;
+        }
+    }
+    memmove(&v->materials[materialIndex], &v->materials[materialIndex + 1u], (size_t)(v->materialCount - materialIndex - 1u) * sizeof(HostMaterial));
+    v->materialCount--;
+    for (uint32_t i = 0; i < v->meshCount; i++)
+        if (v->meshes[i].info.materialIndex > materialIndex) v->meshes[i].info.materialIndex--;
+    v->materialsDirty = v->sceneResourcesDirty = v->lightsDirty = v->accelDirty = 1;
+    hostResetSceneData(v);
+    /* releaseTexturesReferencedByMaterialIfUnused: distinct indices, highest first, so that a removal does not shift the ones still to do */
+    uint32_t tex[4] = {removed.baseColorTextureIndex, removed.metallicRoughnessTextureIndex, removed.normalTextureIndex, removed.emissiveTextureIndex};
+    for (int a = 0; a < 4; a++)
+        for (int b = a + 1; b < 4; b++)
+            if (tex[b] != VKRT_INVALID_INDEX && (tex[a] == VKRT_INVALID_INDEX || tex[b] > tex[a])) { uint32_t t = tex[a]; tex[a] = tex[b]; tex[b] = t; }
+    for (int a = 0; a < 4; a++) {
+        if (tex[a] == VKRT_INVALID_INDEX || tex[a] >= v->textureCount || (a > 0 && tex[a] == tex[a - 1])) continue;
+        if (textureUsers(v, tex[a]) != 0u) continue;
+        VKRT_Result r = VKRT_removeTexture(v, tex[a]);
+        if (r != VKRT_SUCCESS) return r;
+    }
+    return VKRT_SUCCESS;
+}
 VKRT_Result VKRT_setMaterialName(VKRT* v, uint32_t idx, const char* name) {
     VKRT_Result ready = requireReady(v);
     if (ready != VKRT_SUCCESS) return ready;
@@ -894,9 +927,9 @@ VKRT_Result VKRT_updateScene(VKRT* v) {
         if (r != VKRT_SUCCESS) return r;
     }
     if (v->materialsDirty && (r = cudaCheck(v, vkrt_cuda_set_materials(c, v->materialArray, v->materialCount), "set_materials")) != VKRT_SUCCESS) return r;
-    if (v->sceneResourcesDirty || v->materialsDirty) {
+    if (v->sceneResourcesDirty || v->materialsDirty || v->lightsDirty) {   /* MeshInfo carries materialIndex, opacity and lightPdfArea */
         if ((r = cudaCheck(v, vkrt_cuda_set_instances(c, v->meshInfos, v->world3x4, v->geometrySource, v->alphaTested, v->meshCount), "set_instances")) != VKRT_SUCCESS) return r;
-        v->accelDirty = 1;
+        v->accelDirty = 1;   /* vkrt_cuda_build_accel returns at once when nothing the BVH depends on changed (a colour / roughness edit) */
     }
     if (v->lightsDirty &&
         (r = cudaCheck(v, vkrt_cuda_set_lights(c, v->emissiveMeshes, v->emissiveMeshCount, v->emissiveTriangles, v->emissiveTriangleCount, v->meshAliasQ,

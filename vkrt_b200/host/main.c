@@ -109,6 +109,7 @@ int main(int argc, char** argv) {
            bs.uniqueGeometries, bs.instanceCount, (unsigned long long)bs.bvh8NodeCount);
     {   /* the first build of a process also pays for scratch allocation and module loading: time a rebuild of the same scene */
         vkrt_cuda_build_stats again;
+        vkrt_cuda_invalidate_accel(VKRT_cudaContext(vkrt));
         if (vkrt_cuda_build_accel(VKRT_cudaContext(vkrt), &again) == VKRT_SUCCESS)
             printf("Acceleration structure rebuild: %.3f ms (%.1f M triangles/s), %u of %u hierarchies kept PLOC\n", again.buildMs,
                    again.buildMs > 0 ? (double)again.triangleCount / again.buildMs / 1e3 : 0.0, again.plocHierarchies, again.flat ? 1u : again.uniqueGeometries + 1u);
