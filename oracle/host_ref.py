@@ -5,6 +5,9 @@ SceneData sync) plus the glTF / vkrt.scene ingest.  It serves two purposes:
   * it is the checker for the product's C host library (vkrt_b200/host): tests compare array-for-array;
   * it prepares device-format scene arrays for oracle-vs-CUDA parity tests.
 The product never imports this module.
+Parity status: pinned where it matters for the tests -- pack_shader_vertices is compared with the reference's own packing.c on a million
+vertices (tests/test_reference_pin.py); the product's C host, which this module checks array for array on the bundled scenes, is itself
+byte-identical to the reference's host sources (oracle/_ref/libvkrt_refhost.so) for transforms, materials, camera and light tables.
 
 Reference files followed (paths relative to /root/reference/src):
   core/utility/packing.c:92-156          pack_shader_vertex, pack_oct_normal32, pack_tangent32, pack_color_rgba8

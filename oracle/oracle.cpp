@@ -4,10 +4,12 @@
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this library.
 // The product (vkrt_b200/) never links, includes or calls it.
 //
-// PARITY STATUS: UNPINNED. The reference has no tests, fixtures or golden vectors and cannot be compiled
-// or run in this environment (needs meson, slangc, Vulkan + a ray-tracing ICD, GLFW, spng, turbojpeg, OIDN),
-// and its BVH/intersection arithmetic lives in the Vulkan driver. This restatement is checked against the integer
-// known-answer values of SURVEY Appendix A.5 (tests/test_oracle_kat.py) and analytic scenes (tests/test_oracle_render.py).
+// PARITY STATUS: PINNED against the reference's own shader sources. `make -C oracle ref` compiles /root/reference/src/shaders/**/*.slang
+// (transliterated to C++ by oracle/ref_slang/) into oracle/_ref/libvkrt_refshade.so, and tests/test_reference_pin.py requires this
+// restatement to reproduce it BIT FOR BIT: known-answer functions, 20 000 randomised closure evaluations / samplings per render mode
+// with every lobe switched on, and whole frames (accumulation, denoiser features, display image) in RGB / single / hero. Not pinnable,
+// because upstream it is the Vulkan driver's and the repository holds no source for it: BVH build and traversal order, the ray /
+// triangle test, the texture filter (specified in accel.h and below; both sides of every comparison use these stand-ins).
 //
 // Structure follows the reference one function at a time; each block cites file:line under /root/reference/src/shaders.
 #include <cstdio>
@@ -209,7 +211,7 @@ static bool buildAccel(Ctx& c) {
 
 // ------------------------------------------------------------------------------------------------------------------
 // Textures (material/textures.slang:8-73; sampler setup core/scene/textures.c:141-209): LOD 0, bilinear, 3 wrap modes.
-// The reference uses the driver's fixed-function sampler (parity unpinned); pinned here as fp32 bilinear with
+// The reference uses the driver's fixed-function sampler (not pinnable upstream); specified here as fp32 bilinear with
 // the Vulkan texel-centre convention, sRGB decode per texel before filtering (8-bit LUT).
 // ------------------------------------------------------------------------------------------------------------------
 static int wrapCoord(int i, int n, uint32_t mode) {

@@ -1,7 +1,7 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle/README.md). CPU restatement of vkrt's Slang shading code.
-// Parity status: UNPINNED — the reference ships no tests/golden vectors for this path and
-// cannot be built here; this file is checked against the integer KATs of SURVEY Appendix A.5 and against
-// analytic properties (tests/test_oracle_*.py). Every function cites the reference file:line it follows
+// ORACLE — TEST INFRASTRUCTURE ONLY. CPU restatement of vkrt's Slang shading code.
+// Parity status: PINNED — bit-identical to the reference's own src/shaders/bsdf, utility, sampling sources compiled for the CPU
+// (oracle/_ref/libvkrt_refshade.so, built by `make -C oracle ref`): 20 000 randomised closure evaluations and samplings per render mode
+// with every lobe on, plus whole frames (tests/test_reference_pin.py). Every function cites the reference file:line it follows
 // (paths relative to /root/reference/src/shaders unless noted).
 #pragma once
 #include "vecmath.h"

@@ -1169,7 +1169,7 @@ struct BSDFState {
     // Hero mode evaluates the closure twice per vertex with the same (material, wo): once for the light sample, once for the sampled
     // direction. The two spectral upsamplings that do not depend on wi are kept from the first evaluation (the state lives in the
     // kernel's local frame; each lookup is ~100 instructions and 8 gathered 128-bit loads).
-    mutable float4 cachedDiffuse4, cachedVd4;
+    mutable float cachedDiffuse4[4], cachedVd4[4];   // plain floats (no alignment demands on the state record, which k_shade keeps in shared memory)
     mutable uint cachedMask = 0u;   // bit 0: cachedDiffuse4 valid, bit 1: cachedVd4 valid
     __device__ BSDFState() {}
     __device__ BSDFState(const BSDFMaterial& m, float3 wo_, uint ff, float wl, uint sm)
@@ -1285,10 +1285,11 @@ VK_D float4 evalSpectralReflectionStack(const SpectralTables& t, const BSDFState
     }
     if (s.sampleWeights.diffuse > 0.0f || s.sampleWeights.subsurface > 0.0f) {
         if (!(s.cachedMask & 1u)) {
-            s.cachedDiffuse4 = spectralScalarFromLinearSrgb4(t, saturate(bsdfDiffuseColor(m)), wl);
+            const float4 c = spectralScalarFromLinearSrgb4(t, saturate(bsdfDiffuseColor(m)), wl);
+            s.cachedDiffuse4[0] = c.x; s.cachedDiffuse4[1] = c.y; s.cachedDiffuse4[2] = c.z; s.cachedDiffuse4[3] = c.w;
             s.cachedMask |= 1u;
         }
-        const float4 diffuseColor = s.cachedDiffuse4;
+        const float4 diffuseColor(s.cachedDiffuse4[0], s.cachedDiffuse4[1], s.cachedDiffuse4[2], s.cachedDiffuse4[3]);
         if (s.sampleWeights.diffuse > 0.0f) {
             float ds = (1.0f - m.transmission) * (1.0f - m.subsurface);
             BSDFEval d = m.diffuseRoughness <= 0.0f ? evalLambertian(float3(ds), wi) : evalOrenNayar(float3(ds), m.diffuseRoughness, s.wo, wi);
@@ -1309,10 +1310,11 @@ VK_D float4 evalSpectralReflectionStack(const SpectralTables& t, const BSDFState
     float vc = coatDirectionalAttenuation(m, s.wo);
     const float4 vs = anyGreater(sheenColor, 0.0f) ? saturate(1.0f - sheenColor * sheenDirectionalAlbedo(cosTheta(s.wo), m.sheenRoughness)) : float4(1.0f);
     if (!(s.cachedMask & 2u)) {
-        s.cachedVd4 = spectralScalarFromLinearSrgb4(t, saturate(dielectricDirectionalAttenuation(m, s.wo)), wl);
+        const float4 c = spectralScalarFromLinearSrgb4(t, saturate(dielectricDirectionalAttenuation(m, s.wo)), wl);
+        s.cachedVd4[0] = c.x; s.cachedVd4[1] = c.y; s.cachedVd4[2] = c.z; s.cachedVd4[3] = c.w;
         s.cachedMask |= 2u;
     }
-    const float4 vd = s.cachedVd4;
+    const float4 vd(s.cachedVd4[0], s.cachedVd4[1], s.cachedVd4[2], s.cachedVd4[3]);
     float nonMetal = 1.0f - m.metallic;
     float ra = reflectionStackAttenuation(m, vc, wi);
     float4 baseValue = float4(coatValue) + ra * (m.metallic * metalValue + nonMetal * (dielectricValue + vd * substrateValue));

@@ -343,10 +343,11 @@ __device__ __forceinline__ float computeSpectralMISWeight(float4 sampled, float4
 // shade: one path vertex (the body of the reference's depth loop between two TraceRay calls)
 // ----------------------------------------------------------------------------------------------------------------------
 #ifndef SHADE_MIN_BLOCKS
-#define SHADE_MIN_BLOCKS 1
+#define SHADE_MIN_BLOCKS 2   // 2 x 256 threads x 128 registers: same 16 warps per SM as 1 x 512, but a phase barrier stalls 8 warps, not 16
 #endif
 #ifndef SHADE_BLOCK
-#define SHADE_BLOCK 512
+#define SHADE_BLOCK 256      // measured with the state in shared memory (profiles/r02_notes.md): 512 x 1 29.0 ms, 384 x 1 29.4, 256 x 2 27.2,
+                             // 192 x 3 (112 registers) 30.4, 128 x 4 28.3
 #endif
 // The body is cut into four phases separated by block barriers. k_shade is bound by instruction fetch, not by ALU or memory
 // (profiles/r01_notes.md: "no instruction" is the top stall with ~200 KB of SASS live); keeping the warps of a block inside the same
@@ -362,6 +363,21 @@ __device__ __forceinline__ float computeSpectralMISWeight(float4 sampled, float4
 #else
 #define SHADE_SUBPHASE_BARRIER()
 #endif
+// Per-thread record in SHARED memory for what a vertex carries across the phases of k_shade. The closure state is passed by reference
+// to out-of-line lobe functions, so it has to live in memory; as part of the kernel's local frame (0.5 KB x 512 threads) it overflowed
+// the L1 (r02c capture: L1 hit rate 58 %, lg_throttle on the state stores, long scoreboard 4.8 per issue). In shared memory the state,
+// the shading basis and the hit geometry cost no registers between phases and never leave the SM: hero shade 33.0 -> 27.2 ms per
+// 33 M-path frame together with 256-thread blocks (profiles/r02_notes.md). Putting the pending shadow ray and the hero technique pdfs
+// there as well was slower (30.5 ms): 2 x 100 KB of records leave the L1 only 28 KB for the spill slots.
+// Records sit at a stride of an odd number of 16-byte units: 128-bit accesses are conflict-free, 32-bit ones 4-way at worst.
+struct ShadeScratch {
+    BSDFState state;
+    ShadingBasis basis;
+    float3 geometricNormal, hitPoint, emission;
+};
+static_assert(alignof(ShadeScratch) <= 16, "ShadeScratch alignment");
+constexpr size_t SHADE_SCRATCH_STRIDE = (((sizeof(ShadeScratch) + 15) / 16) | 1) * 16;
+constexpr size_t SHADE_DYNAMIC_SMEM = SHADE_SCRATCH_STRIDE * SHADE_BLOCK;
 template <int MODE, bool ENVIS>
 __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ FrameParams fp, const uint32_t depth) {
     const uint32_t count = fp.extCount[depth];
@@ -397,12 +413,14 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const _
         float4 thr4(0.0f), wl4(0.0f), techPdf(0.0f);
         bool heroActive = false;
         MediumState medium;
-        MeshInfo mesh;
-        float3 hitPoint(0.0f);
-        SurfaceShadingData surface;
-        ShadingBasis basis;
-        BSDFState state;           // holds the only copy of the closure parameters that outlives phase 1 (state.material)
-        float3 emission(0.0f);     // textured, per-hit emission (integrator.slang:79-85)
+        float lightPdfArea = 0.0f;
+        extern __shared__ __align__(16) unsigned char shadeDynamicSmem[];
+        ShadeScratch& scratch = *reinterpret_cast<ShadeScratch*>(shadeDynamicSmem + (size_t)threadIdx.x * SHADE_SCRATCH_STRIDE);
+        BSDFState& state = scratch.state;        // holds the only copy of the closure parameters that outlives phase 1 (state.material)
+        ShadingBasis& basis = scratch.basis;
+        float3& hitPoint = scratch.hitPoint;
+        float3& geometricNormal = scratch.geometricNormal;
+        float3& emission = scratch.emission;     // textured, per-hit emission (integrator.slang:79-85)
         bool currentVertexNeeAllowed = false;
 
         if (live) {
@@ -506,7 +524,8 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const _
 
         // ---- surface (PathSurfaceState.__init) -----------------------------------------------------------------------
         if (live) {
-            mesh = loadMeshInfo(sc.meshInfos + hitInst);
+            const MeshInfo mesh = loadMeshInfo(sc.meshInfos + hitInst);
+            lightPdfArea = mesh.lightPdfArea;
             hitPoint = ray.origin + ray.direction * hitT;
             MeshTrig trig;
             {
@@ -514,7 +533,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const _
                 const ::float4 t0 = __ldg(tq), t1 = __ldg(tq + 1);
                 trig.sx = t0.x; trig.cx = t0.y; trig.sy = t0.z; trig.cy = t0.w; trig.sz = t1.x; trig.cz = t1.y; trig.pad0 = trig.pad1 = 0.0f;
             }
-            surface = reconstructSurfaceShading(sc, mesh, trig, hitPrim, float2(hitU, hitV), ray.direction);
+            SurfaceShadingData surface = reconstructSurfaceShading(sc, mesh, trig, hitPrim, float2(hitU, hitV), ray.direction);
             Material material = loadMaterial(sc.materials + surface.materialIndex);
             {
                 const ShadingBasis unperturbed = makeShadingBasis(surface.shadingNormal, surface.tangent);
@@ -522,9 +541,10 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const _
             }
             surface.shadingNormal = sanitizeShadingNormal(surface.shadingNormal, surface.geometricNormal, -ray.direction);
             basis = makeShadingBasis(surface.shadingNormal, surface.tangent);
+            geometricNormal = surface.geometricNormal;
             applySurfaceTextures(sc, material, surface.textureData);
             emission = float3(material.emissionColor[0], material.emissionColor[1], material.emissionColor[2]) * material.emissionLuminance;
-            state.material = BSDFMaterial(material);
+            const BSDFMaterial bm(material);
 
             // ---- primary-surface debug views (integrator/path/debug.slang:31-64) -----------------------------------------
             if (sampleIndex == 0u && depth == 0u && scene.debugMode != VKRT_DEBUG_MODE_NONE) {
@@ -544,10 +564,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const _
                     live = false;
                 }
             }
-        }
-        SHADE_SUBPHASE_BARRIER();
-        if (live) {
-            const BSDFMaterial bm = state.material;
+          if (live) {
             // ---- denoiser features (loop.slang:83-103) ----------------------------------------------------------------
             const bool follow = materialDenoiserShouldFollowSpecularHit(bm, surface.frontFace);
             if (depth == 0u) fp.rec.follow[rec] = follow ? 1.0f : 0.0f;
@@ -559,6 +576,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const _
             const float stateWavelength = MODE == MODE_RGB ? 0.0f : lambdaScalar;
             state = BSDFState(bm, worldToLocal(-ray.direction, basis), surface.frontFace, stateWavelength, MODE == MODE_RGB ? 0u : 1u);
             currentVertexNeeAllowed = !medium.refractiveActive();
+          }
         }
         SHADE_PHASE_BARRIER();
 
@@ -586,7 +604,8 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const _
                 ls = sampleDirectLightSurface(sc, scene, hitPoint, rng);
             }
             if (ls.valid) {
-                const float3 shadowOffset = dot(ls.wi, surface.geometricNormal) >= 0.0f ? surface.geometricNormal : -surface.geometricNormal;
+                const float3 gn = geometricNormal;
+                const float3 shadowOffset = dot(ls.wi, gn) >= 0.0f ? gn : -gn;
                 const float3 shadowOrigin = hitPoint + shadowOffset * SHADOW_ORIGIN_OFFSET;
                 const float3 wiLocal = worldToLocal(ls.wi, basis);
                 // common.slang:47-50 rejects the sample after the visibility test; evaluating it first and skipping the
@@ -644,7 +663,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const _
                     if (MODE == MODE_HERO && heroActive) {
                         float misWeight = heroWavelengthBalanceWeight(techPdf);
                         if (misActive) {
-                            const float lp2 = lightPdfAreaToSolidAngle(mesh.lightPdfArea, surface.geometricNormal, ray.direction, hitT) * (ENVIS ? 1.0f - sc.env.pEnv : 1.0f);
+                            const float lp2 = lightPdfAreaToSolidAngle(lightPdfArea, geometricNormal, ray.direction, hitT) * (ENVIS ? 1.0f - sc.env.pEnv : 1.0f);
                             const float4 pv = fromF4(S.prevVertexTechPdf[i]), pb = fromF4(S.prevBsdfTechPdf[i]);
                             misWeight = computeSpectralMISWeight(pv * pb, pv * lp2);
                         }
@@ -655,7 +674,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const _
                     } else {
                         float misWeight = 1.0f;
                         if (misActive && prevBsdfPdf > 0.0f) {
-                            const float lp2 = lightPdfAreaToSolidAngle(mesh.lightPdfArea, surface.geometricNormal, ray.direction, hitT) * (ENVIS ? 1.0f - sc.env.pEnv : 1.0f);
+                            const float lp2 = lightPdfAreaToSolidAngle(lightPdfArea, geometricNormal, ray.direction, hitT) * (ENVIS ? 1.0f - sc.env.pEnv : 1.0f);
                             misWeight = lp2 <= 0.0f ? 1.0f : powerHeuristic(prevBsdfPdf, lp2);
                         }
                         if (MODE == MODE_RGB) {
@@ -722,9 +741,9 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const _
         if (live) {
             if (pathContinues) {
                 // medium update + NEE bookkeeping (integrator.slang:96-98)
-                if (MODE == MODE_RGB) updateMediumStateFromTransmission(T, state.material, surface.frontFace, isTransmission, 0.0f, 0u, medium);
-                else if (MODE == MODE_HERO && heroActive) updateMediumStateFromTransmissionSpectral(T, state.material, surface.frontFace, isTransmission, wl4, medium);
-                else updateMediumStateFromTransmission(T, state.material, surface.frontFace, isTransmission, lambdaScalar, 1u, medium);
+                if (MODE == MODE_RGB) updateMediumStateFromTransmission(T, state.material, state.frontFace, isTransmission, 0.0f, 0u, medium);
+                else if (MODE == MODE_HERO && heroActive) updateMediumStateFromTransmissionSpectral(T, state.material, state.frontFace, isTransmission, wl4, medium);
+                else updateMediumStateFromTransmission(T, state.material, state.frontFace, isTransmission, lambdaScalar, 1u, medium);
                 const bool sampledPathNeeAllowed = currentVertexNeeAllowed && isTransmission == 0u;  // shadow kernel clears it on "unsupported"
                 flags = (flags & ~(PF_PREV_VERTEX_NEE_ALLOWED | PF_MEDIUM_REFRACTIVE | PF_MEDIUM_ABSORPTION)) |
                         (sampledPathNeeAllowed ? PF_PREV_VERTEX_NEE_ALLOWED : 0u) | (medium.flags << 1);
@@ -752,7 +771,8 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const _
             uint32_t newPos = 0x7fffffffu;
             if (pathContinues) {
                 newPos = allocSlots(fp.extCount + depth + 1u);
-                const float3 off = isTransmission != 0u ? -surface.geometricNormal : surface.geometricNormal;
+                const float3 gn = geometricNormal;
+                const float3 off = isTransmission != 0u ? -gn : gn;
                 N.rayO[newPos] = toF4(hitPoint + off * SHADOW_ORIGIN_OFFSET, RAY_T_MIN);
                 N.rayD[newPos] = toF4(wi, RAY_T_MAX);
                 N.meta[newPos] = make_uint4(rec, rng, flags, 0u);
@@ -1147,9 +1167,18 @@ int traceBlocksPerSm(bool count) {
 }
 int shadeBlocksPerSm(int mode) {
     int n = 0;
-    if (mode == MODE_RGB) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shade<MODE_RGB, false>, SHADE_BLOCK, 0);
-    else if (mode == MODE_SINGLE) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shade<MODE_SINGLE, false>, SHADE_BLOCK, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shade<MODE_HERO, false>, SHADE_BLOCK, 0);
+    if (SHADE_DYNAMIC_SMEM > 0) {   // more than the default 48 KB of dynamic shared memory needs an opt-in per kernel
+        const int bytes = (int)SHADE_DYNAMIC_SMEM;
+        cudaFuncSetAttribute(k_shade<MODE_RGB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        cudaFuncSetAttribute(k_shade<MODE_SINGLE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        cudaFuncSetAttribute(k_shade<MODE_HERO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        cudaFuncSetAttribute(k_shade<MODE_RGB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        cudaFuncSetAttribute(k_shade<MODE_SINGLE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        cudaFuncSetAttribute(k_shade<MODE_HERO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    }
+    if (mode == MODE_RGB) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shade<MODE_RGB, false>, SHADE_BLOCK, SHADE_DYNAMIC_SMEM);
+    else if (mode == MODE_SINGLE) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shade<MODE_SINGLE, false>, SHADE_BLOCK, SHADE_DYNAMIC_SMEM);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shade<MODE_HERO, false>, SHADE_BLOCK, SHADE_DYNAMIC_SMEM);
     return n > 0 ? n : 1;
 }
 
@@ -1161,14 +1190,14 @@ void launchRaygen(int mode, const FrameParams& fp, int grid, cudaStream_t st) {
 }
 void launchShade(int mode, const FrameParams& fp, uint32_t depth, int grid, cudaStream_t st) {
     if (fp.scene.env.active) {  // environment-map importance sampling: separate instantiations, the default kernels are untouched
-        if (mode == MODE_RGB) k_shade<MODE_RGB, true><<<grid, SHADE_BLOCK, 0, st>>>(fp, depth);
-        else if (mode == MODE_SINGLE) k_shade<MODE_SINGLE, true><<<grid, SHADE_BLOCK, 0, st>>>(fp, depth);
-        else k_shade<MODE_HERO, true><<<grid, SHADE_BLOCK, 0, st>>>(fp, depth);
+        if (mode == MODE_RGB) k_shade<MODE_RGB, true><<<grid, SHADE_BLOCK, SHADE_DYNAMIC_SMEM, st>>>(fp, depth);
+        else if (mode == MODE_SINGLE) k_shade<MODE_SINGLE, true><<<grid, SHADE_BLOCK, SHADE_DYNAMIC_SMEM, st>>>(fp, depth);
+        else k_shade<MODE_HERO, true><<<grid, SHADE_BLOCK, SHADE_DYNAMIC_SMEM, st>>>(fp, depth);
         return;
     }
-    if (mode == MODE_RGB) k_shade<MODE_RGB, false><<<grid, SHADE_BLOCK, 0, st>>>(fp, depth);
-    else if (mode == MODE_SINGLE) k_shade<MODE_SINGLE, false><<<grid, SHADE_BLOCK, 0, st>>>(fp, depth);
-    else k_shade<MODE_HERO, false><<<grid, SHADE_BLOCK, 0, st>>>(fp, depth);
+    if (mode == MODE_RGB) k_shade<MODE_RGB, false><<<grid, SHADE_BLOCK, SHADE_DYNAMIC_SMEM, st>>>(fp, depth);
+    else if (mode == MODE_SINGLE) k_shade<MODE_SINGLE, false><<<grid, SHADE_BLOCK, SHADE_DYNAMIC_SMEM, st>>>(fp, depth);
+    else k_shade<MODE_HERO, false><<<grid, SHADE_BLOCK, SHADE_DYNAMIC_SMEM, st>>>(fp, depth);
 }
 // weight of every environment texel for the importance-sampling table: luminance x sin(theta of the texel row)
 __global__ void k_env_weights(const SceneView sc, uint32_t textureIndex, float* __restrict__ out) {
