@@ -198,6 +198,9 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_nccl_unique_id(void* outId128);
 VKRT_CUDA_API VKRT_Result vkrt_cuda_comm_init(vkrt_cuda_ctx* ctx, const void* uniqueId128);
 /* Gathers every rank's tile-compact film images to rank 0 and un-permutes them into full-frame images there. */
 VKRT_CUDA_API VKRT_Result vkrt_cuda_gather(vkrt_cuda_ctx* ctx, float* outGatherMs);
+/* The same for a subset: bit k of aovMask = AOV k (bit 0 accumulation, 1 albedo, 2 normal, 3 display image). A progressive read-back
+ * of the accumulation alone moves a third of the bytes; one NCCL group and one un-tiling launch per AOV, one host synchronisation per call. */
+VKRT_CUDA_API VKRT_Result vkrt_cuda_gather_aovs(vkrt_cuda_ctx* ctx, uint32_t aovMask, float* outGatherMs);
 /* Device pointers of this rank's tile-compact images, for callers that run the collective themselves
  * (e.g. torch.distributed): bytes = localPixelCount * 16 (accum) / 8 (albedo, normal, output). */
 VKRT_CUDA_API VKRT_Result vkrt_cuda_local_film(vkrt_cuda_ctx* ctx, vkrt_cuda_aov which, void** outDevicePtr,

@@ -68,7 +68,7 @@ EXPORTS = [
     "vkrt_cuda_render_frame", "vkrt_cuda_render_frame_async", "vkrt_cuda_sync", "vkrt_cuda_timer_begin", "vkrt_cuda_timer_end", "vkrt_cuda_nccl_unique_id",
     "vkrt_cuda_comm_init", "vkrt_cuda_gather", "vkrt_cuda_local_film", "vkrt_cuda_import_gathered",
     "vkrt_cuda_max_local_pixels", "vkrt_cuda_read_aov", "vkrt_cuda_read_accum_samples", "vkrt_cuda_trace_primary", "vkrt_cuda_trace_rays",
-    "vkrt_cuda_eval_closures", "vkrt_cuda_invalidate_accel",
+    "vkrt_cuda_eval_closures", "vkrt_cuda_invalidate_accel", "vkrt_cuda_gather_aovs",
 ]
 
 _lib = None
@@ -219,9 +219,9 @@ class CudaContext:
         buf = C.create_string_buffer(unique_id, 128)
         self._check(self.lib.vkrt_cuda_comm_init(self.ctx, buf), "comm_init")
 
-    def gather(self):
+    def gather(self, aov_mask=0xF):
         ms = C.c_float()
-        self._check(self.lib.vkrt_cuda_gather(self.ctx, C.byref(ms)), "gather")
+        self._check(self.lib.vkrt_cuda_gather_aovs(self.ctx, C.c_uint32(aov_mask), C.byref(ms)), "gather")
         return ms.value
 
     def local_film(self, which):

@@ -35,6 +35,8 @@ void launchPackRgb2spec(const float* table, uint32_t dataOffset, size_t cellCoun
 void launchPrimaryStore(const FrameParams& fp, int grid, cudaStream_t st);
 void launchUntile(const void* src, void* dst, const TileMap& tm, const uint32_t* l2g, uint32_t words, int grid, cudaStream_t st);
 void launchMeshTrig(const MeshInfo* infos, MeshTrig* out, uint32_t count, cudaStream_t st);
+void launchUntileAll(const void* gathered, void* dst, const TileMap& tm, uint32_t worldSize, const uint32_t* tileLocalIndex, uint64_t rankStrideWords,
+                     uint32_t words, int grid, cudaStream_t st);
 void launchEvalClosures(const SceneView& sc, const vkrt_closure_query* queries, uint32_t count, vkrt_closure_result* results, cudaStream_t st);
 int traceBlocksPerSm(bool count);
 int shadeBlocksPerSm(int mode);
@@ -162,6 +164,7 @@ struct vkrt_cuda_ctx {
     DevBuf<uint8_t> gathered; // rank 0: concatenated tile-compact buffers of all ranks
     bool filmIsFullFrame[8] = {false};
     DevBuf<uint8_t> fullFrame[4];  // rank 0 after gather: accum, albedo, normal, output (row-major)
+    DevBuf<uint32_t> tileLocalIndex;  // per global tile: its position among its owner's tiles (built by resize, used by the gather)
 
     // per-launch stage timing (VKRT_CUDA_FLAG_STAGE_TIMING): event after every launch, kind 0 = raygen/shade/film, 1 = trace
     std::vector<cudaEvent_t> stageEvents;
@@ -1049,6 +1052,12 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_resize(vkrt_cuda_ctx* ctx, uint32_t width, u
         ctx->width = ctx->height = 0;
         return r;
     }
+    if (ctx->worldSize > 1) {   // the un-tiling table of the gather: once per resize, not once per rank, AOV and call
+        std::vector<uint32_t> local((size_t)lay.tilesX * lay.tilesY), next(ctx->worldSize, 0u);
+        for (uint32_t ty = 0; ty < lay.tilesY; ty++)
+            for (uint32_t tx = 0; tx < lay.tilesX; tx++) local[(size_t)ty * lay.tilesX + tx] = next[vkrt_tile_owner(&lay, tx, ty)]++;
+        CU(ctx->tileLocalIndex.upload(local.data(), local.size(), ctx->stream));
+    }
     ctx->readIndex = 0;
     r = resetAccumulation(ctx);
     if (r != VKRT_SUCCESS) return r;
@@ -1372,26 +1381,20 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_import_gathered(vkrt_cuda_ctx* ctx, vkrt_cud
     const size_t px = (size_t)ctx->width * ctx->height;
     const uint64_t stride = vkrt_cuda_max_local_pixels(ctx);
     CU(ctx->fullFrame[which].alloc(px * words * 4));
-    CU(cudaMemsetAsync(ctx->fullFrame[which].p, 0, px * words * 4, ctx->stream));
-    for (uint32_t r = 0; r < ctx->worldSize; r++) {
-        vkrt_tile_layout lay;
-        vkrt_tile_layout_init(&lay, ctx->width, ctx->height, ctx->tileW, ctx->tileH, r, ctx->worldSize);
-        std::vector<uint32_t> l2g(std::max(lay.localTileCount, 1u));
-        vkrt_tile_layout_local_tiles(&lay, l2g.data());
-        DevBuf<uint32_t> dl2g;
-        CU(dl2g.upload(l2g.data(), l2g.size(), ctx->stream));
-        TileMap tm = ctx->tiles;
-        tm.localTileCount = lay.localTileCount;
-        tm.localPixelCount = lay.localTileCount * lay.tileW * lay.tileH;
-        launchUntile((const uint8_t*)deviceGathered + (size_t)r * stride * words * 4, ctx->fullFrame[which].p, tm, dl2g.p, words, ctx->smCount * 4, ctx->stream);
-        CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->worldSize > 1) {
+        launchUntileAll(deviceGathered, ctx->fullFrame[which].p, ctx->tiles, ctx->worldSize, ctx->tileLocalIndex.p, stride * words, words, ctx->smCount * 8, ctx->stream);
+    } else {
+        launchUntile(deviceGathered, ctx->fullFrame[which].p, ctx->tiles, ctx->l2g.p, words, ctx->smCount * 4, ctx->stream);
     }
+    CU(cudaGetLastError());
     ctx->filmIsFullFrame[which] = true;
     return VKRT_SUCCESS;
 }
 
-VKRT_CUDA_API VKRT_Result vkrt_cuda_gather(vkrt_cuda_ctx* ctx, float* outGatherMs) {
-    if (!ctx || !ctx->width) return VKRT_ERROR_INVALID_ARGUMENT;
+VKRT_CUDA_API VKRT_Result vkrt_cuda_gather(vkrt_cuda_ctx* ctx, float* outGatherMs) { return vkrt_cuda_gather_aovs(ctx, 0xFu, outGatherMs); }
+
+VKRT_CUDA_API VKRT_Result vkrt_cuda_gather_aovs(vkrt_cuda_ctx* ctx, uint32_t aovMask, float* outGatherMs) {
+    if (!ctx || !ctx->width || (aovMask & ~0xFu)) return VKRT_ERROR_INVALID_ARGUMENT;
     cudaSetDevice(ctx->device);
     if (outGatherMs) *outGatherMs = 0.0f;
     if (ctx->worldSize == 1) return VKRT_SUCCESS;
@@ -1400,6 +1403,7 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_gather(vkrt_cuda_ctx* ctx, float* outGatherM
     const vkrt_cuda_aov aovs[4] = {VKRT_CUDA_AOV_ACCUM_RGBA32F, VKRT_CUDA_AOV_ALBEDO_RGBA16F, VKRT_CUDA_AOV_NORMAL_RGBA16F, VKRT_CUDA_AOV_OUTPUT_RGBA16};
     CU(cudaEventRecord(ctx->evA, ctx->stream));
     for (vkrt_cuda_aov which : aovs) {
+        if (!(aovMask & (1u << (uint32_t)which))) continue;
         const uint32_t words = which == VKRT_CUDA_AOV_ACCUM_RGBA32F ? 4u : 2u;
         void* local = nullptr;
         uint64_t bytes = 0;

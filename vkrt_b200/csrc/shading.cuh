@@ -314,7 +314,8 @@ struct BSDFMaterial {
     float specular = 0.5f;
     float specularTint = 0.0f;
     float abbeNumber = 0.0f;
-    float4 sheenTintWeight = float4(0.0f);
+    float3 sheenTint = float3(0.0f);   // sheenTintWeight.xyz / .w (two members: a float4 would force 16-byte alignment on the closure
+    float sheenWeight = 0.0f;          // state, which k_shade keeps in shared memory at a bank-conflict-avoiding odd stride)
     float clearcoat = 0.0f;
     float clearcoatGloss = 0.0f;
     float ior = 1.0f;
@@ -335,7 +336,8 @@ struct BSDFMaterial {
         specular = m.specular;
         specularTint = m.specularTint;
         abbeNumber = m.abbeNumber;
-        sheenTintWeight = float4(m.sheenTintWeight[0], m.sheenTintWeight[1], m.sheenTintWeight[2], m.sheenTintWeight[3]);
+        sheenTint = float3(m.sheenTintWeight[0], m.sheenTintWeight[1], m.sheenTintWeight[2]);
+        sheenWeight = m.sheenTintWeight[3];
         clearcoat = m.clearcoat;
         clearcoatGloss = m.clearcoatGloss;
         ior = m.ior;
@@ -352,8 +354,8 @@ VK_D float3 bsdfTintColor(float3 baseColor) {
     float lum = linearSrgbLuminance(baseColor);
     return lum <= 0.0f ? float3(1.0f) : baseColor / lum;
 }
-VK_D float bsdfSheenWeight(const BSDFMaterial& m) { return saturate(m.sheenTintWeight.w); }
-VK_D float3 bsdfSheenTint(const BSDFMaterial& m) { return saturate(m.sheenTintWeight.xyz()); }
+VK_D float bsdfSheenWeight(const BSDFMaterial& m) { return saturate(m.sheenWeight); }
+VK_D float3 bsdfSheenTint(const BSDFMaterial& m) { return saturate(m.sheenTint); }
 VK_D float3 bsdfSheenColor(const BSDFMaterial& m) { return bsdfSheenTint(m) * bsdfSheenWeight(m); }
 VK_D float3 bsdfTransmissionColor(const BSDFMaterial& m) {
     return m.transmission > 0.0f && m.metallic <= 0.0f ? float3(1.0f) : m.baseColor;

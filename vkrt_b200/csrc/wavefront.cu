@@ -369,14 +369,18 @@ __device__ __forceinline__ float computeSpectralMISWeight(float4 sampled, float4
 // the shading basis and the hit geometry cost no registers between phases and never leave the SM: hero shade 33.0 -> 27.2 ms per
 // 33 M-path frame together with 256-thread blocks (profiles/r02_notes.md). Putting the pending shadow ray and the hero technique pdfs
 // there as well was slower (30.5 ms): 2 x 100 KB of records leave the L1 only 28 KB for the spill slots.
-// Records sit at a stride of an odd number of 16-byte units: 128-bit accesses are conflict-free, 32-bit ones 4-way at worst.
+// Records sit at a stride of an odd number of 8-byte units: 32-bit accesses conflict 2-way at worst.
 struct ShadeScratch {
     BSDFState state;
     ShadingBasis basis;
     float3 geometricNormal, hitPoint, emission;
 };
-static_assert(alignof(ShadeScratch) <= 16, "ShadeScratch alignment");
+#ifdef SHADE_STRIDE16
 constexpr size_t SHADE_SCRATCH_STRIDE = (((sizeof(ShadeScratch) + 15) / 16) | 1) * 16;
+#else
+static_assert(alignof(ShadeScratch) <= 8, "ShadeScratch must not need more than 8-byte alignment");
+constexpr size_t SHADE_SCRATCH_STRIDE = (((sizeof(ShadeScratch) + 7) / 8) | 1) * 8;   // an odd number of 8-byte units: 2-way conflicts at worst
+#endif
 constexpr size_t SHADE_DYNAMIC_SMEM = SHADE_SCRATCH_STRIDE * SHADE_BLOCK;
 template <int MODE, bool ENVIS>
 __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ FrameParams fp, const uint32_t depth) {
@@ -414,7 +418,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const _
         bool heroActive = false;
         MediumState medium;
         float lightPdfArea = 0.0f;
-        extern __shared__ __align__(16) unsigned char shadeDynamicSmem[];
+        extern __shared__ __align__(16) unsigned char shadeDynamicSmem[];   // (per-thread records need 8-byte alignment only)
         ShadeScratch& scratch = *reinterpret_cast<ShadeScratch*>(shadeDynamicSmem + (size_t)threadIdx.x * SHADE_SCRATCH_STRIDE);
         BSDFState& state = scratch.state;        // holds the only copy of the closure parameters that outlives phase 1 (state.material)
         ShadingBasis& basis = scratch.basis;
@@ -1057,6 +1061,29 @@ __global__ void __launch_bounds__(256) k_untile(const uint32_t* __restrict__ src
         (void)srcStridePixels;
         for (uint32_t k = 0; k < words; k++) dst[d + k] = src[s + k];
     }
+}
+
+// Rank 0 after the NCCL gather: every rank's tile-compact buffer (rank r at r * strideWords) -> the full-frame row-major image, in ONE
+// launch. One thread per full-frame pixel: its tile's owner is (ty * tilesX + tx + ty) mod G (tiles.h) and tileLocalIndex[tile] is the
+// position of that tile among the owner's tiles (uploaded once per resize), so writes are coalesced and reads are 32-pixel runs.
+__global__ void __launch_bounds__(256) k_untile_all(const uint32_t* __restrict__ gathered, uint32_t* __restrict__ dst, TileMap tm, uint32_t worldSize,
+                                                    const uint32_t* __restrict__ tileLocalIndex, uint64_t rankStrideWords, uint32_t words) {
+    const uint64_t pixels = (uint64_t)tm.width * tm.height;
+    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < pixels; p += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t gy = (uint32_t)(p / tm.width), gx = (uint32_t)(p - (uint64_t)gy * tm.width);
+        const uint32_t tx = gx / tm.tileW, ty = gy / tm.tileH;
+        const uint32_t tile = ty * tm.tilesX + tx;
+        const uint32_t owner = (uint32_t)(((uint64_t)ty * tm.tilesX + tx + ty) % worldSize);
+        const uint64_t lp = (uint64_t)tileLocalIndex[tile] * tm.tileW * tm.tileH + (gy % tm.tileH) * tm.tileW + gx % tm.tileW;
+        const uint32_t* src = gathered + owner * rankStrideWords + lp * words;
+        uint32_t* d = dst + p * words;
+        if (words == 4u) *reinterpret_cast<::uint4*>(d) = *reinterpret_cast<const ::uint4*>(src);
+        else *reinterpret_cast<::uint2*>(d) = *reinterpret_cast<const ::uint2*>(src);
+    }
+}
+void launchUntileAll(const void* gathered, void* dst, const TileMap& tm, uint32_t worldSize, const uint32_t* tileLocalIndex, uint64_t rankStrideWords,
+                     uint32_t words, int grid, cudaStream_t st) {
+    k_untile_all<<<grid, 256, 0, st>>>((const uint32_t*)gathered, (uint32_t*)dst, tm, worldSize, tileLocalIndex, rankStrideWords, words);
 }
 
 // Accumulation texels at a few global pixel positions (auto-exposure probe): global pixel -> owning local tile by binary search in the
