@@ -26,6 +26,8 @@ namespace vk {
 void launchRaygen(int mode, const FrameParams& fp, int grid, cudaStream_t st);
 void launchShade(int mode, const FrameParams& fp, uint32_t depth, int grid, cudaStream_t st);
 void launchShadeSort(const FrameParams& fp, uint32_t depth, int smCount, cudaStream_t st);
+void launchRaySort(const ::float4* rayO, const ::float4* rayD, const uint32_t* count, uint32_t* order, uint32_t* bins, const float* lo, const float* invExtent,
+                   int smCount, cudaStream_t st);
 void launchFilm(int mode, const FrameParams& fp, int firstChunk, int lastChunk, int grid, cudaStream_t st);
 void launchEnvWeights(const SceneView& sc, uint32_t textureIndex, float* out, int grid, cudaStream_t st);
 void launchTrace(const TraceParams& tp, bool count, int grid, cudaStream_t st);  // picks the flat / two-level kernel from tp.scene.accel.flat
@@ -153,6 +155,9 @@ struct vkrt_cuda_ctx {
     DevBuf<::uint2> u2pool[8];
     DevBuf<uint32_t> counters;  // extCount | shCount | traceWork, MAX_DEPTH_SLOTS each
     DevBuf<uint32_t> shadeOrder, sortBins;
+    DevBuf<uint32_t> rayOrderExt, rayOrderShadow, raySortBins;   // ray binning experiment (VKRT_RAY_SORT)
+    int raySortMode = 0;                                          // 0 off, 1 extension rays, 2 shadow rays, 3 both
+    float sceneLo[3] = {0, 0, 0}, sceneInvExtent[3] = {1, 1, 1};  // box of the top-level BVH root (for the binning grid)
     DevBuf<unsigned long long> stats;
     FrameParams fp = {};
     int readIndex = 0;
@@ -297,6 +302,8 @@ VKRT_Result allocateWavefront(vkrt_cuda_ctx* ctx) {
     if (!ok) return fail(ctx, VKRT_ERROR_OUT_OF_MEMORY, "wavefront allocation failed (capacity %u paths, %u local pixels)", cap, lpc);
     if (ctx->counters.alloc(MAX_DEPTH_SLOTS * 4) != cudaSuccess || ctx->stats.alloc(4) != cudaSuccess)
         return fail(ctx, VKRT_ERROR_OUT_OF_MEMORY, "counter allocation failed");
+    if (ctx->raySortMode && (ctx->rayOrderExt.alloc(cap) != cudaSuccess || ctx->rayOrderShadow.alloc(cap) != cudaSuccess || ctx->raySortBins.alloc(1024) != cudaSuccess))
+        return fail(ctx, VKRT_ERROR_OUT_OF_MEMORY, "ray sort buffer allocation failed");
     if (ctx->shadeOrder.alloc(cap) != cudaSuccess || ctx->sortBins.alloc(512) != cudaSuccess)
         return fail(ctx, VKRT_ERROR_OUT_OF_MEMORY, "sort buffer allocation failed");
     fp.shadeOrder = (ctx->flags & VKRT_CUDA_FLAG_NO_MATERIAL_SORT) ? nullptr : ctx->shadeOrder.p;
@@ -422,6 +429,22 @@ TraceParams makeTraceParams(vkrt_cuda_ctx* ctx, uint32_t depth, bool haveExt, bo
     return tp;
 }
 
+// Box of the top-level BVH root (decoded from its quantisation frame): the grid of the ray-binning experiment.
+void updateSceneBox(vkrt_cuda_ctx* ctx) {
+    Bvh8Node root;
+    if (!ctx->raySortMode || cudaMemcpy(&root, ctx->nodes.p + ctx->tlasRoot, sizeof(root), cudaMemcpyDeviceToHost) != cudaSuccess) return;
+    const float p[3] = {root.px, root.py, root.pz};
+    const uint8_t e[3] = {root.ex, root.ey, root.ez};
+    for (int a = 0; a < 3; a++) {
+        uint32_t bits = (uint32_t)e[a] << 23;
+        float scale;
+        memcpy(&scale, &bits, 4);
+        const float extent = 255.0f * scale;
+        ctx->sceneLo[a] = p[a];
+        ctx->sceneInvExtent[a] = extent > 0.0f ? 1.0f / extent : 0.0f;
+    }
+}
+
 int renderModeOf(const SceneData& sd) {
     if (VKRT_RENDER_SETTINGS_MODE(sd.packedRenderSettings) != VKRT_RENDER_MODE_SPECTRAL) return 0;
     return VKRT_RENDER_SETTINGS_SPECTRAL(sd.packedRenderSettings) == VKRT_SPECTRAL_SAMPLING_MODE_HERO ? 2 : 1;
@@ -481,7 +504,19 @@ VKRT_Result enqueueFrame(vkrt_cuda_ctx* ctx, const SceneData* sceneData, uint32_
                 launchTrace(sp, count, ctx->traceGrid, st);
                 nl++;
             } else {
-                launchTrace(makeTraceParams(ctx, d, true, d > 0), count, ctx->traceGrid, st);
+                TraceParams tp = makeTraceParams(ctx, d, true, d > 0);
+                if ((ctx->raySortMode & 1) && d > 0) {   // depth 0: primary rays are in pixel order already
+                    launchRaySort(tp.rayO, tp.rayD, tp.extCount, ctx->rayOrderExt.p, ctx->raySortBins.p, ctx->sceneLo, ctx->sceneInvExtent, ctx->smCount, st);
+                    tp.extOrder = ctx->rayOrderExt.p;
+                    nl += 3;
+                }
+                if ((ctx->raySortMode & 2) && d > 0) {
+                    launchRaySort(tp.shO, tp.shD, tp.shCount, ctx->rayOrderShadow.p, ctx->raySortBins.p, ctx->sceneLo, ctx->sceneInvExtent, ctx->smCount, st);
+                    tp.shOrder = ctx->rayOrderShadow.p;
+                    nl += 3;
+                }
+                mark(0);
+                launchTrace(tp, count, ctx->traceGrid, st);
             }
             mark(1);
             if (fp.shadeOrder) { launchShadeSort(fp, d, ctx->smCount, st); nl += 3; mark(0); }
@@ -550,6 +585,7 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_create(const vkrt_cuda_create_info* info, vk
         return VKRT_ERROR_INVALID_ARGUMENT;
     }
     ctx->splitShadowTrace = getenv("VKRT_TRACE_SPLIT") && atoi(getenv("VKRT_TRACE_SPLIT")) != 0;
+    ctx->raySortMode = getenv("VKRT_RAY_SORT") ? atoi(getenv("VKRT_RAY_SORT")) : 0;
     ctx->builder.mode = (ctx->flags & VKRT_CUDA_FLAG_LBVH) ? AccelBuilder::BUILD_LBVH : ((ctx->flags & VKRT_CUDA_FLAG_PLOC) ? AccelBuilder::BUILD_PLOC : AccelBuilder::BUILD_BEST);
     if (cudaSetDevice(dev) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&ctx->evA) != cudaSuccess || cudaEventCreate(&ctx->evB) != cudaSuccess) {
@@ -891,6 +927,7 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_build_accel(vkrt_cuda_ctx* ctx, vkrt_cuda_bu
         CU(cudaStreamSynchronize(st));
         CU(cudaGetLastError());
         ctx->tlasRoot = 0;
+        updateSceneBox(ctx);
         ctx->accelValid = true;
         vkrt_cuda_build_stats& s = ctx->buildStats;
         float ms = 0;
@@ -1001,6 +1038,7 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_build_accel(vkrt_cuda_ctx* ctx, vkrt_cuda_bu
     cudaEventElapsedTime(&blasMs, ctx->evA, ctx->evB);
     cudaEventElapsedTime(&tlasMs, ctx->evB, evC);
     cudaEventDestroy(evC);
+    updateSceneBox(ctx);
     ctx->accelValid = true;
     vkrt_cuda_build_stats& s = ctx->buildStats;
     s.blasMs = blasMs;
