@@ -26,8 +26,6 @@ namespace vk {
 void launchRaygen(int mode, const FrameParams& fp, int grid, cudaStream_t st);
 void launchShade(int mode, const FrameParams& fp, uint32_t depth, int grid, cudaStream_t st);
 void launchShadeSort(const FrameParams& fp, uint32_t depth, int smCount, cudaStream_t st);
-void launchRaySort(const ::float4* rayO, const ::float4* rayD, const uint32_t* count, uint32_t* order, uint32_t* bins, const float* lo, const float* invExtent,
-                   int smCount, cudaStream_t st);
 void launchFilm(int mode, const FrameParams& fp, int firstChunk, int lastChunk, int grid, cudaStream_t st);
 void launchEnvWeights(const SceneView& sc, uint32_t textureIndex, float* out, int grid, cudaStream_t st);
 void launchTrace(const TraceParams& tp, bool count, int grid, cudaStream_t st);  // picks the flat / two-level kernel from tp.scene.accel.flat
@@ -140,6 +138,7 @@ struct vkrt_cuda_ctx {
     DevBuf<uint32_t> instanceBlas;
     uint32_t tlasRoot = 0;
     bool accelValid = false;
+    bool anyTransmissive = false;   // some instance record carries INSTANCE_FLAG_TRANSMISSIVE (set by build_accel)
     vkrt_cuda_build_stats buildStats = {};
 
     // film + wavefront
@@ -155,16 +154,12 @@ struct vkrt_cuda_ctx {
     DevBuf<::uint2> u2pool[8];
     DevBuf<uint32_t> counters;  // extCount | shCount | traceWork, MAX_DEPTH_SLOTS each
     DevBuf<uint32_t> shadeOrder, sortBins;
-    DevBuf<uint32_t> rayOrderExt, rayOrderShadow, raySortBins;   // ray binning experiment (VKRT_RAY_SORT)
-    int raySortMode = 0;                                          // 0 off, 1 extension rays, 2 shadow rays, 3 both
-    float sceneLo[3] = {0, 0, 0}, sceneInvExtent[3] = {1, 1, 1};  // box of the top-level BVH root (for the binning grid)
     DevBuf<unsigned long long> stats;
     FrameParams fp = {};
     int readIndex = 0;
     SceneData lastScene = {};
     bool haveScene = false;
     int traceGrid = 0, shadeGrid[3] = {0, 0, 0};
-    bool splitShadowTrace = false;
     DevBuf<uint8_t> staging;  // full-frame un-tiled image for read_aov
     DevBuf<uint8_t> gathered; // rank 0: concatenated tile-compact buffers of all ranks
     bool filmIsFullFrame[8] = {false};
@@ -302,8 +297,6 @@ VKRT_Result allocateWavefront(vkrt_cuda_ctx* ctx) {
     if (!ok) return fail(ctx, VKRT_ERROR_OUT_OF_MEMORY, "wavefront allocation failed (capacity %u paths, %u local pixels)", cap, lpc);
     if (ctx->counters.alloc(MAX_DEPTH_SLOTS * 4) != cudaSuccess || ctx->stats.alloc(4) != cudaSuccess)
         return fail(ctx, VKRT_ERROR_OUT_OF_MEMORY, "counter allocation failed");
-    if (ctx->raySortMode && (ctx->rayOrderExt.alloc(cap) != cudaSuccess || ctx->rayOrderShadow.alloc(cap) != cudaSuccess || ctx->raySortBins.alloc(1024) != cudaSuccess))
-        return fail(ctx, VKRT_ERROR_OUT_OF_MEMORY, "ray sort buffer allocation failed");
     if (ctx->shadeOrder.alloc(cap) != cudaSuccess || ctx->sortBins.alloc(512) != cudaSuccess)
         return fail(ctx, VKRT_ERROR_OUT_OF_MEMORY, "sort buffer allocation failed");
     fp.shadeOrder = (ctx->flags & VKRT_CUDA_FLAG_NO_MATERIAL_SORT) ? nullptr : ctx->shadeOrder.p;
@@ -396,7 +389,7 @@ void fillFrameParams(vkrt_cuda_ctx* ctx, const SceneData& sd) {
     fp.tiles = ctx->tiles;
     fp.tiles.localToGlobalTile = ctx->l2g.p;
     fp.readIndex = ctx->readIndex;
-    fp.modeFlags = modeFlagsFor(sd, envImportance);
+    fp.modeFlags = modeFlagsFor(sd, envImportance) | (ctx->anyTransmissive ? MODE_SCENE_TRANSMISSIVE : 0u);
 }
 
 TraceParams makeTraceParams(vkrt_cuda_ctx* ctx, uint32_t depth, bool haveExt, bool haveShadow) {
@@ -427,22 +420,6 @@ TraceParams makeTraceParams(vkrt_cuda_ctx* ctx, uint32_t depth, bool haveExt, bo
     tp.workCounter = fp.traceWork + depth;
     tp.stats = (ctx->flags & VKRT_CUDA_FLAG_COUNT_RAYS) ? ctx->stats.p : nullptr;
     return tp;
-}
-
-// Box of the top-level BVH root (decoded from its quantisation frame): the grid of the ray-binning experiment.
-void updateSceneBox(vkrt_cuda_ctx* ctx) {
-    Bvh8Node root;
-    if (!ctx->raySortMode || cudaMemcpy(&root, ctx->nodes.p + ctx->tlasRoot, sizeof(root), cudaMemcpyDeviceToHost) != cudaSuccess) return;
-    const float p[3] = {root.px, root.py, root.pz};
-    const uint8_t e[3] = {root.ex, root.ey, root.ez};
-    for (int a = 0; a < 3; a++) {
-        uint32_t bits = (uint32_t)e[a] << 23;
-        float scale;
-        memcpy(&scale, &bits, 4);
-        const float extent = 255.0f * scale;
-        ctx->sceneLo[a] = p[a];
-        ctx->sceneInvExtent[a] = extent > 0.0f ? 1.0f / extent : 0.0f;
-    }
 }
 
 int renderModeOf(const SceneData& sd) {
@@ -497,27 +474,7 @@ VKRT_Result enqueueFrame(vkrt_cuda_ctx* ctx, const SceneData* sceneData, uint32_
         nl++;
         mark(0);
         for (uint32_t d = 0; d < sd.rrMaxDepth; d++) {
-            if (ctx->splitShadowTrace && d > 0) {   // A/B knob (VKRT_TRACE_SPLIT=1): closest-hit and any-hit rays in separate launches
-                launchTrace(makeTraceParams(ctx, d, true, false), count, ctx->traceGrid, st);
-                TraceParams sp = makeTraceParams(ctx, d, false, true);
-                sp.workCounter = ctx->counters.p + 3 * MAX_DEPTH_SLOTS + d;
-                launchTrace(sp, count, ctx->traceGrid, st);
-                nl++;
-            } else {
-                TraceParams tp = makeTraceParams(ctx, d, true, d > 0);
-                if ((ctx->raySortMode & 1) && d > 0) {   // depth 0: primary rays are in pixel order already
-                    launchRaySort(tp.rayO, tp.rayD, tp.extCount, ctx->rayOrderExt.p, ctx->raySortBins.p, ctx->sceneLo, ctx->sceneInvExtent, ctx->smCount, st);
-                    tp.extOrder = ctx->rayOrderExt.p;
-                    nl += 3;
-                }
-                if ((ctx->raySortMode & 2) && d > 0) {
-                    launchRaySort(tp.shO, tp.shD, tp.shCount, ctx->rayOrderShadow.p, ctx->raySortBins.p, ctx->sceneLo, ctx->sceneInvExtent, ctx->smCount, st);
-                    tp.shOrder = ctx->rayOrderShadow.p;
-                    nl += 3;
-                }
-                mark(0);
-                launchTrace(tp, count, ctx->traceGrid, st);
-            }
+            launchTrace(makeTraceParams(ctx, d, true, d > 0), count, ctx->traceGrid, st);
             mark(1);
             if (fp.shadeOrder) { launchShadeSort(fp, d, ctx->smCount, st); nl += 3; mark(0); }
             launchShade(mode, fp, d, ctx->shadeGrid[mode], st);
@@ -584,8 +541,6 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_create(const vkrt_cuda_create_info* info, vk
         delete ctx;
         return VKRT_ERROR_INVALID_ARGUMENT;
     }
-    ctx->splitShadowTrace = getenv("VKRT_TRACE_SPLIT") && atoi(getenv("VKRT_TRACE_SPLIT")) != 0;
-    ctx->raySortMode = getenv("VKRT_RAY_SORT") ? atoi(getenv("VKRT_RAY_SORT")) : 0;
     ctx->builder.mode = (ctx->flags & VKRT_CUDA_FLAG_LBVH) ? AccelBuilder::BUILD_LBVH : ((ctx->flags & VKRT_CUDA_FLAG_PLOC) ? AccelBuilder::BUILD_PLOC : AccelBuilder::BUILD_BEST);
     if (cudaSetDevice(dev) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&ctx->evA) != cudaSuccess || cudaEventCreate(&ctx->evB) != cudaSuccess) {
@@ -876,6 +831,7 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_build_accel(vkrt_cuda_ctx* ctx, vkrt_cuda_bu
         std::vector<::uint4> instTable(n);
         std::vector<uint32_t> triOffsets(n + 1, 0u);
         std::vector<InstanceRecord> records(n);
+        bool anyTransmissive = false;
         for (uint32_t i = 0; i < n; i++) {
             const BlasDesc& d = blas[instanceBlas[i]];
             instTable[i] = make_uint4(d.vertexBase, d.indexBase, d.primBase, d.triCount);
@@ -889,7 +845,7 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_build_accel(vkrt_cuda_ctx* ctx, vkrt_cuda_bu
             r.blasRoot = 0;
             r.flags = 0;
             if (ctx->hostAlpha[i]) r.flags |= INSTANCE_FLAG_ALPHA_TESTED;
-            if (ctx->hostMaterials[ctx->hostMeshInfos[i].materialIndex].transmission > 0.0f) r.flags |= INSTANCE_FLAG_TRANSMISSIVE;
+            if (ctx->hostMaterials[ctx->hostMeshInfos[i].materialIndex].transmission > 0.0f) { r.flags |= INSTANCE_FLAG_TRANSMISSIVE; anyTransmissive = true; }
             if (d.triCount == 0) r.flags |= INSTANCE_FLAG_EMPTY;
             r.instanceIndex = i;
             r.pad = 0;
@@ -927,8 +883,8 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_build_accel(vkrt_cuda_ctx* ctx, vkrt_cuda_bu
         CU(cudaStreamSynchronize(st));
         CU(cudaGetLastError());
         ctx->tlasRoot = 0;
-        updateSceneBox(ctx);
         ctx->accelValid = true;
+        ctx->anyTransmissive = anyTransmissive;
         vkrt_cuda_build_stats& s = ctx->buildStats;
         float ms = 0;
         cudaEventElapsedTime(&ms, ctx->evA, ctx->evB);
@@ -979,6 +935,7 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_build_accel(vkrt_cuda_ctx* ctx, vkrt_cuda_bu
     CU(cudaEventRecord(ctx->evB, st));
     // --- instance records ---
     std::vector<InstanceRecord> records(std::max(n, 1u));
+    bool anyTransmissive = false;
     for (uint32_t i = 0; i < n; i++) {
         float inv[12];
         invertAffine3x4(&ctx->hostWorld[(size_t)i * 12], inv);
@@ -990,7 +947,7 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_build_accel(vkrt_cuda_ctx* ctx, vkrt_cuda_bu
         r.blasRoot = d.nodeBase;  // rebased below once nodes are compacted
         r.flags = 0;
         if (ctx->hostAlpha[i]) r.flags |= INSTANCE_FLAG_ALPHA_TESTED;
-        if (ctx->hostMaterials[ctx->hostMeshInfos[i].materialIndex].transmission > 0.0f) r.flags |= INSTANCE_FLAG_TRANSMISSIVE;
+        if (ctx->hostMaterials[ctx->hostMeshInfos[i].materialIndex].transmission > 0.0f) { r.flags |= INSTANCE_FLAG_TRANSMISSIVE; anyTransmissive = true; }
         if (d.triCount == 0) r.flags |= INSTANCE_FLAG_EMPTY;
         r.instanceIndex = i;
         r.pad = 0;
@@ -1038,8 +995,8 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_build_accel(vkrt_cuda_ctx* ctx, vkrt_cuda_bu
     cudaEventElapsedTime(&blasMs, ctx->evA, ctx->evB);
     cudaEventElapsedTime(&tlasMs, ctx->evB, evC);
     cudaEventDestroy(evC);
-    updateSceneBox(ctx);
     ctx->accelValid = true;
+    ctx->anyTransmissive = anyTransmissive;
     vkrt_cuda_build_stats& s = ctx->buildStats;
     s.blasMs = blasMs;
     s.tlasMs = tlasMs;

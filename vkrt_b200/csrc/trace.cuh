@@ -56,10 +56,6 @@ struct TraceParams {
     float* radianceScalar;       // hero mode: single-wavelength lane after dispersive collapse
     uint32_t* pathFlags;         // new path-state flags (bit 0 = prevVertexNeeAllowed)
     uint32_t* shadowResult;      // optional (trace_rays API): 0 visible, 1 occluded, 2 unsupported transmission
-    // optional traversal order (ray binning, api.cu): work item k of the extension part traces slot extOrder[k], of the shadow part
-    // shOrder[k]; nullptr = queue order. Results are written by slot, so the order never changes a result.
-    const uint32_t* extOrder;
-    const uint32_t* shOrder;
     // bookkeeping
     uint32_t* workCounter;       // zero-initialised per launch
     unsigned long long* stats;   // optional: [0] nodes visited, [1] triangles tested, [2] instances entered
@@ -178,16 +174,12 @@ __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS) k_trace(const T
                     const uint32_t idx = base + __popc(idle & ((1u << lane) - 1u));
                     if (idx < total) {
                         R.anyHit = idx >= extCount;
+                        R.index = idx;
                         ::float4 ro, rd;
                         if (!R.anyHit) {
-                            const uint32_t slot = P.extOrder ? __ldg(P.extOrder + idx) : idx;
-                            R.index = slot;
-                            ro = __ldg(P.rayO + slot); rd = __ldg(P.rayD + slot);
+                            ro = __ldg(P.rayO + idx); rd = __ldg(P.rayD + idx);
                         } else {
-                            const uint32_t k = idx - extCount;
-                            const uint32_t slot = P.shOrder ? __ldg(P.shOrder + k) : k;
-                            R.index = extCount + slot;
-                            ro = __ldg(P.shO + slot); rd = __ldg(P.shD + slot);
+                            ro = __ldg(P.shO + (idx - extCount)); rd = __ldg(P.shD + (idx - extCount));
                         }
                         R.o = float3(ro.x, ro.y, ro.z);
                         R.d = float3(rd.x, rd.y, rd.z);

@@ -612,9 +612,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const _
                 const float3 shadowOffset = dot(ls.wi, gn) >= 0.0f ? gn : -gn;
                 const float3 shadowOrigin = hitPoint + shadowOffset * SHADOW_ORIGIN_OFFSET;
                 const float3 wiLocal = worldToLocal(ls.wi, basis);
-                // common.slang:47-50 rejects the sample after the visibility test; evaluating it first and skipping the
-                // ray is equivalent for the radiance and only changes what "unsupported transmission" can observe when the
-                // contribution is zero anyway -- so the shadow ray is always traced when the light sample is valid.
+                // common.slang:47-50 rejects the sample after the visibility test; evaluating it first is equivalent for the radiance.
                 float4 c(0.0f);
                 const bool refractiveReject = materialMediumIsRefractive(state.material) && cosTheta(wiLocal) <= 0.0f;
                 if (!refractiveReject) {
@@ -645,7 +643,9 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const _
                         }
                     }
                 }
-                shadowPending = true;
+                // A shadow ray whose contribution is zero (light below the shading horizon, zero MIS weight) can only be observed through
+                // "unsupported transmission" (it clears the next vertex's NEE flag): with no transmissive instance in the scene it is dropped.
+                shadowPending = (fp.modeFlags & MODE_SCENE_TRANSMISSIVE) || c.x != 0.0f || c.y != 0.0f || c.z != 0.0f || c.w != 0.0f;
                 shadowO = toF4(shadowOrigin, RAY_T_MIN);
                 shadowD = toF4(ls.wi, ls.shadowDistance);
                 shadowC = toF4(c);
@@ -867,87 +867,6 @@ __global__ void __launch_bounds__(256) k_sort_scatter(const FrameParams fp, cons
         __syncthreads();
     }
 }
-// ----------------------------------------------------------------------------------------------------------------------
-// Ray binning before traversal (experiment, VKRT_RAY_SORT=1): a 512-bin counting sort of a ray queue on key = direction octant (3 bits)
-// | origin cell on a 4 x 4 x 4 grid over the scene box (6 bits), so that the rays a warp pulls together start in the same region and
-// head the same way. Same three-kernel shape as the material sort.
-// ----------------------------------------------------------------------------------------------------------------------
-constexpr int RAY_BINS = 512;
-struct RaySortParams {
-    const ::float4* rayO;
-    const ::float4* rayD;
-    const uint32_t* count;
-    uint32_t* order;
-    uint32_t* bins;       // [0..511] counts -> starts, [512..1023] cursors
-    float lo[3], invExtent[3];
-};
-__device__ __forceinline__ uint32_t raySortKey(const RaySortParams& P, uint32_t i) {
-    const ::float4 o = P.rayO[i], d = P.rayD[i];
-    const int cx = ::min(3, ::max(0, (int)((o.x - P.lo[0]) * P.invExtent[0] * 4.0f)));
-    const int cy = ::min(3, ::max(0, (int)((o.y - P.lo[1]) * P.invExtent[1] * 4.0f)));
-    const int cz = ::min(3, ::max(0, (int)((o.z - P.lo[2]) * P.invExtent[2] * 4.0f)));
-    const uint32_t oct = (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u);
-    return (oct << 6) | (uint32_t)(cx | (cy << 2) | (cz << 4));
-}
-__global__ void __launch_bounds__(RAY_BINS) k_raysort_count(const RaySortParams P) {
-    __shared__ uint32_t hist[RAY_BINS];
-    hist[threadIdx.x] = 0u;
-    __syncthreads();
-    const uint32_t count = *P.count;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) atomicAdd(&hist[raySortKey(P, i)], 1u);
-    __syncthreads();
-    if (hist[threadIdx.x]) atomicAdd(&P.bins[threadIdx.x], hist[threadIdx.x]);
-}
-__global__ void __launch_bounds__(RAY_BINS) k_raysort_scan(const RaySortParams P) {
-    __shared__ uint32_t s[RAY_BINS];
-    const uint32_t c = P.bins[threadIdx.x];
-    s[threadIdx.x] = c;
-    __syncthreads();
-    for (int o = 1; o < RAY_BINS; o <<= 1) {
-        uint32_t v = threadIdx.x >= (uint32_t)o ? s[threadIdx.x - o] : 0u;
-        __syncthreads();
-        s[threadIdx.x] += v;
-        __syncthreads();
-    }
-    P.bins[threadIdx.x] = s[threadIdx.x] - c;
-    P.bins[RAY_BINS + threadIdx.x] = 0u;
-}
-__global__ void __launch_bounds__(RAY_BINS) k_raysort_scatter(const RaySortParams P) {
-    __shared__ uint32_t hist[RAY_BINS], base[RAY_BINS];
-    const uint32_t count = *P.count;
-    constexpr uint32_t ITEMS = 4;
-    for (uint32_t chunk = blockIdx.x * RAY_BINS * ITEMS; chunk < count; chunk += gridDim.x * RAY_BINS * ITEMS) {
-        hist[threadIdx.x] = 0u;
-        __syncthreads();
-        uint32_t key[ITEMS], rank[ITEMS];
-#pragma unroll
-        for (uint32_t k = 0; k < ITEMS; k++) {
-            const uint32_t i = chunk + k * RAY_BINS + threadIdx.x;
-            key[k] = i < count ? raySortKey(P, i) : 0u;
-            if (i < count) rank[k] = atomicAdd(&hist[key[k]], 1u);
-        }
-        __syncthreads();
-        if (hist[threadIdx.x]) base[threadIdx.x] = P.bins[threadIdx.x] + atomicAdd(&P.bins[RAY_BINS + threadIdx.x], hist[threadIdx.x]);
-        __syncthreads();
-#pragma unroll
-        for (uint32_t k = 0; k < ITEMS; k++) {
-            const uint32_t i = chunk + k * RAY_BINS + threadIdx.x;
-            if (i < count) P.order[base[key[k]] + rank[k]] = i;
-        }
-        __syncthreads();
-    }
-}
-void launchRaySort(const ::float4* rayO, const ::float4* rayD, const uint32_t* count, uint32_t* order, uint32_t* bins, const float* lo, const float* invExtent,
-                   int smCount, cudaStream_t st) {
-    RaySortParams P;
-    P.rayO = rayO; P.rayD = rayD; P.count = count; P.order = order; P.bins = bins;
-    for (int a = 0; a < 3; a++) { P.lo[a] = lo[a]; P.invExtent[a] = invExtent[a]; }
-    cudaMemsetAsync(bins, 0, sizeof(uint32_t) * 2 * RAY_BINS, st);
-    k_raysort_count<<<smCount * 4, RAY_BINS, 0, st>>>(P);
-    k_raysort_scan<<<1, RAY_BINS, 0, st>>>(P);
-    k_raysort_scatter<<<smCount * 4, RAY_BINS, 0, st>>>(P);
-}
-
 void launchShadeSort(const FrameParams& fp, uint32_t depth, int smCount, cudaStream_t st) {
     cudaMemsetAsync(fp.sortBins, 0, sizeof(uint32_t) * 512, st);
     k_sort_count<<<smCount * 8, 256, 0, st>>>(fp, depth);

@@ -108,7 +108,8 @@ struct FrameParams {
 enum : uint32_t {
     MODE_BSDF_ONLY = 1u << 0, MODE_NEE_ONLY = 1u << 1, MODE_BOUNCE_COUNT = 1u << 2, MODE_DN_ALBEDO = 1u << 3,
     MODE_DN_NORMAL = 1u << 4, MODE_DN_VALIDITY = 1u << 5, MODE_DN_DEPTH = 1u << 6, MODE_DN_FOLLOW = 1u << 7,
-    MODE_NEE_ENABLED = 1u << 8
+    MODE_NEE_ENABLED = 1u << 8,
+    MODE_SCENE_TRANSMISSIVE = 1u << 9   // some instance has material.transmission > 0: shadow rays can report "unsupported transmission"
 };
 
 } // namespace vk
