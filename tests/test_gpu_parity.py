@@ -199,6 +199,30 @@ def test_accumulation_is_a_running_mean_and_deterministic():
     assert np.array_equal(a.view(np.uint32), g1.read(H.AOV_ACCUM).view(np.uint32)), "re-render must be bit-identical"
 
 
+@pytest.mark.parametrize("scene", ["cornell_glass", "lobes", "textured"])
+@pytest.mark.parametrize("spectral", [1, 2])
+def test_spectral_memo_changes_no_bit(scene, spectral, monkeypatch):
+    """k_spectral_memo looks the rgb2spec table up once per material / light constant (diffuse colour, emission) instead of once per path
+    vertex; an entry is used only when its key equals the colour at hand bit for bit. Frames with the memo and with every lookup going to
+    the table (VKRT_NO_SPECTRAL_MEMO=1, read at context creation) must be bit-identical, textured materials (memo misses) included."""
+    w = h = 96
+    prep = {"cornell_glass": lambda: scenes.cornell(w, h, spp=4, glass=True), "lobes": lambda: scenes.lobes(w, h, spp=4),
+            "textured": lambda: scenes.textured(w, h, spp=4)}[scene]()
+    prep["sceneData"]["packedRenderSettings"] = H.hr.pack_render_settings(0, 1, 1 if spectral == 2 else 0)
+    table = scenes.rgb2spec()
+    images = []
+    for off in ("0", "1"):
+        monkeypatch.setenv("VKRT_NO_SPECTRAL_MEMO", off)
+        g = H.CudaBackend()
+        g.upload(prep, rgb2spec=table)
+        g.resize(w, h)
+        g.render(prep["sceneData"], frames=2)
+        images.append(g.read(H.AOV_ACCUM))
+        g.close()
+    assert float(images[0][..., :3].mean()) > 0.0
+    assert np.array_equal(images[0].view(np.uint32), images[1].view(np.uint32))
+
+
 def test_full_size_frame_properties():
     """BASELINE config C2 at full size (1920x1080, spectral hero, 16 spp per frame = 33.2 M paths), where the oracle would take minutes:
     size-independent properties instead. (1) a frame rendered in three sample chunks equals the unchunked frame bit for bit; (2) the

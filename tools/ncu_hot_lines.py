@@ -74,3 +74,6 @@ print("-- innermost source line: samples %, warp-instructions %, lanes per instr
 for k, s in by_in.most_common(top):
     rs = ", ".join("%s %d" % kv for kv in reasons[k].most_common(3))
     print("%-18s:%-5d %5.1f%% %5.1f%% %5.1f  %s" % (k[0], k[1], 100.0 * s / total, 100.0 * inst_in[k] / max(tot_inst, 1), thr_in[k] / max(inst_in[k], 1), rs))
+print("-- outermost frame (line of the kernel body or of the out-of-line function that the instruction was inlined into): samples %")
+for k, s in by_out.most_common(top):
+    print("%-18s:%-5d %5.1f%%" % (k[0], k[1], 100.0 * s / total))

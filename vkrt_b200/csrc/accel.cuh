@@ -63,6 +63,7 @@ struct AccelView {
     uint32_t instanceCount; // 0 = nothing to hit
     uint32_t flat;          // 1 = single-level BVH over instanced triangles
     uint32_t stackNeed;     // upper bound of the traversal stack entries a ray can need (from the built tree depths); picks the k_trace stack size
+    uint32_t refillLanes;   // a warp of k_trace fetches new rays when fewer lanes than this are still traversing (trace.cuh)
 };
 
 } // namespace vk

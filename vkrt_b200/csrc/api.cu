@@ -28,6 +28,7 @@ void launchShade(int mode, const FrameParams& fp, uint32_t depth, int grid, cuda
 void launchShadeSort(const FrameParams& fp, uint32_t depth, int smCount, cudaStream_t st);
 void launchFilm(int mode, const FrameParams& fp, int firstChunk, int lastChunk, int grid, cudaStream_t st);
 void launchEnvWeights(const SceneView& sc, uint32_t textureIndex, float* out, int grid, cudaStream_t st);
+void launchSpectralMemo(const SceneView& sc, uint32_t materialCount, uint32_t emissiveMeshCount, SpectralMemoEntry* materialMemo, SpectralMemoEntry* emissiveMemo, cudaStream_t st);
 void launchTrace(const TraceParams& tp, bool count, int grid, cudaStream_t st);  // picks the flat / two-level kernel from tp.scene.accel.flat
 void launchPrimaryRaygen(const FrameParams& fp, int jittered, int grid, cudaStream_t st);
 void launchProbeAccum(const ::float4* accum, const TileMap& tm, const uint32_t* l2g, const ::uint2* xy, uint32_t count, ::float4* out, cudaStream_t st);
@@ -109,6 +110,9 @@ struct vkrt_cuda_ctx {
     DevBuf<MeshTrig> meshTrig;
     DevBuf<Material> materials;
     DevBuf<EmissiveMesh> emissiveMeshes;
+    DevBuf<SpectralMemoEntry> materialMemo, emissiveMemo;   // memoised rgb2spec lookups of material / light constants (k_spectral_memo)
+    bool memoDisabled = false;                                // VKRT_NO_SPECTRAL_MEMO=1: every lookup goes to the table (A/B and the bit-identity test)
+    bool memoDirty = true;                                    // materials, lights or the rgb2spec table changed since the memo was filled
     DevBuf<EmissiveTriangle> emissiveTriangles;
     DevBuf<float> meshAliasQ, triAliasQ, rgb2spec, srgbLut, world3x4;
     DevBuf<::float4> rgb2specCells;   // the coefficient cells of rgb2spec re-packed as float4 (shading.cuh SpectralTables)
@@ -138,6 +142,7 @@ struct vkrt_cuda_ctx {
     DevBuf<uint32_t> instanceBlas;
     uint32_t tlasRoot = 0;
     bool accelValid = false;
+    uint32_t traceRefill = 0;       // VKRT_TRACE_REFILL (tuning override of AccelView::refillLanes; 0 = automatic)
     bool anyTransmissive = false;   // some instance record carries INSTANCE_FLAG_TRANSMISSIVE (set by build_accel)
     vkrt_cuda_build_stats buildStats = {};
 
@@ -253,6 +258,10 @@ SceneView makeSceneView(vkrt_cuda_ctx* c) {
     v.spectral.table = c->rgb2spec.p;
     v.spectral.cells = c->rgb2specCells.p;
     v.spectral.scale = c->rgb2spec.p + c->rgb2specInfo.scaleOffset;
+    if (!c->memoDirty && !c->memoDisabled) {
+        v.spectral.materialMemo = c->materialMemo.p;
+        v.spectral.emissiveMemo = c->emissiveMemo.p;
+    }
     v.accel.nodes = c->nodes.p;
     v.accel.triangles = c->accelFlat ? c->flatTriangles.p : c->triangles.p;
     v.accel.instances = c->instancesLeafOrder.p;
@@ -262,6 +271,10 @@ SceneView makeSceneView(vkrt_cuda_ctx* c) {
     v.accel.flat = c->accelFlat ? 1u : 0u;
     v.env = {};
     v.accel.stackNeed = (c->flags & VKRT_CUDA_FLAG_DEEP_STACK) ? (uint32_t)TRACE_STACK_DEEP : c->stackNeed;
+    // Refill threshold (measured, profiles/r02_notes.md): long traversals of a big single-level tree amortise a refill over many trips and
+    // want the warp full (24); short ones (a few nodes per ray) pay for every refill and do better at 20, like the two-level walk.
+    v.accel.refillLanes = c->traceRefill ? c->traceRefill
+                                         : ((c->accelFlat && c->buildStats.instancedTriangleCount >= TRACE_REFILL_BIG_SCENE) ? TRACE_REFILL_FLAT : TRACE_REFILL);
     return v;
 }
 
@@ -433,6 +446,14 @@ VKRT_Result enqueueFrame(vkrt_cuda_ctx* ctx, const SceneData* sceneData, uint32_
     SceneData sd = *sceneData;
     const int mode = renderModeOf(sd);
     if (mode != 0 && !ctx->haveRgb2spec) return fail(ctx, VKRT_ERROR_OPERATION_FAILED, "spectral rendering needs vkrt_cuda_set_rgb2spec");
+    if (mode != 0 && ctx->memoDirty) {   // spectral memo of the material / light constants (k_spectral_memo), refreshed after a scene edit
+        const uint32_t nm = (uint32_t)ctx->hostMaterials.size(), ne = ctx->lightMeshCount;
+        CU(ctx->materialMemo.alloc((size_t)std::max(nm, 1u) * SPECTRAL_MEMO_SLOTS));
+        CU(ctx->emissiveMemo.alloc(std::max(ne, 1u)));
+        launchSpectralMemo(makeSceneView(ctx), nm, ne, ctx->materialMemo.p, ctx->emissiveMemo.p, ctx->stream);
+        CU(cudaGetLastError());
+        ctx->memoDirty = false;
+    }
     if (sd.rrMaxDepth > 64u) sd.rrMaxDepth = 64u;
     if (sd.emissiveMeshCount > ctx->lightMeshCount) return fail(ctx, VKRT_ERROR_INVALID_ARGUMENT, "render_frame: SceneData names %u emissive meshes, %u uploaded", sd.emissiveMeshCount, ctx->lightMeshCount);
     const uint32_t spp = std::max(sd.samplesPerPixel, 1u);
@@ -549,6 +570,8 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_create(const vkrt_cuda_create_info* info, vk
     }
     cudaDeviceGetAttribute(&ctx->smCount, cudaDevAttrMultiProcessorCount, dev);
     ctx->traceGrid = ctx->smCount * traceBlocksPerSm((ctx->flags & VKRT_CUDA_FLAG_COUNT_RAYS) != 0);
+    if (const char* m = getenv("VKRT_NO_SPECTRAL_MEMO")) ctx->memoDisabled = atoi(m) != 0;
+    if (const char* r = getenv("VKRT_TRACE_REFILL")) ctx->traceRefill = (uint32_t)std::min(std::max(atoi(r), 0), 32);   // tuning knob (tests/perf_probe.py sweeps)
     for (int m = 0; m < 3; m++) ctx->shadeGrid[m] = ctx->smCount * shadeBlocksPerSm(m);
     // sRGB decode table (256 entries), same formula as the oracle
     float lut[256];
@@ -638,6 +661,7 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_set_materials(vkrt_cuda_ctx* ctx, const Mate
     bool same = ctx->accelValid && ctx->hostMaterials.size() == materialCount;
     for (uint32_t i = 0; same && i < materialCount; i++) same = (ctx->hostMaterials[i].transmission > 0.0f) == (materials[i].transmission > 0.0f);
     ctx->hostMaterials.assign(materials, materials + materialCount);
+    ctx->memoDirty = true;
     CU(ctx->materials.upload(materials, materialCount, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     if (!same) ctx->accelValid = false;
@@ -660,6 +684,7 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_set_lights(vkrt_cuda_ctx* ctx, const Emissiv
     }
     cudaSetDevice(ctx->device);
     ctx->lightMeshCount = meshCount;
+    ctx->memoDirty = true;
     CU(ctx->emissiveMeshes.upload(meshes, meshCount, ctx->stream));
     CU(ctx->emissiveTriangles.upload(triangles, triangleCount, ctx->stream));
     CU(ctx->meshAliasQ.upload(meshAliasQ, meshCount, ctx->stream));
@@ -710,6 +735,7 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_set_rgb2spec(vkrt_cuda_ctx* ctx, const float
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->rgb2specInfo = info;
     ctx->haveRgb2spec = true;
+    ctx->memoDirty = true;
     return VKRT_SUCCESS;
 }
 

@@ -570,7 +570,10 @@ __global__ void k_refit(uint32_t n, ::float4* nodeLo, ::float4* nodeHi, const ui
 // (k_ploc_apply); the last <= PLOC_TAIL clusters are finished by one block in shared memory (k_ploc_tail).
 // Node numbering as k_hierarchy's: leaves at (n-1)+k, internal nodes 0..n-2 with the ROOT AT 0 (ids are handed out from n-2 downwards,
 // and a binary tree over n leaves has exactly n-1 merges).
-constexpr int PLOC_RADIUS = 10;
+#ifndef VKRT_PLOC_RADIUS
+#define VKRT_PLOC_RADIUS 10
+#endif
+constexpr int PLOC_RADIUS = VKRT_PLOC_RADIUS;
 constexpr int PLOC_THREADS = 256;
 constexpr int PLOC_TAIL = 512;
 

@@ -139,11 +139,21 @@ VK_D float linearSrgbLuminance(float3 rgb) { return dot(rgb, float3(0.2126f, 0.7
 // Device layout of the coefficient table (written once by vkrt_cuda_set_rgb2spec, k_pack_rgb2spec): `cells` holds one float4 per
 // grid cell {c0, c1, c2, 0} in the payload's cell order, so the 8 corners of a lookup are 8 aligned 128-bit loads (two neighbours along
 // x share a 32-byte sector) instead of 24 scalar loads; `scale` is the res-entry scale axis, which k_shade stages in shared memory.
+struct SpectralMemoEntry {
+    ::float4 key;     // xyz = the linear sRGB colour the value was computed for
+    ::float4 value;   // {c0, c1, c2} of rgb / scale, w = scale (spectralScalarFromLinearSrgb4), 0 when the colour is black
+};
+enum : uint { SPECTRAL_MEMO_DIFFUSE = 0u, SPECTRAL_MEMO_EMISSION = 1u, SPECTRAL_MEMO_SLOTS = 2u };
 struct SpectralTables {
     RGB2SpecTableInfo info = {0, 0, 0};
     const float* table = nullptr;      // the payload as uploaded (rgb2spec.c:17-59)
     const ::float4* cells = nullptr;   // 3 * res^3 packed coefficient cells
     const float* scale = nullptr;      // table + scaleOffset, or its shared-memory copy
+    // Memoised upsamplings (k_spectral_memo): colours that are constants of a material or of a light are looked up in the table once per
+    // scene edit, not once per path vertex. An entry is used only when its key equals the colour at hand bit for bit, so a texture or a
+    // vertex colour that changes the colour simply misses; nullptr = no memo (closure test entry, RGB frames).
+    const SpectralMemoEntry* materialMemo = nullptr;   // SPECTRAL_MEMO_SLOTS entries per material
+    const SpectralMemoEntry* emissiveMemo = nullptr;   // one entry per emissive mesh (EmissiveMesh::emission)
 };
 static constexpr float RGB2SPEC_EPSILON = 1e-8f;
 static constexpr uint RGB2SPEC_SMEM_RES = 64u;
@@ -239,6 +249,36 @@ VK_D float4 spectralScalarFromLinearSrgb4(const SpectralTables& t, float3 rgb, f
     float3 coeff = rgb2specFetch(t, rgb / scale);
     return scale * float4(rgb2specEvalCoeffs(coeff, lambdaNm.x), rgb2specEvalCoeffs(coeff, lambdaNm.y),
                           rgb2specEvalCoeffs(coeff, lambdaNm.z), rgb2specEvalCoeffs(coeff, lambdaNm.w));
+}
+// The coefficient fetch of spectralScalarFromLinearSrgb4 on its own (memo producer), and the two consumers: same arithmetic, same order.
+VK_D ::float4 spectralCoefficientsFromLinearSrgb(const SpectralTables& t, float3 rgb) {
+    float maxValue = max(rgb.x, max(rgb.y, rgb.z));
+    if (maxValue <= 0.0f) return make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    float scale = maxValue <= 1.0f ? 1.0f : maxValue;
+    float3 coeff = rgb2specFetch(t, rgb / scale);
+    return make_float4(coeff.x, coeff.y, coeff.z, scale);
+}
+VK_D bool spectralMemoHit(const SpectralMemoEntry* e, float3 rgb, ::float4& value) {
+    if (!e) return false;
+    const ::float4 k = __ldg(&e->key);
+    if (__float_as_uint(k.x) != __float_as_uint(rgb.x) || __float_as_uint(k.y) != __float_as_uint(rgb.y) || __float_as_uint(k.z) != __float_as_uint(rgb.z)) return false;
+    value = __ldg(&e->value);
+    return true;
+}
+VK_D float4 spectralScalarFromLinearSrgb4(const SpectralTables& t, const SpectralMemoEntry* memo, float3 rgb, float4 lambdaNm) {
+    ::float4 v;
+    if (!spectralMemoHit(memo, rgb, v)) return spectralScalarFromLinearSrgb4(t, rgb, lambdaNm);
+    if (v.w <= 0.0f) return float4(0.0f);
+    const float3 coeff(v.x, v.y, v.z);
+    return v.w * float4(rgb2specEvalCoeffs(coeff, lambdaNm.x), rgb2specEvalCoeffs(coeff, lambdaNm.y),
+                        rgb2specEvalCoeffs(coeff, lambdaNm.z), rgb2specEvalCoeffs(coeff, lambdaNm.w));
+}
+VK_D float spectralScalarFromLinearSrgb(const SpectralTables& t, const SpectralMemoEntry* memo, float3 rgb, float lambdaNm) {
+    ::float4 v;
+    if (!spectralMemoHit(memo, rgb, v)) return spectralScalarFromLinearSrgb(t, rgb, lambdaNm);
+    if (v.w <= 0.0f) return 0.0f;
+    const float e = rgb2specEvalCoeffs(float3(v.x, v.y, v.z), lambdaNm);
+    return v.w <= 1.0f ? e : v.w * e;
 }
 VK_D float spectralXFit1931(float l) {
     float t1 = (l - 442.0f) * (l < 442.0f ? 0.0624f : 0.0374f);
@@ -1173,6 +1213,7 @@ struct BSDFState {
     // kernel's local frame; each lookup is ~100 instructions and 8 gathered 128-bit loads).
     mutable float cachedDiffuse4[4], cachedVd4[4];   // plain floats (no alignment demands on the state record, which k_shade keeps in shared memory)
     mutable uint cachedMask = 0u;   // bit 0: cachedDiffuse4 valid, bit 1: cachedVd4 valid
+    uint memoIndex = 0xffffffffu;   // first SpectralTables::materialMemo entry of this vertex's material (k_shade), or none
     __device__ BSDFState() {}
     __device__ BSDFState(const BSDFMaterial& m, float3 wo_, uint ff, float wl, uint sm)
         : material(m), wo(wo_), frontFace(ff), wavelengthNm(wl), spectralMode(sm) {
@@ -1181,6 +1222,9 @@ struct BSDFState {
         sampleWeights = makeBSDFBranchWeights(m, wo_, ff);
     }
 };
+VK_D const SpectralMemoEntry* spectralMemoOf(const SpectralTables& t, const BSDFState& s, uint slot) {
+    return (t.materialMemo && s.memoIndex != 0xffffffffu) ? t.materialMemo + (s.memoIndex + slot) : nullptr;
+}
 VK_D bool useInteriorDielectricInterface(const BSDFState& s) { return s.material.transmission > 0.0f && s.frontFace == 0u; }
 
 // ---- bsdf/principled/eval_rgb.slang:4-140 -------------------------------------------------------------------------
@@ -1216,7 +1260,7 @@ VK_D BSDFEval evalScalarReflectionStack(const SpectralTables& t, const BSDFState
     }
     if (s.sampleWeights.diffuse > 0.0f || s.sampleWeights.subsurface > 0.0f) {
         float3 diffuseColor = bsdfDiffuseColor(m);
-        if (spectralMode != 0u) diffuseColor = float3(spectralScalarFromLinearSrgb(t, saturate(diffuseColor), s.wavelengthNm));
+        if (spectralMode != 0u) diffuseColor = float3(spectralScalarFromLinearSrgb(t, spectralMemoOf(t, s, SPECTRAL_MEMO_DIFFUSE), saturate(diffuseColor), s.wavelengthNm));
         if (s.sampleWeights.diffuse > 0.0f) {
             float3 dw = diffuseColor * ((1.0f - m.transmission) * (1.0f - m.subsurface));
             BSDFEval d = m.diffuseRoughness <= 0.0f ? evalLambertian(dw, wi) : evalOrenNayar(dw, m.diffuseRoughness, s.wo, wi);
@@ -1287,7 +1331,7 @@ VK_D float4 evalSpectralReflectionStack(const SpectralTables& t, const BSDFState
     }
     if (s.sampleWeights.diffuse > 0.0f || s.sampleWeights.subsurface > 0.0f) {
         if (!(s.cachedMask & 1u)) {
-            const float4 c = spectralScalarFromLinearSrgb4(t, saturate(bsdfDiffuseColor(m)), wl);
+            const float4 c = spectralScalarFromLinearSrgb4(t, spectralMemoOf(t, s, SPECTRAL_MEMO_DIFFUSE), saturate(bsdfDiffuseColor(m)), wl);
             s.cachedDiffuse4[0] = c.x; s.cachedDiffuse4[1] = c.y; s.cachedDiffuse4[2] = c.z; s.cachedDiffuse4[3] = c.w;
             s.cachedMask |= 1u;
         }

@@ -8,7 +8,7 @@
 //   * one launch processes one bounce's extension-ray queue AND the previous shade's shadow-ray queue as a single work
 //     list; rays are read/written as 16-byte SoA vectors (coalesced: lane i <-> ray base+i);
 //   * persistent warps (grid = k * 148 SMs) pull rays with a warp-aggregated atomic; a warp refills its idle lanes as soon
-//     as fewer than TRACE_REFILL (two-level) or TRACE_REFILL_FLAT lanes are still traversing (Aila & Laine 2009 dynamic fetch), so a long ray does
+//     as fewer than AccelView::refillLanes lanes (20 or 24, chosen per scene) are still traversing (Aila & Laine 2009 dynamic fetch), so a long ray does
 //     not hold 31 idle lanes hostage;
 //   * traversal stack: uint2 entries (node group / primitive group, Ylitie et al. 2017) in per-thread local memory (L1);
 //   * 80-byte nodes are fetched as five 128-bit loads, triangles as three; everything read-only goes through LDG.
@@ -25,8 +25,11 @@ constexpr int TRACE_BLOCK = 128;
 #define TRACE_REFILL 20        // two-level kernel; measured 16 / 20 / 24 / 28 lanes: cornell 33.1 / 33.2 / 34.8 / 39.0 ms
 #endif
 #ifndef TRACE_REFILL_FLAT
-#define TRACE_REFILL_FLAT 24   // single-level kernel (long, uniform traversals): 10 M-triangle soup 25.1 / 24.7 / 24.3 / 24.8 ms
+#define TRACE_REFILL_FLAT 24   // single-level BVH over TRACE_REFILL_BIG_SCENE triangles or more. Measured at 20 / 24 lanes (profiles/r02k_sweeps.txt): soup of 1 M / 3 M /
+                               // 10 M triangles 30.2 / 29.6, 18.5 / 18.2, 20.2 / 19.9 ms; 1000 spheres (0.6 M) 34.3 / 34.0 ms; but the flat cornell box (70 k
+                               // triangles, 6 node visits per ray: a refill is a large share of such a short walk) 28.3 / 29.4 ms -> 20 for small scenes
 #endif
+constexpr unsigned long long TRACE_REFILL_BIG_SCENE = 262144ull;
 #ifndef TRACE_PRIM_VOTE
 #define TRACE_PRIM_VOTE 8   // lanes with a pending primitive wait until 8 of them can run the primitive section together (0 = every trip)
 #endif
@@ -412,7 +415,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS) k_trace(const T
                 }
                 G = stack[--sp];
             }
-            if (!exhausted && __popc(__activemask()) < (FLAT ? TRACE_REFILL_FLAT : TRACE_REFILL)) break;
+            if (!exhausted && __popc(__activemask()) < (int)A.refillLanes) break;
         }
     }
     if (COUNT && P.stats) {

@@ -178,16 +178,8 @@ __device__ __forceinline__ SurfaceShadingData reconstructSurfaceShading(const Sc
 }
 
 // material/textures.slang:123-155
-__device__ __forceinline__ void applySurfaceTextures(const SceneView& sc, Material& m, const SurfaceTextureData& s) {
-    float4 bc = sampleBaseColorTexture(sc, m, s);
-    m.baseColor[0] *= bc.x * s.color.x;
-    m.baseColor[1] *= bc.y * s.color.y;
-    m.baseColor[2] *= bc.z * s.color.z;
-    float4 mr = sampleMetallicRoughnessTexture(sc, m, s);
-    m.roughness = saturate(m.roughness * mr.y);
-    m.metallic = saturate(m.metallic * mr.z);
-    float4 et = sampleEmissiveTexture(sc, m, s);
-    float3 emission = float3(m.emissionColor[0], m.emissionColor[1], m.emissionColor[2]) * m.emissionLuminance * et.xyz();
+__device__ __forceinline__ void normalizeEmission(Material& m, float3 emissiveTexel) {
+    float3 emission = float3(m.emissionColor[0], m.emissionColor[1], m.emissionColor[2]) * m.emissionLuminance * emissiveTexel;
     float emissionMax = maxComponent(emission);
     if (emissionMax > 0.0f) {
         float3 ec = emission / emissionMax;
@@ -197,6 +189,17 @@ __device__ __forceinline__ void applySurfaceTextures(const SceneView& sc, Materi
         m.emissionColor[0] = m.emissionColor[1] = m.emissionColor[2] = 1.0f;
         m.emissionLuminance = 0.0f;
     }
+}
+__device__ __forceinline__ void applySurfaceTextures(const SceneView& sc, Material& m, const SurfaceTextureData& s) {
+    float4 bc = sampleBaseColorTexture(sc, m, s);
+    m.baseColor[0] *= bc.x * s.color.x;
+    m.baseColor[1] *= bc.y * s.color.y;
+    m.baseColor[2] *= bc.z * s.color.z;
+    float4 mr = sampleMetallicRoughnessTexture(sc, m, s);
+    m.roughness = saturate(m.roughness * mr.y);
+    m.metallic = saturate(m.metallic * mr.z);
+    float4 et = sampleEmissiveTexture(sc, m, s);
+    normalizeEmission(m, et.xyz());
 }
 __device__ __forceinline__ float3 applyNormalTexture(const SceneView& sc, const Material& m, const SurfaceTextureData& s, const ShadingBasis& basis) {
     if (m.normalTextureIndex == VKRT_INVALID_INDEX) return basis.normal;
@@ -241,6 +244,7 @@ __device__ __forceinline__ float3 sampleEnvironmentRadiance(const SceneView& sc,
 struct DirectLightSurfaceSample {
     float3 emission, wi;
     float shadowDistance, pdfSolidAngle;
+    uint emissiveMesh;   // index of the sampled emissive mesh (its emission has a spectral memo entry), 0xffffffff for the environment
     bool valid;
 };
 
@@ -264,6 +268,7 @@ static __device__ __noinline__ DirectLightSurfaceSample sampleEnvironmentLight(c
     DirectLightSurfaceSample s;
     s.valid = false;
     s.shadowDistance = s.pdfSolidAngle = 0.0f;
+    s.emissiveMesh = 0xffffffffu;
     const uint32_t n = E.width * E.height;
     const uint64_t hi = (uint64_t)(rand(rng) * 16777216.0f), lo = (uint64_t)(rand(rng) * 16777216.0f);
     // 48 random bits x n needs a 128-bit product: in 64 bits it wraps as soon as n > 65536 texels, and every map larger than 256 x 256
@@ -290,9 +295,11 @@ __device__ __forceinline__ DirectLightSurfaceSample sampleDirectLightSurface(con
     DirectLightSurfaceSample s;
     s.valid = false;
     s.shadowDistance = s.pdfSolidAngle = 0.0f;
+    s.emissiveMesh = 0xffffffffu;
     const uint meshCount = scene.emissiveMeshCount;
     if (meshCount == 0u) return s;
     const uint meshIdx = sampleAlias(rand(rng), meshCount, 0u, sc.meshAliasQ, sc.meshAliasIdx);
+    s.emissiveMesh = meshIdx;
     const EmissiveMesh em = sc.emissiveMeshes[meshIdx];
     if (em.triCount == 0u) return s;
     const uint localTri = sampleAlias(rand(rng), em.triCount, em.triOffset, sc.triAliasQ, sc.triAliasIdx);
@@ -382,6 +389,7 @@ static_assert(alignof(ShadeScratch) <= 8, "ShadeScratch must not need more than 
 constexpr size_t SHADE_SCRATCH_STRIDE = (((sizeof(ShadeScratch) + 7) / 8) | 1) * 8;   // an odd number of 8-byte units: 2-way conflicts at worst
 #endif
 constexpr size_t SHADE_DYNAMIC_SMEM = SHADE_SCRATCH_STRIDE * SHADE_BLOCK;
+static_assert((SHADE_DYNAMIC_SMEM + 1024 + 256 + 64) * SHADE_MIN_BLOCKS <= 228 * 1024, "the per-vertex records of SHADE_MIN_BLOCKS blocks must fit the SM's shared memory (228 KB, 1 KB reserved per block)");
 template <int MODE, bool ENVIS>
 __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ FrameParams fp, const uint32_t depth) {
     const uint32_t count = fp.extCount[depth];
@@ -579,6 +587,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const _
             }
             const float stateWavelength = MODE == MODE_RGB ? 0.0f : lambdaScalar;
             state = BSDFState(bm, worldToLocal(-ray.direction, basis), surface.frontFace, stateWavelength, MODE == MODE_RGB ? 0u : 1u);
+            if (MODE != MODE_RGB) state.memoIndex = surface.materialIndex * SPECTRAL_MEMO_SLOTS;
             currentVertexNeeAllowed = !medium.refractiveActive();
           }
         }
@@ -614,6 +623,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const _
                 const float3 wiLocal = worldToLocal(ls.wi, basis);
                 // common.slang:47-50 rejects the sample after the visibility test; evaluating it first is equivalent for the radiance.
                 float4 c(0.0f);
+                const SpectralMemoEntry* lightMemo = (MODE != MODE_RGB && T.emissiveMemo && ls.emissiveMesh != 0xffffffffu) ? T.emissiveMemo + ls.emissiveMesh : nullptr;
                 const bool refractiveReject = materialMediumIsRefractive(state.material) && cosTheta(wiLocal) <= 0.0f;
                 if (!refractiveReject) {
                     if (MODE == MODE_RGB) {
@@ -631,12 +641,12 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const _
                         const float misWeight = computeSpectralMISWeight(techPdf * ls.pdfSolidAngle, techPdf * localTp);
                         if (misWeight > 0.0f) {
                             c = thr4 * (misWeight * mediumSpectralTransmittance(medium, ls.shadowDistance) * fCos *
-                                        spectralScalarFromLinearSrgb4(T, ls.emission, wl4) / ls.pdfSolidAngle);
+                                        spectralScalarFromLinearSrgb4(T, lightMemo, ls.emission, wl4) / ls.pdfSolidAngle);
                         }
                     } else {
                         const BSDFEval e = evalSingleWavelengthBSDF(T, state, wiLocal);
                         if (e.pdf > 0.0f) {
-                            const float sv = e.value.x * absCosTheta(wiLocal) * spectralScalarFromLinearSrgb(T, ls.emission, lambdaScalar);
+                            const float sv = e.value.x * absCosTheta(wiLocal) * spectralScalarFromLinearSrgb(T, lightMemo, ls.emission, lambdaScalar);
                             const float misWeight = powerHeuristic(ls.pdfSolidAngle, e.pdf);
                             c.x = thrScalar * (misWeight * mediumTransmittance(medium, ls.shadowDistance).x * sv / ls.pdfSolidAngle);
                             shadowScalarLane = MODE == MODE_HERO;
@@ -671,7 +681,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const _
                             const float4 pv = fromF4(S.prevVertexTechPdf[i]), pb = fromF4(S.prevBsdfTechPdf[i]);
                             misWeight = computeSpectralMISWeight(pv * pb, pv * lp2);
                         }
-                        const float4 c = thr4 * (spectralScalarFromLinearSrgb4(T, emission, wl4) * misWeight);
+                        const float4 c = thr4 * (spectralScalarFromLinearSrgb4(T, spectralMemoOf(T, state, SPECTRAL_MEMO_EMISSION), emission, wl4) * misWeight);
                         ::float4 r = fp.rec.radiance[rec];
                         r.x += c.x; r.y += c.y; r.z += c.z; r.w += c.w;
                         fp.rec.radiance[rec] = r;
@@ -687,7 +697,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const _
                             r.x += c.x; r.y += c.y; r.z += c.z;
                             fp.rec.radiance[rec] = r;
                         } else {
-                            const float c = thrScalar * (spectralScalarFromLinearSrgb(T, emission, lambdaScalar) * misWeight);
+                            const float c = thrScalar * (spectralScalarFromLinearSrgb(T, spectralMemoOf(T, state, SPECTRAL_MEMO_EMISSION), emission, lambdaScalar) * misWeight);
                             if (MODE == MODE_SINGLE) fp.rec.radiance[rec].x += c;
                             else fp.rec.radianceScalar[rec] += c;
                         }
@@ -1172,6 +1182,35 @@ __global__ void __launch_bounds__(128) k_mesh_trig(const MeshInfo* __restrict__ 
     out[i] = makeMeshTrig(float3(infos[i].rotation[0], infos[i].rotation[1], infos[i].rotation[2]));
 }
 // rgb2spec payload -> float4 cells (shading.cuh SpectralTables)
+// Spectral memo (shading.cuh, SpectralMemoEntry): the table lookups of the colours that are constants of a material (diffuse colour, emission;
+// both as k_shade derives them when no texture or vertex colour intervenes) and of an emissive mesh. Same device functions, same arithmetic
+// as the per-vertex path; an entry whose key does not match at run time is simply not used.
+__global__ void __launch_bounds__(128) k_spectral_memo(const SceneView sc, uint32_t materialCount, uint32_t emissiveMeshCount, SpectralMemoEntry* __restrict__ materialMemo,
+                                                       SpectralMemoEntry* __restrict__ emissiveMemo) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const SpectralTables& T = sc.spectral;
+    if (i < materialCount) {
+        Material m = loadMaterial(sc.materials + i);
+        m.roughness = saturate(m.roughness * 1.0f);   // applySurfaceTextures with unit texels and unit vertex colour
+        m.metallic = saturate(m.metallic * 1.0f);
+        normalizeEmission(m, float3(1.0f));
+        const float3 emission = float3(m.emissionColor[0], m.emissionColor[1], m.emissionColor[2]) * m.emissionLuminance;
+        const BSDFMaterial bm(m);
+        const float3 diffuse = saturate(bsdfDiffuseColor(bm));
+        materialMemo[i * SPECTRAL_MEMO_SLOTS + SPECTRAL_MEMO_DIFFUSE] = {make_float4(diffuse.x, diffuse.y, diffuse.z, 0.0f), spectralCoefficientsFromLinearSrgb(T, diffuse)};
+        materialMemo[i * SPECTRAL_MEMO_SLOTS + SPECTRAL_MEMO_EMISSION] = {make_float4(emission.x, emission.y, emission.z, 0.0f), spectralCoefficientsFromLinearSrgb(T, emission)};
+    } else if (i - materialCount < emissiveMeshCount) {
+        const uint32_t k = i - materialCount;
+        const EmissiveMesh em = sc.emissiveMeshes[k];
+        const float3 emission(em.emission[0], em.emission[1], em.emission[2]);
+        emissiveMemo[k] = {make_float4(emission.x, emission.y, emission.z, 0.0f), spectralCoefficientsFromLinearSrgb(T, emission)};
+    }
+}
+void launchSpectralMemo(const SceneView& sc, uint32_t materialCount, uint32_t emissiveMeshCount, SpectralMemoEntry* materialMemo, SpectralMemoEntry* emissiveMemo, cudaStream_t st) {
+    const uint32_t n = materialCount + emissiveMeshCount;
+    if (n) k_spectral_memo<<<(n + 127) / 128, 128, 0, st>>>(sc, materialCount, emissiveMeshCount, materialMemo, emissiveMemo);
+}
+
 __global__ void __launch_bounds__(256) k_pack_rgb2spec(const float* __restrict__ table, uint32_t dataOffset, size_t cellCount, ::float4* __restrict__ cells) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cellCount; i += (size_t)gridDim.x * blockDim.x) {
         const float* c = table + dataOffset + 3u * i;
