@@ -174,20 +174,22 @@ def textured(w, h, spp=2, cutout=True):
     return prep
 
 
-def sunlit(w, h, spp=16, lamp=False, balls=True):
+def sunlit(w, h, spp=16, lamp=False, balls=True, env_scale=1):
     """A matte floor, a matte ball and a glossy ball under a lat-long RGBA32F environment whose energy sits in a small, very bright
     sun (16 of 2048 texels): the case environment-map importance sampling exists for. `lamp` adds an emissive quad, so that the one
     light sample per vertex has to be split between the environment and the emissive triangles. Roughness stays <= 0.5: the reference
     draws GGX normals with the bounded-VNDF sampler (ggx.slang:180) but reports the unbounded VNDF density (ggx.slang:88-99), so for
     alpha -> 1 a BSDF-sampled estimate sits 1 - 2.6 % above the quadrature of its own eval (measured on the oracle), and an estimator
     that moves weight from BSDF sampling to light sampling inherits that offset. Below alpha = 0.25 the two agree to 0.05 %."""
-    env = np.ones((32, 64, 4), np.float32)
-    tt = (np.arange(32) + 0.5) / 32 * np.pi
+    k = int(env_scale)   # env_scale = 16: the same sky on a 1024 x 512 map (524 288 texels, the sun at texel indices >= 98 304)
+    eh, ew = 32 * k, 64 * k
+    env = np.ones((eh, ew, 4), np.float32)
+    tt = (np.arange(eh) + 0.5) / eh * np.pi
     env[..., 0] = 0.05 + 0.05 * np.clip(np.cos(tt), 0, 1)[:, None]
     env[..., 1] = 0.07 + 0.06 * np.clip(np.cos(tt), 0, 1)[:, None]
     env[..., 2] = 0.10 + 0.10 * np.clip(np.cos(tt), 0, 1)[:, None]
-    env[6:10, 20:24, :3] = (260.0, 230.0, 180.0)
-    textures = [dict(pixels=env, width=64, height=32, format=3, colorSpace=1)]
+    env[6 * k:10 * k, 20 * k:24 * k, :3] = (260.0, 230.0, 180.0)
+    textures = [dict(pixels=env, width=ew, height=eh, format=3, colorSpace=1)]
     mats = np.zeros(5, hr.MATERIAL)
     mats[:] = hr.default_material()
     for k, (col, rough, metal) in enumerate([((0.7, 0.7, 0.7), 0.5, 0.0), ((0.8, 0.3, 0.2), 0.45, 0.0), ((0.9, 0.8, 0.5), 0.25, 1.0)]):

@@ -419,6 +419,33 @@ def test_environment_importance_sampling_extension(mode, lamp):
     assert err_is < 0.5 * err_default, (err_is, err_default)
 
 
+def test_environment_importance_sampling_on_a_large_map():
+    """A 1024 x 512 environment (524 288 texels) whose sun sits at texel indices >= 98 304: the texel draw multiplies 48 random bits by the
+    texel count, which needs the high half of a 128-bit product - in 64 bits it wraps for every map above 65 536 texels and the draw never
+    leaves the first 65 536 (the sun would be reached through alias links only, against a density that assumes the full table: a dark,
+    biased image). Same expectation as the default estimator, and the variance gain must survive the larger table."""
+    w, h = 96, 64
+    prep = scenes.sunlit(w, h, spp=64, env_scale=16)
+
+    def render(flags, frames):
+        g = H.CudaBackend(flags=flags)
+        g.upload(prep)
+        g.resize(w, h)
+        g.render(prep["sceneData"], frames=frames)
+        img = g.read(H.AOV_ACCUM)[..., :3].astype(np.float64)
+        g.close()
+        return img
+
+    long_default, short_default = render(0, 48), render(0, 1)
+    long_is, short_is = render(64, 4), render(64, 1)
+    assert np.isfinite(long_is).all()
+    ma, mb = long_default.mean(axis=(0, 1)), long_is.mean(axis=(0, 1))
+    assert np.all(np.abs(ma - mb) <= 0.015 * ma), (ma, mb)
+    err_default = np.sqrt(((short_default - long_default) ** 2).mean())
+    err_is = np.sqrt(((short_is - long_default) ** 2).mean())
+    assert err_is < 0.5 * err_default, (err_is, err_default)
+
+
 def test_environment_importance_flag_is_inert_without_environment_texture():
     w, h = 96, 64
     prep = scenes.cornell(w, h, spp=4)

@@ -175,18 +175,6 @@ __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS) k_trace(const T
                 base = __shfl_sync(0xffffffffu, base, leader);
                 if (!R.active) {
                     const uint32_t idx = base + __popc(idle & ((1u << lane) - 1u));
-#ifdef TRACE_PREFETCH_AHEAD
-                    {   // the ray some warp will fetch TRACE_PREFETCH_AHEAD work items from now (about what the grid holds in flight): into L2 now
-                        const uint32_t pidx = idx + (uint32_t)TRACE_PREFETCH_AHEAD;
-                        if (pidx < extCount) {
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(P.rayO + pidx));
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(P.rayD + pidx));
-                        } else if (pidx < total) {
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(P.shO + (pidx - extCount)));
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(P.shD + (pidx - extCount)));
-                        }
-                    }
-#endif
                     if (idx < total) {
                         R.anyHit = idx >= extCount;
                         R.index = idx;
