@@ -30,9 +30,6 @@ constexpr int TRACE_BLOCK = 128;
                                // triangles, 6 node visits per ray: a refill is a large share of such a short walk) 28.3 / 29.4 ms -> 20 for small scenes
 #endif
 constexpr unsigned long long TRACE_REFILL_BIG_SCENE = 262144ull;
-#ifndef TRACE_CHUNK
-#define TRACE_CHUNK 0
-#endif
 #ifndef TRACE_PRIM_VOTE
 #define TRACE_PRIM_VOTE 8   // lanes with a pending primitive wait until 8 of them can run the primitive section together (0 = every trip)
 #endif
@@ -163,9 +160,6 @@ __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS) k_trace(const T
     float3 objO(0.0f);  // flat variant: ray origin in the cached instance's object space
     uint2 G = make_uint2(0u, 0u), Gt = make_uint2(0u, 0u);  // pending node group / pending primitive group of this lane
     bool exhausted = false;
-#if TRACE_CHUNK > 0
-    uint32_t resNext = 0u, resEnd = 0u;   // warp-uniform: the warp's reserved slice [resNext, resEnd) of the work list
-#endif
     uint32_t one;  // 1.0f as an opaque register value (byteToUnitFloat)
     asm volatile("mov.b32 %0, 0x3F800000;" : "=r"(one));
     unsigned long long nNodes = 0, nTris = 0, nInst = 0;
@@ -175,31 +169,12 @@ __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS) k_trace(const T
         if (!exhausted) {
             const unsigned idle = __ballot_sync(0xffffffffu, !R.active);
             if (idle) {
-#if TRACE_CHUNK > 0
-                // The warp reserves TRACE_CHUNK work items at a time and hands them to its idle lanes from that slice: one atomic on the
-                // launch's single work counter per TRACE_CHUNK rays instead of one per refill (~10 rays).
-                const uint32_t need = (uint32_t)__popc(idle), avail = resEnd - resNext;
-                uint32_t fresh = 0;
-                if (avail < need) {
-                    const int leader = __ffs(idle) - 1;
-                    if (lane == leader) fresh = atomicAdd(P.workCounter, (uint32_t)TRACE_CHUNK);
-                    fresh = __shfl_sync(0xffffffffu, fresh, leader);
-                }
-                const uint32_t rank = __popc(idle & ((1u << lane) - 1u));
-                const uint32_t myIdx = rank < avail ? resNext + rank : fresh + (rank - avail);
-                if (avail < need) { resNext = fresh + (need - avail); resEnd = fresh + (uint32_t)TRACE_CHUNK; }
-                else resNext += need;
-                const uint32_t base = resNext - need;   // (only its comparison with `total` below is used)
-                if (!R.active) {
-                    const uint32_t idx = myIdx;
-#else
                 uint32_t base = 0;
                 const int leader = __ffs(idle) - 1;
                 if (lane == leader) base = atomicAdd(P.workCounter, (uint32_t)__popc(idle));
                 base = __shfl_sync(0xffffffffu, base, leader);
                 if (!R.active) {
                     const uint32_t idx = base + __popc(idle & ((1u << lane) - 1u));
-#endif
                     if (idx < total) {
                         R.anyHit = idx >= extCount;
                         R.index = idx;
@@ -229,11 +204,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS) k_trace(const T
                         if (A.instanceCount == 0u) G = make_uint2(0u, 0u);
                     }
                 }
-#if TRACE_CHUNK > 0
-                if (resNext >= total) exhausted = true;   // slices are handed out in increasing order: nothing below `total` is left for this warp
-#else
                 if (base + (uint32_t)__popc(idle) >= total) exhausted = true;
-#endif
             }
         }
         if (__ballot_sync(0xffffffffu, R.active) == 0u) break;
