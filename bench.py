@@ -533,7 +533,7 @@ def _run_ours(args, real_stdout):
         peak, peak_src = (float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
         # per-ray BVH visit counts from one instrumented frame (same kernels with counters, untimed, reduced spp)
         visits = None
-        if world == 1 and not args.no_visit_counts:
+        if not args.no_visit_counts:   # (every N: rank 0 renders one small full-frame probe on its own GPU; the BVH is the same on all ranks)
             hc = setup_scene(host, w, h, 2, device=local_rank, max_paths=w * h * 2 + 65536, cuda_flags=FLAG_COUNT_RAYS)
             hc.draw()
             cs = hc.last_frame_stats()
