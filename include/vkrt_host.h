@@ -5,7 +5,9 @@
  * path-tracing hot path: same function names, argument meaning, clamping and error behaviour, so that vkrt's app layer
  * (src/app/{cli,render,scene,mesh,session}) links against it unchanged for headless rendering. Functions of the reference
  * API that only serve the window/editor (swapchain, selection outline, overlay, camera mouse input, render-view pan/zoom,
- * OIDN denoise) are not part of the path and are not provided.
+ * the viewport variant of the denoiser) are not part of the path and are not provided. The save-time denoise stage of
+ * VKRT_saveRenderImageEx (feature AOVs -> Open Image Denoise, src/core/utility/export/image.c:840-905) is provided; the OIDN
+ * library itself is bound at run time (VKRT_OIDN_LIBRARY or the usual sonames) and a missing library saves the raw image.
  *
  * What the implementation does differently underneath: VKRT_updateScene keeps the reference's dirty-revision logic
  * (src/core/api/frame.c:227-263) but calls vkrt_cuda_set_* / vkrt_cuda_build_accel instead of rebuilding Vulkan buffers and
@@ -137,7 +139,7 @@ typedef struct VKRT_RenderStatusSnapshot {
 } VKRT_RenderStatusSnapshot;
 
 typedef struct VKRT_RenderExportSettings {
-    uint8_t denoiseEnabled; /* must be 0: OIDN is outside this path */
+    uint8_t denoiseEnabled; /* 1: denoise with the albedo / normal AOVs before saving (needs libOpenImageDenoise at run time; raw image otherwise) */
 } VKRT_RenderExportSettings;
 
 typedef struct VKRT_SystemInfo {
@@ -271,6 +273,15 @@ VKRT_HOST_API int vkrtLoadImageFromMemory(const void* data, size_t size, const c
 VKRT_HOST_API void vkrtFreeLoadedImage(VKRT_LoadedImage* image);
 /* baseline 4:4:4 JPEG writer behind VKRT_saveRenderImage("*.jpg") (src/core/utility/export/image.c:220-263 uses quality 95) */
 VKRT_HOST_API int vkrtWriteJPEGFromRGBA8(const char* path, const uint8_t* rgba8, uint32_t width, uint32_t height, int quality);
+
+/* The host-side stages of a denoised save, exported for the parity tests (tests/test_denoise.py compares them with the reference's own
+ * source over a stand-in OIDN): image.c:840-905 denoiseLinearRenderOutput on a linear RGBA32F image with the RGBA16F feature AOVs
+ * (returns 0 when the save must fail, else 1; `note` says why the raw image was kept), and image.c:641-699 convertLinearToDisplayRGBA16. */
+VKRT_HOST_API int vkrtHostDenoiseLinear(float* linear, const uint16_t* albedoHalf, const uint16_t* normalHalf, uint32_t width, uint32_t height, int allowRawFallback,
+                                        char* note, size_t noteLength);
+VKRT_HOST_API void vkrtHostLinearToDisplay16(const float* linear, uint32_t width, uint32_t height, uint32_t toneMappingMode, float exposure, uint32_t debugMode,
+                                             uint16_t* outRgba16);
+VKRT_HOST_API void vkrtHostResetDenoiser(void); /* forget the bound OIDN library (it is looked up again on the next use) */
 
 /* ---- app layer: scene files, model import, procedural benchmark scenes, offline render loop ----
  * (src/app/scene/controller.c:1528-1597, src/app/mesh/loader.c:2133-2179, src/app/render/benchmark.c:13-293) */

@@ -23,8 +23,9 @@ static void adaptEqualEnergyXYZToD65(const float xyz[3], float adapted[3]) {
     mul3(bradfordInverse, a, adapted);
 }
 
-/* accumulation (RGBA32F, w = sample count) -> linear sRGB, alpha 1 */
-static void linearizeAccumulation(float* px, size_t count, int spectral) {
+/* accumulation (RGBA32F, w = sample count) -> linear sRGB, alpha 1; non-finite channels become 0 when `sanitise` is set (the denoiser
+ * is handed the image before that step, as in image.c:907-952) */
+static void linearizeAccumulationEx(float* px, size_t count, int spectral, int sanitise) {
     for (size_t i = 0; i < count; i++) {
         float* p = px + i * 4;
         if (spectral) {
@@ -34,11 +35,12 @@ static void linearizeAccumulation(float* px, size_t count, int spectral) {
             p[1] = (-0.9692660f * a[0]) + (1.8760108f * a[1]) + (0.0415560f * a[2]);
             p[2] = (0.0556434f * a[0]) + (-0.2040259f * a[1]) + (1.0572252f * a[2]);
         }
-        for (int c = 0; c < 3; c++)
+        for (int c = 0; sanitise && c < 3; c++)
             if (!isfinite(p[c])) p[c] = 0.0f;
         p[3] = 1.0f;
     }
 }
+static void linearizeAccumulation(float* px, size_t count, int spectral) { linearizeAccumulationEx(px, count, spectral, 1); }
 
 /* ---- OpenEXR ------------------------------------------------------------------------------------------------------------- */
 static void putStr(FILE* f, const char* s) { fwrite(s, 1, strlen(s) + 1, f); }
@@ -153,7 +155,6 @@ void VKRT_defaultRenderExportSettings(VKRT_RenderExportSettings* s) {
 VKRT_Result VKRT_saveRenderImageEx(VKRT* v, const char* path, const VKRT_RenderExportSettings* settings) {
     if (!v || !path || !path[0]) return VKRT_ERROR_INVALID_ARGUMENT;
     if (!v->initialized || v->hostOnly || !v->cuda) return VKRT_ERROR_OPERATION_FAILED;
-    if (settings && settings->denoiseEnabled) return hostFail(v, VKRT_ERROR_OPERATION_FAILED, "OIDN denoising is outside this path; save with denoiseEnabled = 0");
     char withExtension[4096];
     {   /* export/image.c:134-149 resolveRenderImagePath: a path without an extension is saved as PNG */
         const char* base = strrchr(path, '/');
@@ -171,6 +172,52 @@ VKRT_Result VKRT_saveRenderImageEx(VKRT* v, const char* path, const VKRT_RenderE
         r = vkrt_cuda_gather(v->cuda, &ms);
         if (r != VKRT_SUCCESS) return hostFail(v, r, "gather: %s", vkrt_cuda_last_error(v->cuda));
         if (v->createInfo.rank != 0u) return VKRT_SUCCESS;
+    }
+    /* export/api.c:213-236 + image.c:907-1016: with the denoiser on (and no debug view) every format starts from the accumulation buffer:
+       linear sRGB -> OIDN with the feature AOVs -> sanitise; EXR stores that, PNG / JPEG tone-map it on the CPU. A failed or missing
+       denoiser saves the raw image (allowRawFallback = 1 for a save) and leaves the reason in the last-error string. */
+    const int denoise = settings && settings->denoiseEnabled && v->sceneSettings.debugMode == VKRT_DEBUG_MODE_NONE;
+    const int isExr = hasSuffix(path, ".exr"), isPng = hasSuffix(path, ".png"), isJpeg = hasSuffix(path, ".jpg") || hasSuffix(path, ".jpeg");
+    if (denoise && (isExr || isPng || isJpeg)) {
+        float* acc = (float*)malloc(px * 16);
+        uint16_t* albedo = (uint16_t*)malloc(px * 8);
+        uint16_t* normal = (uint16_t*)malloc(px * 8);
+        uint16_t* display = (uint16_t*)malloc(px * 8);
+        r = (acc && albedo && normal && display) ? VKRT_SUCCESS : VKRT_ERROR_OUT_OF_MEMORY;
+        if (r == VKRT_SUCCESS) r = vkrt_cuda_read_aov(v->cuda, VKRT_CUDA_AOV_ACCUM_RGBA32F, acc, px * 16);
+        if (r == VKRT_SUCCESS) r = vkrt_cuda_read_aov(v->cuda, VKRT_CUDA_AOV_ALBEDO_RGBA16F, albedo, px * 8);
+        if (r == VKRT_SUCCESS) r = vkrt_cuda_read_aov(v->cuda, VKRT_CUDA_AOV_NORMAL_RGBA16F, normal, px * 8);
+        if (r != VKRT_SUCCESS) {
+            hostFail(v, r, "read_aov: %s", v->cuda ? vkrt_cuda_last_error(v->cuda) : "");
+        } else {
+            char note[256];
+            linearizeAccumulationEx(acc, px, v->sceneSettings.renderMode == VKRT_RENDER_MODE_SPECTRAL, 0);
+            const int proceed = vkrtHostDenoiseLinear(acc, albedo, normal, w, h, 1, note, sizeof(note));
+            for (size_t i = 0; i < px * 4; i++)   /* sanitizeLinearRGBA32FInPlace(.., 1.0f, 0): alpha is 1 already */
+                if ((i & 3u) != 3u && !isfinite(acc[i])) acc[i] = 0.0f;
+            if (!proceed) {
+                r = hostFail(v, VKRT_ERROR_OPERATION_FAILED, "OIDN denoising failed for '%s': %s", path, note);
+            } else {
+                if (note[0]) hostFail(v, VKRT_SUCCESS, "OIDN denoising failed for '%s'; using raw render (%s)", path, note);
+                int ok;
+                if (isExr) {
+                    ok = writeExr(path, acc, w, h);
+                } else {
+                    vkrtHostLinearToDisplay16(acc, w, h, v->sceneSettings.toneMappingMode, v->sceneSettings.exposure, v->sceneSettings.debugMode, display);
+                    if (isPng) {
+                        ok = writePng16(path, display, w, h);
+                    } else {
+                        uint8_t* out8 = (uint8_t*)albedo; /* (px * 8 bytes: room for px * 4) */
+                        for (size_t i = 0; i < px * 4; i++) out8[i] = (uint8_t)((((uint32_t)display[i] * 255u) + 32767u) / 65535u);
+                        ok = hostWriteJpegRgba8(path, out8, w, h, 95);
+                        if (!ok) remove(path);
+                    }
+                }
+                if (!ok) r = hostFail(v, VKRT_ERROR_OPERATION_FAILED, "cannot write %s", path);
+            }
+        }
+        free(acc); free(albedo); free(normal); free(display);
+        return r;
     }
     if (hasSuffix(path, ".exr")) {
         float* acc = (float*)malloc(px * 16);
