@@ -279,6 +279,10 @@ VKRT_HOST_API int vkrtWriteJPEGFromRGBA8(const char* path, const uint8_t* rgba8,
  * (returns 0 when the save must fail, else 1; `note` says why the raw image was kept), and image.c:641-699 convertLinearToDisplayRGBA16. */
 VKRT_HOST_API int vkrtHostDenoiseLinear(float* linear, const uint16_t* albedoHalf, const uint16_t* normalHalf, uint32_t width, uint32_t height, int allowRawFallback,
                                         char* note, size_t noteLength);
+/* image.c:907-960 prepareLinearRenderOutput on read-back buffers (what a denoised save runs between the read-backs and the file writer):
+ * accumulation (RGBA32F, XYZ when `spectral`) -> linear sRGB with alpha 1, vkrtHostDenoiseLinear when `denoise`, non-finite channels -> 0 */
+VKRT_HOST_API int vkrtHostPrepareLinearOutput(float* accumulation, const uint16_t* albedoHalf, const uint16_t* normalHalf, uint32_t width, uint32_t height, int spectral,
+                                              int denoise, int allowRawFallback, char* note, size_t noteLength);
 VKRT_HOST_API void vkrtHostLinearToDisplay16(const float* linear, uint32_t width, uint32_t height, uint32_t toneMappingMode, float exposure, uint32_t debugMode,
                                              uint16_t* outRgba16);
 VKRT_HOST_API void vkrtHostResetDenoiser(void); /* forget the bound OIDN library (it is looked up again on the next use) */

@@ -356,3 +356,50 @@ def test_saved_render_images_match_the_reference_shaders(tmp_path, mode, hero):
     assert (np.abs(want - gpu_out) > 64).mean() < 0.01
     lib.vkrtFreeLoadedImage(C.byref(img))
     hs.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode,hero", [(0, 0), (1, 1)], ids=["rgb", "hero"])
+def test_denoised_save_is_the_reference_stage_applied_to_the_gpu_film(tmp_path, monkeypatch, mode, hero):
+    """VKRT_saveRenderImageEx with denoiseEnabled = 1 through the whole product path, over the stand-in OIDN (oracle/ref_host/fake_oidn.c):
+    the saved .exr / .png must hold exactly what the reference's own export stage (src/core/utility/export/image.c:907-1016 +
+    denoise.c, compiled into oracle/_ref/libvkrt_refexport.so) makes of the same accumulation, albedo and normal AOVs."""
+    from vkrt_b200 import host
+    import test_denoise
+    ref = refpin._load("libvkrt_refexport.so")
+    monkeypatch.setenv("VKRT_OIDN_LIBRARY", test_denoise._fake())
+    w, h, spp, frames = 96, 64, 4, 2
+    hs, prep, read = _host_scene(w, h, lambda x: x.load_scene(os.path.join(ASSETS, "scenes", "cornell.json")), mode, hero, spp, frames)
+    hs.lib.vkrtHostResetDenoiser()
+    exr, png = str(tmp_path / "dn.exr"), str(tmp_path / "dn.png")
+    hs.save_render_image(exr, denoise=True)
+    hs.save_render_image(png, denoise=True)
+    acc, albedo, normal = read(0, np.float32, 4), read(1, np.uint16, 4), read(2, np.uint16, 4)
+    assert (albedo[..., 3] != 0).any(), "the feature AOVs must carry weight for the test to mean anything"
+    linear = np.zeros((h, w, 4), np.float32)
+    ref.refexport_prepare_linear.restype = C.c_int
+    assert ref.refexport_prepare_linear(acc.ctypes.data_as(C.c_void_p), albedo.ctypes.data_as(C.c_void_p), normal.ctypes.data_as(C.c_void_p), C.c_uint32(w), C.c_uint32(h),
+                                        C.c_uint32(mode), C.c_uint32(0), C.c_int(1), C.c_int(1), linear.ctypes.data_as(C.c_void_p)) == 1
+    got = _read_exr_rgba32f(exr)
+    assert np.array_equal(got.view(np.uint32), linear.view(np.uint32))
+    raw = str(tmp_path / "raw.exr")
+    hs.save_render_image(raw)
+    assert not np.array_equal(_read_exr_rgba32f(raw)[..., :3], got[..., :3]), "the denoiser must have changed the image"
+    display = np.zeros((h, w, 4), np.uint16)
+    snapshot_exposure, tone = 1.0, 1   # cornell.json: ACES, exposure 1 (the scene file's settings; checked below against the host)
+    ref.refexport_linear_to_display.restype = C.c_int
+    assert ref.refexport_linear_to_display(linear.ctypes.data_as(C.c_void_p), C.c_uint32(w), C.c_uint32(h), C.c_uint32(tone), C.c_float(snapshot_exposure), C.c_uint32(0),
+                                           display.ctypes.data_as(C.c_void_p)) == 1
+
+    class Loaded(C.Structure):
+        _fields_ = [("pixels", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32), ("format", C.c_uint32), ("colorSpace", C.c_uint32)]
+    lib = host.load_host_library()
+    img = Loaded()
+    assert lib.vkrtLoadImageFromFile(png.encode(), C.c_uint32(1), C.byref(img)) == 1
+    assert (img.width, img.height) == (w, h)
+    # a 16-bit PNG read as LINEAR comes back as its RGBA16 UNORM codes (host/image_decode.c)
+    codes = np.ctypeslib.as_array(C.cast(img.pixels, C.POINTER(C.c_uint16)), shape=(h, w, 4)).copy()
+    assert np.array_equal(codes, display)
+    lib.vkrtFreeLoadedImage(C.byref(img))
+    hs.lib.vkrtHostResetDenoiser()
+    hs.close()

@@ -222,8 +222,10 @@ class Host:
     def draw(self):
         self._check(self.lib.VKRT_draw(self.h), "VKRT_draw")
 
-    def save_render_image(self, path):
-        self._check(self.lib.VKRT_saveRenderImage(self.h, os.fsencode(path)), "VKRT_saveRenderImage")
+    def save_render_image(self, path, denoise=False):
+        """VKRT_saveRenderImageEx; denoise=True runs the feature AOVs through Open Image Denoise first (bound at run time, raw image if absent)."""
+        settings = (C.c_uint8 * 1)(1 if denoise else 0)   # VKRT_RenderExportSettings { uint8_t denoiseEnabled; }
+        self._check(self.lib.VKRT_saveRenderImageEx(self.h, os.fsencode(path), settings), "VKRT_saveRenderImageEx")
 
     def last_frame_stats(self):
         st = FrameStats()

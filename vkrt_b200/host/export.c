@@ -42,6 +42,19 @@ static void linearizeAccumulationEx(float* px, size_t count, int spectral, int s
 }
 static void linearizeAccumulation(float* px, size_t count, int spectral) { linearizeAccumulationEx(px, count, spectral, 1); }
 
+/* image.c:907-960 prepareLinearRenderOutput on the read-back buffers: accumulation -> linear sRGB (alpha 1), the denoise stage when asked
+ * for, then non-finite channels -> 0. Returns 0 when the denoiser failed and no raw fallback is allowed. */
+int vkrtHostPrepareLinearOutput(float* accum, const uint16_t* albedoHalf, const uint16_t* normalHalf, uint32_t w, uint32_t h, int spectral, int denoise,
+                                int allowRawFallback, char* note, size_t noteLen) {
+    const size_t px = (size_t)w * h;
+    if (note && noteLen) note[0] = 0;
+    linearizeAccumulationEx(accum, px, spectral, 0);
+    if (denoise && !vkrtHostDenoiseLinear(accum, albedoHalf, normalHalf, w, h, allowRawFallback, note, noteLen)) return 0;
+    for (size_t i = 0; i < px * 4; i++)   /* sanitizeLinearRGBA32FInPlace(.., 1.0f, 0): alpha is 1 already */
+        if ((i & 3u) != 3u && !isfinite(accum[i])) accum[i] = 0.0f;
+    return 1;
+}
+
 /* ---- OpenEXR ------------------------------------------------------------------------------------------------------------- */
 static void putStr(FILE* f, const char* s) { fwrite(s, 1, strlen(s) + 1, f); }
 static void putI32(FILE* f, int32_t v) { fwrite(&v, 4, 1, f); }
@@ -191,11 +204,7 @@ VKRT_Result VKRT_saveRenderImageEx(VKRT* v, const char* path, const VKRT_RenderE
             hostFail(v, r, "read_aov: %s", v->cuda ? vkrt_cuda_last_error(v->cuda) : "");
         } else {
             char note[256];
-            linearizeAccumulationEx(acc, px, v->sceneSettings.renderMode == VKRT_RENDER_MODE_SPECTRAL, 0);
-            const int proceed = vkrtHostDenoiseLinear(acc, albedo, normal, w, h, 1, note, sizeof(note));
-            for (size_t i = 0; i < px * 4; i++)   /* sanitizeLinearRGBA32FInPlace(.., 1.0f, 0): alpha is 1 already */
-                if ((i & 3u) != 3u && !isfinite(acc[i])) acc[i] = 0.0f;
-            if (!proceed) {
+            if (!vkrtHostPrepareLinearOutput(acc, albedo, normal, w, h, v->sceneSettings.renderMode == VKRT_RENDER_MODE_SPECTRAL, 1, 1, note, sizeof(note))) {
                 r = hostFail(v, VKRT_ERROR_OPERATION_FAILED, "OIDN denoising failed for '%s': %s", path, note);
             } else {
                 if (note[0]) hostFail(v, VKRT_SUCCESS, "OIDN denoising failed for '%s'; using raw render (%s)", path, note);
