@@ -56,7 +56,7 @@ def test_mutated_files_decode_or_fail_cleanly(fuzzer, codec):
     assert r.stdout.startswith("decoded ")
 
 
-HOST_SRCS = ["api.c", "scene_prep.c", "scene_file.c", "gltf_import.c", "hjson.c", "export.c", "image_decode.c", "jpeg_encode.c", "controllers.c"]
+HOST_SRCS = ["api.c", "scene_prep.c", "scene_file.c", "gltf_import.c", "hjson.c", "export.c", "image_decode.c", "jpeg_encode.c", "controllers.c", "denoise.c"]
 ENV = dict(os.environ, ASAN_OPTIONS="detect_leaks=1:allocator_may_return_null=1:max_allocation_size_mb=1024",
            UBSAN_OPTIONS="print_stacktrace=1:halt_on_error=1")
 
@@ -70,7 +70,7 @@ def _build_host_fuzzer(tmp, name):
     exe = str(tmp / name)
     cmd = ["gcc", "-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-std=gnu11", "-o", exe,
            os.path.join(ROOT, "tests", "fuzz", name + ".c")] + [os.path.join(lib_dir, "host", f) for f in HOST_SRCS] + [
-           "-I" + os.path.join(ROOT, "include"), "-L" + lib_dir, "-lvkrt_cuda", "-lz", "-lm", "-Wl,-rpath," + lib_dir]
+           "-I" + os.path.join(ROOT, "include"), "-L" + lib_dir, "-lvkrt_cuda", "-lz", "-lm", "-ldl", "-Wl,-rpath," + lib_dir]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         pytest.skip("sanitizer build unavailable: " + r.stderr[-300:])
