@@ -1290,6 +1290,7 @@ VK_D BSDFEval evalScalarReflectionStack(const SpectralTables& t, const BSDFState
 }
 VK_NOINLINE BSDFEval evalBSDFMode(const SpectralTables& t, const BSDFState& s, float3 wi, uint spectralMode) {
     if (cosTheta(wi) > 0.0f) return evalScalarReflectionStack(t, s, wi, spectralMode);
+    if (!(s.material.transmission > 0.0f)) return BSDFEval();   // opaque: the transmission lobe is zero with zero density (checked again inside)
     BSDFEval tr = evalDielectricTransmission(
         t, s.material, s.wo, wi, s.frontFace, s.ggx,
         useInteriorDielectricInterface(s) ? 1.0f : materialTransmissionStackAttenuation(s.material, s.wo), s.wavelengthNm,
@@ -1368,6 +1369,10 @@ VK_D float4 evalSpectralReflectionStack(const SpectralTables& t, const BSDFState
 }
 VK_NOINLINE float4 evalSpectralBSDF(const SpectralTables& t, const BSDFState& s, float3 wi, float4 wl, float4& techniquePdf) {
     if (cosTheta(wi) > 0.0f) return evalSpectralReflectionStack(t, s, wi, wl, techniquePdf);
+    if (!(s.material.transmission > 0.0f)) {   // opaque: every lane of the transmission lobe is zero with zero density; skip its colour lookup
+        techniquePdf = float4(0.0f);
+        return float4(0.0f);
+    }
     float coatAtt = useInteriorDielectricInterface(s) ? 1.0f : materialTransmissionStackAttenuation(s.material, s.wo);
     float4 v = evalSpectralDielectricTransmission(t, s.material, s.wo, wi, s.frontFace, s.ggx, coatAtt, wl, techniquePdf);
     techniquePdf *= s.sampleWeights.dielectric;

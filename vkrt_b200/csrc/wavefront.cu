@@ -625,7 +625,10 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const _
                 float4 c(0.0f);
                 const SpectralMemoEntry* lightMemo = (MODE != MODE_RGB && T.emissiveMemo && ls.emissiveMesh != 0xffffffffu) ? T.emissiveMemo + ls.emissiveMesh : nullptr;
                 const bool refractiveReject = materialMediumIsRefractive(state.material) && cosTheta(wiLocal) <= 0.0f;
-                if (!refractiveReject) {
+                // A light below the shading horizon of an opaque surface contributes exactly zero (the reflection stack needs cos > 0, the
+                // transmission lobe needs transmission > 0): not evaluating it keeps the warp out of the transmission code altogether.
+                const bool belowOpaqueHorizon = cosTheta(wiLocal) <= 0.0f && !(state.material.transmission > 0.0f);
+                if (!refractiveReject && !belowOpaqueHorizon) {
                     if (MODE == MODE_RGB) {
                         const BSDFEval e = evalBSDF(T, state, wiLocal);
                         if (e.pdf > 0.0f) {
