@@ -193,6 +193,18 @@ VK_NOINLINE float3 rgb2specFetchTable(const ::float4* __restrict__ cells, const 
     if (z <= RGB2SPEC_EPSILON) return float3(0.0f);
     // rgb2spec.slang:39-44: the LAST channel that reaches the maximum dominates; the other two follow in cyclic order. Written as
     // selects: indexing a float3 with a runtime channel compiles to branches.
+    if (rgb.x == rgb.y && rgb.y == rgb.z) {
+        // Grey (a Schlick colour or a directional attenuation of an untinted dielectric): the last channel dominates and both ratios are 1,
+        // i.e. x = y = res - 1 up to the rounding of the division below: cell (res - 2, res - 2) with weights (0, 1). The trilinear form
+        // then reduces to the z interpolation of two cells: 2 loads instead of 8, 3 lerps instead of 21, same value.
+        const uint zi = rgb2specFindInterval(scale, res, z);
+        const ::float4* c = cells + ((((size_t)2u * res + zi) * res + (res - 1u)) * res + (res - 1u));
+        const ::float4 lo = __ldg(c), hi = __ldg(c + res * res);
+        const float scale0 = scale[zi], scale1 = scale[zi + 1u];
+        const float z1 = (z - scale0) / max(scale1 - scale0, RGB2SPEC_EPSILON);
+        const float z0 = 1.0f - z1;
+        return float3(lo.x * z0 + hi.x * z1, lo.y * z0 + hi.y * z1, lo.z * z0 + hi.z * z1);
+    }
     uint dominantChannel = 0u;
     float top = rgb.x;
     if (rgb.y >= top) { dominantChannel = 1u; top = rgb.y; }
