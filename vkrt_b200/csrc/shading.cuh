@@ -992,8 +992,11 @@ VK_D BSDFEval evalDielectricReflection(const SpectralTables& t, const BSDFMateri
     float3 wm;
     float woDotWm;
     if (!ggxHalfVector(wo, wi, wm, woDotWm)) return e;
-    float fresnel = dielectricFresnel(mat, frontFace, woDotWm, lambdaNm, spectralMode);
-    float reflectionProbability = 1.0f - dielectricTransmissionProbability(mat, fresnel);
+    // An opaque dielectric reflects with probability 1 and takes its colour from Schlick's F0 (dielectricReflectionColor): the exact Fresnel
+    // term is needed only when the material transmits.
+    const bool transmits = mat.transmission > 0.0f;
+    float fresnel = transmits ? dielectricFresnel(mat, frontFace, woDotWm, lambdaNm, spectralMode) : 0.0f;
+    float reflectionProbability = transmits ? 1.0f - dielectricTransmissionProbability(mat, fresnel) : 1.0f;
     if (reflectionProbability <= 0.0f) return e;
     float Dm = ggxDistribution(wm, p.alpha);
     float G = ggxMasking(wo, wi, p.alpha);
@@ -1040,15 +1043,20 @@ VK_D float4 evalSpectralDielectricReflection(const SpectralTables& t, const BSDF
     float3 wm;
     float woDotWm;
     if (!ggxHalfVector(wo, wi, wm, woDotWm)) return float4(0.0f);
-    float4 fresnel = dielectricFresnel4(mat, frontFace, woDotWm, wl);
     float Dm = ggxDistribution(wm, p.alpha);
     float G = ggxMasking(wo, wi, p.alpha);
     float basePdf = ggxReflectionPdf(wo, wm, p);
-    techniquePdf = float4(1.0f - dielectricTransmissionProbability(mat, fresnel.x),
-                          1.0f - dielectricTransmissionProbability(mat, fresnel.y),
-                          1.0f - dielectricTransmissionProbability(mat, fresnel.z),
-                          1.0f - dielectricTransmissionProbability(mat, fresnel.w)) *
-                   basePdf;
+    float4 fresnel(0.0f);
+    if (mat.transmission > 0.0f) {
+        fresnel = dielectricFresnel4(mat, frontFace, woDotWm, wl);
+        techniquePdf = float4(1.0f - dielectricTransmissionProbability(mat, fresnel.x),
+                              1.0f - dielectricTransmissionProbability(mat, fresnel.y),
+                              1.0f - dielectricTransmissionProbability(mat, fresnel.z),
+                              1.0f - dielectricTransmissionProbability(mat, fresnel.w)) *
+                       basePdf;
+    } else {   // opaque: reflection probability 1 at every wavelength, colour from Schlick's F0: the four exact Fresnel terms are not needed
+        techniquePdf = float4(basePdf);
+    }
     if (!anyGreater(techniquePdf, 0.0f)) return float4(0.0f);
     return dielectricReflectionColor4(t, mat, woDotWm, fresnel, wl) * (Dm * G / max(4.0f * cosTheta(wo) * cosTheta(wi), GGX_EPSILON));
 }
@@ -1111,8 +1119,7 @@ VK_D bool sampleDielectric(const BSDFMaterial& mat, float3 wo, uint frontFace, c
     if (!sampleGGXVNDF(wo, p, float2(ux, uy), wm)) return false;
     float woDotWm = dot(wo, wm);
     if (woDotWm <= 0.0f) return false;
-    float fresnel = dielectricFresnel(mat, frontFace, woDotWm, lambdaNm, spectralMode);
-    float tp = dielectricTransmissionProbability(mat, fresnel);
+    float tp = mat.transmission > 0.0f ? dielectricTransmissionProbability(mat, dielectricFresnel(mat, frontFace, woDotWm, lambdaNm, spectralMode)) : 0.0f;
     if (tp > 0.0f && rand(rng) < tp) {
         float eta = interfaceRefractionEta(mat, frontFace, lambdaNm, spectralMode);
         float3 wi = refract(-wo, wm, eta);
