@@ -547,9 +547,11 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const _
             }
             SurfaceShadingData surface = reconstructSurfaceShading(sc, mesh, trig, hitPrim, float2(hitU, hitV), ray.direction);
             Material material = loadMaterial(sc.materials + surface.materialIndex);
-            {
+            if (material.normalTextureIndex != VKRT_INVALID_INDEX) {
                 const ShadingBasis unperturbed = makeShadingBasis(surface.shadingNormal, surface.tangent);
                 surface.shadingNormal = applyNormalTexture(sc, material, surface.textureData, unperturbed);
+            } else {   // without a texture applyNormalTexture returns the basis normal: the normalised shading normal; the tangent frame is not needed
+                surface.shadingNormal = safeNormalize(surface.shadingNormal);
             }
             surface.shadingNormal = sanitizeShadingNormal(surface.shadingNormal, surface.geometricNormal, -ray.direction);
             basis = makeShadingBasis(surface.shadingNormal, surface.tangent);
@@ -578,7 +580,8 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const _
             }
           if (live) {
             // ---- denoiser features (loop.slang:83-103) ----------------------------------------------------------------
-            const bool follow = materialDenoiserShouldFollowSpecularHit(bm, surface.frontFace);
+            // (the specular-follow test is needed only while the features of this path are unresolved, and for the follow image at depth 0)
+            const bool follow = (depth == 0u || !(flags & PF_FEATURES_RESOLVED)) && materialDenoiserShouldFollowSpecularHit(bm, surface.frontFace);
             if (depth == 0u) fp.rec.follow[rec] = follow ? 1.0f : 0.0f;
             if (!(flags & PF_FEATURES_RESOLVED) && !follow) {
                 fp.rec.featA[rec] = toF4(materialDenoiserAlbedo(bm), 1.0f);
