@@ -377,7 +377,13 @@ struct BSDFMaterial {
     float sheenRoughness = 0.0f;
     float absorptionCoefficient = 0.0f;
     float3 attenuationColor = float3(1.0f);
+    // Derived once per vertex by makeBSDFMaterial (the only way to convert a Material): the Schlick F0 of the dielectric interface, which the
+    // branch weights, the directional attenuation and every evaluation of the dielectric lobe would each recompute (ior, specular, tint).
+    float3 specularF0 = float3(0.0f);
     __device__ BSDFMaterial() {}
+    friend __device__ BSDFMaterial makeBSDFMaterial(const Material& m);
+
+private:
     __device__ explicit BSDFMaterial(const Material& m) {
         baseColor = float3(m.baseColor[0], m.baseColor[1], m.baseColor[2]);
         roughness = m.roughness;
@@ -400,6 +406,8 @@ struct BSDFMaterial {
         absorptionCoefficient = m.absorptionCoefficient;
         attenuationColor = float3(m.attenuationColor[0], m.attenuationColor[1], m.attenuationColor[2]);
     }
+
+public:
 };
 VK_D float3 bsdfDiffuseColor(const BSDFMaterial& m) { return m.baseColor * (1.0f - m.metallic); }
 VK_D float3 bsdfTintColor(float3 baseColor) {
@@ -471,12 +479,18 @@ VK_D float dielectricF0(float eta) {
     return f0 * f0;
 }
 VK_D bool materialHasConductor(const BSDFMaterial& m) { return anyGreater(m.k, 0.0f); }
-VK_D float3 bsdfDielectricSpecularF0(const BSDFMaterial& m) {
+VK_D float3 computeDielectricSpecularF0(const BSDFMaterial& m) {
     float dielectric = dielectricF0(m.ior);
     float specularScale = m.specular / 0.5f;
     float3 tint = lerp(float3(1.0f), bsdfTintColor(m.baseColor), saturate(m.specularTint));
     return saturate(dielectric * specularScale * tint);
 }
+__device__ __forceinline__ BSDFMaterial makeBSDFMaterial(const Material& src) {
+    BSDFMaterial m(src);
+    m.specularF0 = computeDielectricSpecularF0(m);
+    return m;
+}
+VK_D float3 bsdfDielectricSpecularF0(const BSDFMaterial& m) { return m.specularF0; }
 VK_D float bsdfDielectricSpecularF0Luminance(const BSDFMaterial& m) {
     return saturate(linearSrgbLuminance(bsdfDielectricSpecularF0(m)));
 }
@@ -1222,27 +1236,28 @@ struct BSDFState {
     BSDFMaterial material;
     float3 wo;
     GGXParams ggx;
-    ClearcoatParams clearcoat;
-    uint frontFace = 0u;
     float wavelengthNm = 0.0f;
-    uint spectralMode = 0u;
     BSDFBranchWeights sampleWeights;
     // Hero mode evaluates the closure twice per vertex with the same (material, wo): once for the light sample, once for the sampled
     // direction. The two spectral upsamplings that do not depend on wi are kept from the first evaluation (the state lives in the
     // kernel's local frame; each lookup is ~100 instructions and 8 gathered 128-bit loads).
     mutable float cachedDiffuse4[4], cachedVd4[4];   // plain floats (no alignment demands on the state record, which k_shade keeps in shared memory)
-    mutable uint cachedMask = 0u;   // bit 0: cachedDiffuse4 valid, bit 1: cachedVd4 valid
-    uint memoIndex = 0xffffffffu;   // first SpectralTables::materialMemo entry of this vertex's material (k_shade), or none
+    // One word for the small fields: k_shade keeps this record in shared memory and every 8 bytes of it cost 4 KB of L1 per SM (the hero
+    // kernel's spill slots live there). The clearcoat constant is recomputed where the lobe runs (makeClearcoatParams) for the same reason.
+    uint frontFace : 1;
+    uint spectralMode : 1;
+    mutable uint cachedMask : 2;   // bit 0: cachedDiffuse4 valid, bit 1: cachedVd4 valid
+    uint memoIndex : 28;           // first SpectralTables::materialMemo entry of this vertex's material (k_shade), or SPECTRAL_MEMO_NONE
+    static constexpr uint SPECTRAL_MEMO_NONE = 0x0fffffffu;
     __device__ BSDFState() {}
     __device__ BSDFState(const BSDFMaterial& m, float3 wo_, uint ff, float wl, uint sm)
-        : material(m), wo(wo_), frontFace(ff), wavelengthNm(wl), spectralMode(sm) {
+        : material(m), wo(wo_), wavelengthNm(wl), frontFace(ff), spectralMode(sm), cachedMask(0u), memoIndex(SPECTRAL_MEMO_NONE) {
         ggx = makeGGXParams(m, wo_);
-        clearcoat = makeClearcoatParams(m);
         sampleWeights = makeBSDFBranchWeights(m, wo_, ff);
     }
 };
 VK_D const SpectralMemoEntry* spectralMemoOf(const SpectralTables& t, const BSDFState& s, uint slot) {
-    return (t.materialMemo && s.memoIndex != 0xffffffffu) ? t.materialMemo + (s.memoIndex + slot) : nullptr;
+    return (t.materialMemo && s.memoIndex != BSDFState::SPECTRAL_MEMO_NONE) ? t.materialMemo + (s.memoIndex + slot) : nullptr;
 }
 VK_D bool useInteriorDielectricInterface(const BSDFState& s) { return s.material.transmission > 0.0f && s.frontFace == 0u; }
 
@@ -1263,7 +1278,7 @@ VK_D BSDFEval evalScalarReflectionStack(const SpectralTables& t, const BSDFState
         e.pdf += s.sampleWeights.sheen * sh.pdf;
     }
     if (s.sampleWeights.coat > 0.0f) {
-        BSDFEval c = evalClearcoat(m.clearcoat, s.wo, wi, s.clearcoat);
+        BSDFEval c = evalClearcoat(m.clearcoat, s.wo, wi, makeClearcoatParams(m));
         coatValue = c.value;
         e.pdf += s.sampleWeights.coat * c.pdf;
     }
@@ -1335,7 +1350,7 @@ VK_D float4 evalSpectralReflectionStack(const SpectralTables& t, const BSDFState
         techniquePdf += float4(s.sampleWeights.sheen * sh.pdf);
     }
     if (s.sampleWeights.coat > 0.0f) {
-        BSDFEval c = evalClearcoat(m.clearcoat, s.wo, wi, s.clearcoat);
+        BSDFEval c = evalClearcoat(m.clearcoat, s.wo, wi, makeClearcoatParams(m));
         coatValue = c.value.x;
         techniquePdf += float4(s.sampleWeights.coat * c.pdf);
     }
@@ -1408,7 +1423,7 @@ VK_NOINLINE bool sampleBSDFDirection(const BSDFState& s, uint& rng, BSDFDirectio
     float selector = rand(rng);
     if (selector < s.sampleWeights.sheen) return sampleSheen(s.wo, s.material.sheenRoughness, rng, out.wi);
     selector -= s.sampleWeights.sheen;
-    if (selector < s.sampleWeights.coat) return sampleClearcoat(s.wo, s.clearcoat, rng, out.wi);
+    if (selector < s.sampleWeights.coat) return sampleClearcoat(s.wo, makeClearcoatParams(s.material), rng, out.wi);
     selector -= s.sampleWeights.coat;
     if (selector < s.sampleWeights.metal) return sampleGGX(s.wo, s.ggx, rng, out.wi);
     selector -= s.sampleWeights.metal;

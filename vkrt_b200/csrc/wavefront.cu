@@ -558,7 +558,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const _
             geometricNormal = surface.geometricNormal;
             applySurfaceTextures(sc, material, surface.textureData);
             emission = float3(material.emissionColor[0], material.emissionColor[1], material.emissionColor[2]) * material.emissionLuminance;
-            const BSDFMaterial bm(material);
+            const BSDFMaterial bm = makeBSDFMaterial(material);
 
             // ---- primary-surface debug views (integrator/path/debug.slang:31-64) -----------------------------------------
             if (sampleIndex == 0u && depth == 0u && scene.debugMode != VKRT_DEBUG_MODE_NONE) {
@@ -1145,7 +1145,7 @@ __global__ void __launch_bounds__(128) k_eval_closures(const SceneView sc, const
     const vkrt_closure_query& Q = queries[i];
     vkrt_closure_result R = {};
     const Material material = loadMaterial(&Q.material);
-    const BSDFMaterial bm(material);
+    const BSDFMaterial bm = makeBSDFMaterial(material);
     const float3 wo(Q.wo[0], Q.wo[1], Q.wo[2]), wi(Q.wi[0], Q.wi[1], Q.wi[2]);
     const float4 wl(Q.wavelengths[0], Q.wavelengths[1], Q.wavelengths[2], Q.wavelengths[3]);
     const BSDFState st(bm, wo, Q.frontFace, Q.mode == 0u ? 0.0f : wl.x, Q.mode == 0u ? 0u : 1u);
@@ -1201,7 +1201,7 @@ __global__ void __launch_bounds__(128) k_spectral_memo(const SceneView sc, uint3
         m.metallic = saturate(m.metallic * 1.0f);
         normalizeEmission(m, float3(1.0f));
         const float3 emission = float3(m.emissionColor[0], m.emissionColor[1], m.emissionColor[2]) * m.emissionLuminance;
-        const BSDFMaterial bm(m);
+        const BSDFMaterial bm = makeBSDFMaterial(m);
         const float3 diffuse = saturate(bsdfDiffuseColor(bm));
         materialMemo[i * SPECTRAL_MEMO_SLOTS + SPECTRAL_MEMO_DIFFUSE] = {make_float4(diffuse.x, diffuse.y, diffuse.z, 0.0f), spectralCoefficientsFromLinearSrgb(T, diffuse)};
         materialMemo[i * SPECTRAL_MEMO_SLOTS + SPECTRAL_MEMO_EMISSION] = {make_float4(emission.x, emission.y, emission.z, 0.0f), spectralCoefficientsFromLinearSrgb(T, emission)};
