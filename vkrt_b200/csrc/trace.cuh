@@ -139,7 +139,7 @@ struct LaneRay {
 };
 
 template <bool COUNT, bool FLAT, int STACK>
-__global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS) k_trace(const TraceParams P) {
+__global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS) k_trace(const __grid_constant__ TraceParams P) {
     const int lane = threadIdx.x & 31;
     const uint32_t extCount = P.extCount ? *P.extCount : 0u;
     const uint32_t shCount = P.shCount ? *P.shCount : 0u;
