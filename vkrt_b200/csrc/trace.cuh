@@ -34,7 +34,8 @@ constexpr unsigned long long TRACE_REFILL_BIG_SCENE = 262144ull;
 #define TRACE_PRIM_VOTE 8   // lanes with a pending primitive wait until 8 of them can run the primitive section together (0 = every trip)
 #endif
 #ifndef TRACE_MIN_BLOCKS
-#define TRACE_MIN_BLOCKS 6   // 80 registers: 24 warps per SM (measured best, profiles/r01_notes.md)
+#define TRACE_MIN_BLOCKS 7   // 72 registers, 28 warps per SM. Measured again once the parameter block stayed in constant memory (profiles/r02z_trace_occupancy.txt):
+                             // 5 / 6 / 7 / 8 blocks per SM: cornell 27.3 / 26.2 / 25.7 / 26.7 ms, soup 18.6 / 18.0 / 17.8 / 18.7, 1000 spheres 32.5 / 30.9 / 30.2 / 31.6
 #endif
 constexpr uint32_t SHADOW_KIND_SCALAR = 1u << 31;  // in ShadowTarget.statePos: contribution goes to the scalar lane (hero fallback)
 
