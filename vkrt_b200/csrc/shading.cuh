@@ -149,6 +149,9 @@ struct SpectralTables {
     const float* table = nullptr;      // the payload as uploaded (rgb2spec.c:17-59)
     const ::float4* cells = nullptr;   // 3 * res^3 packed coefficient cells
     const float* scale = nullptr;      // table + scaleOffset, or its shared-memory copy
+    // optional (k_shade, res = 64): for q in [0, 1024), the interval index of x = q / 1024. A search starts there and walks up; it ends where
+    // the full search ends (rgb2specFindInterval), after 0 - 1 steps for all but near-black inputs, instead of 14 loads and compares.
+    const unsigned char* intervalLut = nullptr;
     // Memoised upsamplings (k_spectral_memo): colours that are constants of a material or of a light are looked up in the table once per
     // scene edit, not once per path vertex. An entry is used only when its key equals the colour at hand bit for bit, so a texture or a
     // vertex colour that changes the colour simply misses; nullptr = no memo (closure test entry, RGB frames).
@@ -161,7 +164,13 @@ static constexpr uint RGB2SPEC_SMEM_RES = 64u;
 // rgb2spec.slang:14-30: the largest index in [0, res-2] whose scale entry is <= x. The scale axis is non-decreasing, so that index is
 // the NUMBER of entries k in [1, res-2] with scale[k] <= x: for the standard res = 64 two rounds of independent loads (7 block pivots,
 // then 7 entries of the block) replace six dependent ones.
-VK_D uint rgb2specFindInterval(const float* __restrict__ scale, uint res, float x) {
+constexpr uint RGB2SPEC_LUT_SIZE = 1024u;
+VK_D uint rgb2specFindInterval(const float* __restrict__ scale, uint res, float x, const unsigned char* __restrict__ lut = nullptr) {
+    if (lut) {   // (res == 64) same result as below: the table entry is the answer for a lower bound of x, and the scale axis is non-decreasing
+        uint k = lut[min(uint(x * float(RGB2SPEC_LUT_SIZE)), RGB2SPEC_LUT_SIZE - 1u)];
+        while (k < 62u && scale[k + 1u] <= x) k++;
+        return k;
+    }
     if (res == 64u) {
         // all loads of a round are issued before the first comparison: two load latencies per search instead of fourteen
         const float p0 = scale[8], p1 = scale[16], p2 = scale[24], p3 = scale[32], p4 = scale[40], p5 = scale[48], p6 = scale[56];
@@ -188,7 +197,8 @@ VK_D uint rgb2specFindInterval(const float* __restrict__ scale, uint res, float 
     return min(uint(left), res - 2u);
 }
 
-VK_NOINLINE float3 rgb2specFetchTable(const ::float4* __restrict__ cells, const float* __restrict__ scale, uint res, float3 rgb) {
+VK_NOINLINE float3 rgb2specFetchTable(const ::float4* __restrict__ cells, const float* __restrict__ scale, uint res, float3 rgb,
+                                      const unsigned char* __restrict__ lut = nullptr) {
     float z = max(rgb.x, max(rgb.y, rgb.z));
     if (z <= RGB2SPEC_EPSILON) return float3(0.0f);
     // rgb2spec.slang:39-44: the LAST channel that reaches the maximum dominates; the other two follow in cyclic order. Written as
@@ -197,7 +207,7 @@ VK_NOINLINE float3 rgb2specFetchTable(const ::float4* __restrict__ cells, const 
         // Grey (a Schlick colour or a directional attenuation of an untinted dielectric): the last channel dominates and both ratios are 1,
         // i.e. x = y = res - 1 up to the rounding of the division below: cell (res - 2, res - 2) with weights (0, 1). The trilinear form
         // then reduces to the z interpolation of two cells: 2 loads instead of 8, 3 lerps instead of 21, same value.
-        const uint zi = rgb2specFindInterval(scale, res, z);
+        const uint zi = rgb2specFindInterval(scale, res, z, lut);
         const ::float4* c = cells + ((((size_t)2u * res + zi) * res + (res - 1u)) * res + (res - 1u));
         const ::float4 lo = __ldg(c), hi = __ldg(c + res * res);
         const float scale0 = scale[zi], scale1 = scale[zi + 1u];
@@ -216,7 +226,7 @@ VK_NOINLINE float3 rgb2specFetchTable(const ::float4* __restrict__ cells, const 
     float y = cy * xyScale;
     uint xi = min(uint(x), res - 2u);
     uint yi = min(uint(y), res - 2u);
-    uint zi = rgb2specFindInterval(scale, res, z);
+    uint zi = rgb2specFindInterval(scale, res, z, lut);
     const ::float4* c = cells + ((((size_t)dominantChannel * res + zi) * res + yi) * res + xi);
     const uint dy = res, dz = res * res;
     const ::float4 c000 = __ldg(c), c100 = __ldg(c + 1), c010 = __ldg(c + dy), c110 = __ldg(c + dy + 1);
@@ -237,7 +247,7 @@ VK_NOINLINE float3 rgb2specFetchTable(const ::float4* __restrict__ cells, const 
     return coeff;
 }
 VK_D float3 rgb2specFetch(const SpectralTables& t, float3 rgb) {
-    return rgb2specFetchTable(t.cells, t.scale, t.info.res, rgb);
+    return rgb2specFetchTable(t.cells, t.scale, t.info.res, rgb, t.intervalLut);
 }
 VK_D float rgb2specEvalCoeffs(float3 coeff, float lambdaNm) {
     float x = (coeff.x * lambdaNm + coeff.y) * lambdaNm + coeff.z;

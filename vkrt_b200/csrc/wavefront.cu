@@ -389,7 +389,7 @@ static_assert(alignof(ShadeScratch) <= 8, "ShadeScratch must not need more than 
 constexpr size_t SHADE_SCRATCH_STRIDE = (((sizeof(ShadeScratch) + 7) / 8) | 1) * 8;   // an odd number of 8-byte units: 2-way conflicts at worst
 #endif
 constexpr size_t SHADE_DYNAMIC_SMEM = SHADE_SCRATCH_STRIDE * SHADE_BLOCK;
-static_assert((SHADE_DYNAMIC_SMEM + 1024 + 256 + 64) * SHADE_MIN_BLOCKS <= 228 * 1024, "the per-vertex records of SHADE_MIN_BLOCKS blocks must fit the SM's shared memory (228 KB, 1 KB reserved per block)");
+static_assert((SHADE_DYNAMIC_SMEM + 1024 + 1280 + 64) * SHADE_MIN_BLOCKS <= 228 * 1024, "the per-vertex records of SHADE_MIN_BLOCKS blocks must fit the SM's shared memory (228 KB; 1 KB reserved and 1.25 KB of static tables per block)");
 template <int MODE, bool ENVIS>
 __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ FrameParams fp, const uint32_t depth) {
     const uint32_t count = fp.extCount[depth];
@@ -404,6 +404,19 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const _
         if (threadIdx.x < T.info.res) sScale[threadIdx.x] = T.scale[threadIdx.x];
         T.scale = sScale;
         __syncthreads();
+#ifndef SHADE_NO_INTERVAL_LUT
+        if (T.info.res == 64u) {   // start points of the scale-axis search (SpectralTables::intervalLut), rebuilt per launch: 1 KB, ~250 compares per thread
+            __shared__ unsigned char sIntervalLut[RGB2SPEC_LUT_SIZE];
+            for (uint32_t q = threadIdx.x; q < RGB2SPEC_LUT_SIZE; q += blockDim.x) {
+                const float xq = float(q) * (1.0f / float(RGB2SPEC_LUT_SIZE));
+                uint32_t k = 0u;
+                for (uint32_t e = 1u; e <= 62u; e++) k += sScale[e] <= xq ? 1u : 0u;
+                sIntervalLut[q] = (unsigned char)k;
+            }
+            T.intervalLut = sIntervalLut;
+            __syncthreads();
+        }
+#endif
     }
     const uint32_t lpc = fp.tiles.localPixelCount;
     const bool neeEnabled = (fp.modeFlags & MODE_NEE_ENABLED) && !(fp.modeFlags & MODE_BSDF_ONLY);
