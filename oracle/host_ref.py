@@ -663,7 +663,9 @@ def load_glb(path):
                     else:
                         for i in range(n):
                             v["tangent"][i] = _fallback_tangent(v["normal"][i, :3])
-                name = gm.get("name") or node.get("name") or os.path.basename(path)
+                name = node.get("name") or gm.get("name") or "mesh"          # loader.c:1097-1118 buildEntryName
+                if len(gm["primitives"]) > 1:
+                    name = "%s_%d" % (name, pi)
                 hm = HostMesh(name=name, vertices=v, indices=idx, world=world.copy(), node_local=world.copy(),
                               render_backfaces=1 if (gmat and gmat.get("doubleSided")) else 0, gltf_material=gmat)
                 meshes.append(hm)
@@ -738,7 +740,10 @@ def gltf_material_to_vkrt(gmat):
         m["emissionLuminance"] = mx
     am = gmat.get("alphaMode", "OPAQUE")
     m["alphaMode"] = {"OPAQUE": 0, "MASK": 1, "BLEND": 2}[am]
-    m["alphaCutoff"] = gmat.get("alphaCutoff", 0.5)
+    if am == "MASK":                                                             # loader.c:1546-1552
+        m["alphaCutoff"] = gmat.get("alphaCutoff", 0.5)
+    elif am == "BLEND":
+        m["alphaCutoff"] = f32(1.0) / f32(255.0)
     return m
 
 

@@ -76,7 +76,7 @@ VkResult vkGetQueryPoolResults(VkDevice d, VkQueryPool p, uint32_t first, uint32
     return -1;
 }
 VKRT_Result createAutoExposureReadbacks(VKRT* vkrt) { (void)vkrt; return VKRT_SUCCESS; }
-uint64_t getMicroseconds(void) { return 0; }
+uint64_t getMicroseconds(void) { return 0; }   /* (wins over utility/platform.c's clock: first definition on the link line, --allow-multiple-definition) */
 void vkrtLogLine(FILE* stream, const char* level, const char* format, ...) { (void)stream; (void)level; (void)format; }
 /* texture registry (scene/textures.c needs the image loaders): no textures in the pinned host scenes */
 void vkrtAdjustMaterialTextureUseCounts(VKRT* vkrt, const Material* material, int delta) { (void)vkrt; (void)material; (void)delta; }

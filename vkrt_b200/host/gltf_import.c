@@ -426,7 +426,9 @@ static Material convertMaterial(ImportCtx* c, const hj_value* gm, Material m) {
     }
     const char* am = hj_string(hj_get(gm, "alphaMode"), "OPAQUE");
     m.alphaMode = !strcmp(am, "MASK") ? VKRT_MATERIAL_ALPHA_MODE_MASK : (!strcmp(am, "BLEND") ? VKRT_MATERIAL_ALPHA_MODE_BLEND : VKRT_MATERIAL_ALPHA_MODE_OPAQUE);
-    m.alphaCutoff = (float)hj_number(hj_get(gm, "alphaCutoff"), 0.5);
+    /* loader.c:1546-1552: MASK takes the file's cutoff (glTF default 0.5), BLEND a fixed 1/255, OPAQUE keeps the material default */
+    if (m.alphaMode == VKRT_MATERIAL_ALPHA_MODE_MASK) m.alphaCutoff = (float)hj_number(hj_get(gm, "alphaCutoff"), 0.5);
+    else if (m.alphaMode == VKRT_MATERIAL_ALPHA_MODE_BLEND) m.alphaCutoff = 1.0f / 255.0f;
     return m;
 }
 
@@ -460,7 +462,7 @@ static int appendMesh(ImportCtx* c, GltfMesh* m) {
     return 1;
 }
 
-static int importPrimitive(ImportCtx* c, const hj_value* gmesh, const hj_value* node, const hj_value* prim, hmat4 world) {
+static int importPrimitive(ImportCtx* c, const hj_value* gmesh, const hj_value* node, const hj_value* prim, size_t primitiveIndex, hmat4 world) {
     if ((int)hj_number(hj_get(prim, "mode"), 4) != 4) return 1; /* triangles only */
     const hj_value* at = hj_get(prim, "attributes");
     const hj_value* posAcc = hj_get(at, "POSITION");
@@ -533,8 +535,9 @@ static int importPrimitive(ImportCtx* c, const hj_value* gmesh, const hj_value* 
         if (normalTexSet > 1) normalTexSet = 0;
     }
     if (!hasNormals) {
+        /* loader.c:1871-1878: a primitive without normals gets generated normals and NOTHING else: no winding alignment, and its tangents stay
+           zero (the shaders build a fallback frame from a zero tangent, geometry/surface.slang) — found by the pin against the reference loader */
         generateNormals(v, nv, idx, ni);
-        for (size_t i = 0; i < nv; i++) fallbackTangent(v[i].normal, v[i].tangent);
     } else {
         alignWinding(v, nv, idx, ni);
         if (hasTangents) {
@@ -555,9 +558,12 @@ static int importPrimitive(ImportCtx* c, const hj_value* gmesh, const hj_value* 
     memcpy(m.world, world, sizeof(hmat4));
     m.materialIndex = gmat ? (int)hj_number(hj_get(prim, "material"), -1) : -1;
     m.doubleSided = gmat ? hj_bool(hj_get(gmat, "doubleSided"), 0) : 0;
-    const char* name = hj_string(hj_get(gmesh, "name"), NULL);
-    if (!name || !name[0]) name = hj_string(hj_get(node, "name"), NULL);
-    snprintf(m.name, sizeof(m.name), "%s", name && name[0] ? name : "mesh");
+    /* loader.c:1097-1118 buildEntryName: the node's name, else the mesh's, else "mesh"; "_<primitive>" when the mesh has several primitives */
+    const char* name = hj_string(hj_get(node, "name"), NULL);
+    if (!name || !name[0]) name = hj_string(hj_get(gmesh, "name"), NULL);
+    if (!name || !name[0]) name = "mesh";
+    if (hj_count(hj_get(gmesh, "primitives")) > 1) snprintf(m.name, sizeof(m.name), "%s_%zu", name, primitiveIndex);
+    else snprintf(m.name, sizeof(m.name), "%s", name);
     if (!appendMesh(c, &m)) { free(v); free(idx); return 0; }
     return 1;
 }
@@ -575,7 +581,7 @@ static int visitNode(ImportCtx* c, int nodeIndex, hmat4 parentWorld, int depth) 
         const hj_value* gmesh = hj_at(hj_get(c->doc, "meshes"), (size_t)hj_number(meshRef, -1));
         const hj_value* prims = hj_get(gmesh, "primitives");
         for (size_t p = 0; p < hj_count(prims); p++)
-            if (!importPrimitive(c, gmesh, node, hj_at(prims, p), world)) return 0;
+            if (!importPrimitive(c, gmesh, node, hj_at(prims, p), p, world)) return 0;
     }
     const hj_value* children = hj_get(node, "children");
     for (size_t k = 0; k < hj_count(children); k++)

@@ -31,7 +31,8 @@ typedef struct GltfImport {
     uint32_t textureCount;
 } GltfImport;
 
-int gltfImportFile(const char* path, GltfImport* out, char* error, size_t errorSize); /* 1 = ok */
-void gltfImportFree(GltfImport* imp);
+/* (exported so that tests/test_reference_pin.py can compare the importer with the reference's own src/app/mesh/loader.c) */
+VKRT_HOST_API int gltfImportFile(const char* path, GltfImport* out, char* error, size_t errorSize); /* 1 = ok */
+VKRT_HOST_API void gltfImportFree(GltfImport* imp);
 
 #endif
