@@ -17,6 +17,7 @@
  * the upstream sources. */
 #include "vkrt_internal.h"
 #include "buffer.h"
+#include <stdarg.h>
 #include "debug.h"
 #include "packing.h"
 #include "scene.h"
@@ -77,7 +78,15 @@ VkResult vkGetQueryPoolResults(VkDevice d, VkQueryPool p, uint32_t first, uint32
 }
 VKRT_Result createAutoExposureReadbacks(VKRT* vkrt) { (void)vkrt; return VKRT_SUCCESS; }
 uint64_t getMicroseconds(void) { return 0; }   /* (wins over utility/platform.c's clock: first definition on the link line, --allow-multiple-definition) */
-void vkrtLogLine(FILE* stream, const char* level, const char* format, ...) { (void)stream; (void)level; (void)format; }
+void vkrtLogLine(FILE* stream, const char* level, const char* format, ...) {   /* silent unless REFHOST_LOG is set (debugging the tests) */
+    if (!getenv("REFHOST_LOG")) return;
+    va_list args;
+    va_start(args, format);
+    fprintf(stream ? stream : stderr, "%s ", level ? level : "");
+    vfprintf(stream ? stream : stderr, format, args);
+    fputc('\n', stream ? stream : stderr);
+    va_end(args);
+}
 /* texture registry (scene/textures.c needs the image loaders): no textures in the pinned host scenes */
 void vkrtAdjustMaterialTextureUseCounts(VKRT* vkrt, const Material* material, int delta) { (void)vkrt; (void)material; (void)delta; }
 uint32_t vkrtCountTextureUsers(const VKRT* vkrt, uint32_t textureIndex) { (void)vkrt; (void)textureIndex; return 0u; }

@@ -679,3 +679,74 @@ def test_gltf_importer_matches_the_reference_loader(tmp_path):
             assert imp.textures[k].name == name.value and imp.textures[k].colorSpace == desc[3], (path, k)
         host.gltfImportFree(C.byref(imp))
         ref.refloader_free(hp)
+
+
+# ---- vkrt.scene files: the product's reader against the reference's own scene controller --------------------------------------------------
+@pytest.mark.parametrize("scene", ["cornell", "prism", "caustics"])
+def test_scene_file_reader_matches_the_reference_controller(scene):
+    """VKRT_appLoadScene (vkrt_b200/host/scene_file.c: own JSON reader, object hierarchy, material table) against the reference's
+    sceneControllerLoadSceneFromPath compiled where it lies (src/app/scene/controller.c + cJSON, session.c, mesh/controller.c, loader.c + cgltf,
+    api/{query,geometry,texture,environment,render,mesh,settings}.c, scene/{geometry,environment,transform,...}.c behind the null device;
+    oracle/ref_host/ref_scene_entry.c) on the bundled scenes: mesh order and names, geometry sharing, vertex / index ranges, material
+    assignment, back-face and opacity flags identical; materials byte-identical; world matrices and the decomposed position / rotation /
+    scale within a few ulp; every scene setting (camera, depths, modes, exposure, environment) identical."""
+    from vkrt_b200 import host
+    ref = refpin.refhost_lib()
+    ref.refscene_load.argtypes = [C.c_void_p, C.c_char_p]
+    ref.refscene_mesh_count.argtypes = [C.c_void_p]
+    ref.refscene_mesh_count.restype = C.c_uint32
+    path = os.path.join(H.ROOT, "assets", "scenes", scene + ".json")
+    h = C.c_void_p(ref.refhost_create(320, 180))
+    assert ref.refscene_load(h, path.encode()) == 1
+    hs = host.Host(host_only=True, width=320, height=180)
+    hs.load_scene(path)
+    hs.start_render(320, 180, 64)
+    got = hs.prepare_scene()
+    n = ref.refscene_mesh_count(h)
+    assert n == len(got["meshInfos"]) == hs.mesh_count()
+
+    class MeshSnapshot(C.Structure):
+        _fields_ = [("info", C.c_uint8 * 80), ("material", C.c_uint8 * 272), ("materialIndex", C.c_uint32), ("geometrySource", C.c_uint32),
+                    ("hasMaterialAssignment", C.c_uint8), ("ownsGeometry", C.c_uint8), ("name", C.c_char * 256)]
+    for i in range(n):
+        info, world, misc, name = np.zeros(1, H.hr.MESH_INFO), (C.c_float * 16)(), (C.c_uint32 * 4)(), C.create_string_buffer(256)
+        ref.refscene_mesh(h, i, info.ctypes.data_as(C.c_void_p), world, misc, name, 256)
+        mine = got["meshInfos"][i]
+        for key in ("vertexBase", "vertexCount", "indexBase", "indexCount", "materialIndex", "renderBackfaces"):
+            assert int(mine[key]) == int(info[key][0]), (scene, i, key)
+        assert float(mine["opacity"]) == float(info["opacity"][0])
+        assert int(got["geometrySource"][i]) == misc[0], (scene, i)
+        snap = MeshSnapshot()
+        assert hs.lib.VKRT_getMeshSnapshot(hs.h, C.c_uint32(i), C.byref(snap)) == 0
+        assert snap.name == name.value and snap.ownsGeometry == misc[1] and snap.hasMaterialAssignment == misc[2], (scene, i, snap.name, name.value)
+        ref_world = np.array(list(world), np.float32).reshape(4, 4).T[:3]
+        a, b = got["world3x4"][i].astype(np.float64), ref_world.astype(np.float64)
+        assert np.all(np.abs(a - b) <= np.maximum(np.abs(a), np.abs(b)) * 8 * 1.2e-7 + 1e-6), (scene, i, a, b)
+        assert np.allclose(mine["position"], info["position"][0], rtol=0, atol=1e-6)
+        assert np.allclose(mine["scale"], info["scale"][0], rtol=1e-5, atol=1e-6)
+        d = np.abs(((np.asarray(mine["rotation"]) - info["rotation"][0]) + 180.0) % 360.0 - 180.0)
+        assert float(d.max()) < 2e-3, (scene, i)
+    # materials (sanitised by VKRT_addMaterial / VKRT_setMaterial on both sides)
+    count = C.c_uint32()
+    ref.refhost_material_count.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)] if hasattr(ref, "refhost_material_count") else None
+    mats = np.frombuffer(got["materials"].tobytes(), H.hr.MATERIAL)
+    for k in range(len(mats)):
+        snapshot = np.zeros(544, np.uint8)   # VKRT_MaterialSnapshot {Material, useCount, name[256]} (tests above)
+        assert ref.refhost_get_material(h, C.c_uint32(k), snapshot.ctypes.data_as(C.c_void_p)) == 0, (scene, k)
+        assert snapshot[:272].tobytes() == mats[k].tobytes(), (scene, k, [f for f in H.hr.MATERIAL.names
+                                                                          if np.frombuffer(snapshot[:272].tobytes(), H.hr.MATERIAL)[f].tobytes() != mats[k][f].tobytes()])
+    # scene settings
+    rs, ms = host.SceneSettings(), hs.scene_settings()
+    ref.refscene_settings(h, C.byref(rs))
+    for field, _ in host.SceneSettings._fields_:
+        if field == "camera":   # (near / far are engine defaults that the shim's handle creation does not set: not part of a scene file)
+            for part in ("pos", "target", "up"):
+                assert list(getattr(rs.camera, part)) == list(getattr(ms.camera, part)), (scene, part)
+            assert rs.camera.vfov == ms.camera.vfov
+        elif field == "environmentColor":
+            assert list(rs.environmentColor) == list(ms.environmentColor)
+        elif field in ("rrMaxDepth", "rrMinDepth", "toneMappingMode", "renderMode", "spectralSamplingMode", "exposure", "autoExposureEnabled",
+                       "environmentStrength", "environmentRotation", "environmentTextureIndex", "misNeeEnabled"):   # what a scene file sets
+            assert getattr(rs, field) == getattr(ms, field), (scene, field, getattr(rs, field), getattr(ms, field))
+    hs.close()
+    ref.refscene_close()   # (the handle itself is left to the process: refhost_destroy frees what refhost_add_mesh allocated, not what scene/geometry.c did)
