@@ -43,6 +43,20 @@ enum {
 };
 typedef struct VkExtent2D { uint32_t width, height; } VkExtent2D;
 typedef struct VkTransformMatrixKHR { float matrix[3][4]; } VkTransformMatrixKHR;
+/* for src/core/scene/exposure.c (the 256 one-texel copies of the auto-exposure probe) */
+enum { VK_IMAGE_ASPECT_COLOR_BIT = 1 };
+typedef struct VkOffset3D { int32_t x, y, z; } VkOffset3D;
+typedef struct VkExtent3D { uint32_t width, height, depth; } VkExtent3D;
+typedef struct VkImageSubresourceLayers { VkFlags aspectMask; uint32_t mipLevel, baseArrayLayer, layerCount; } VkImageSubresourceLayers;
+typedef struct VkBufferImageCopy {
+    VkDeviceSize bufferOffset;
+    uint32_t bufferRowLength, bufferImageHeight;
+    VkImageSubresourceLayers imageSubresource;
+    VkOffset3D imageOffset;
+    VkExtent3D imageExtent;
+} VkBufferImageCopy;
+void vkCmdCopyImageToBuffer(VkCommandBuffer commandBuffer, VkImage srcImage, VkImageLayout srcImageLayout, VkBuffer dstBuffer, uint32_t regionCount,
+                            const VkBufferImageCopy* regions);
 typedef struct VkSurfaceFormatKHR { VkFormat format; VkColorSpaceKHR colorSpace; } VkSurfaceFormatKHR;
 typedef struct VkStridedDeviceAddressRegionKHR { VkDeviceAddress deviceAddress; VkDeviceSize stride, size; } VkStridedDeviceAddressRegionKHR;
 typedef struct VkSurfaceCapabilitiesKHR { uint32_t opaque[16]; } VkSurfaceCapabilitiesKHR;

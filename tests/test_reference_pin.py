@@ -750,3 +750,63 @@ def test_scene_file_reader_matches_the_reference_controller(scene):
             assert getattr(rs, field) == getattr(ms, field), (scene, field, getattr(rs, field), getattr(ms, field))
     hs.close()
     ref.refscene_close()   # (the handle itself is left to the process: refhost_destroy frees what refhost_add_mesh allocated, not what scene/geometry.c did)
+
+
+# ---- feedback controllers: vkrt_b200/host/controllers.c against the reference's timing.c / exposure.c -----------------------------------------
+def test_feedback_controllers_match_the_reference():
+    """Auto-SPP (src/core/scene/timing.c updateAutoSPP) and auto-exposure (src/core/scene/exposure.c: the 16 x 16 probe grid recorded as 256
+    one-texel copies, resolveAutoExposureReadback), compiled unmodified into libvkrt_refhost.so, driven step by step next to the product's
+    vkrtAutoSPPStep / vkrtAutoExposureStep / vkrtAutoExposureProbePixels: same probe pixels for any frame size, and bit-identical controller
+    state over long random sequences (non-finite and non-positive samples included)."""
+    from vkrt_b200 import host
+    ref = refpin.refhost_lib()
+    lib = host.load_host_library()
+    lib.vkrtAutoSPPStep.restype = C.c_uint32
+    lib.vkrtAutoSPPStep.argtypes = [C.POINTER(C.c_float), C.c_float, C.c_float, C.c_uint32]
+    lib.vkrtAutoExposureStep.restype = C.c_int
+    lib.vkrtAutoExposureStep.argtypes = [C.POINTER(C.c_float), C.c_void_p, C.c_uint32, C.c_float, C.POINTER(C.c_float)]
+    lib.vkrtAutoExposureProbePixels.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p]
+    ref.refcontrol_probe_pixels.restype = C.c_uint32
+    ref.refcontrol_probe_pixels.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+    ref.refcontrol_exposure_step.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    ref.refcontrol_autospp_step.restype = C.c_uint32
+    ref.refcontrol_autospp_step.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_float, C.c_float, C.c_uint32]
+    h = C.c_void_p(ref.refhost_create(64, 64))
+    bits = lambda v: np.float32(v).view(np.uint32)   # noqa: E731
+    # probe pixels
+    for w, hh in ((1920, 1080), (3840, 2160), (512, 512), (17, 9), (16, 16), (5, 3), (1, 1)):
+        a, b = np.zeros(512, np.uint32), np.zeros(512, np.uint32)
+        assert ref.refcontrol_probe_pixels(h, w, hh, a.ctypes.data_as(C.c_void_p)) == 256
+        lib.vkrtAutoExposureProbePixels(w, hh, b.ctypes.data_as(C.c_void_p))
+        assert np.array_equal(a, b), (w, hh)
+    # auto-exposure: a drifting scene brightness with hostile samples, 300 steps
+    rng = np.random.default_rng(21)
+    rf, re_ = C.c_float(0.0), C.c_float(1.0)
+    mf, me = C.c_float(0.0), np.float32(1.0)
+    for step in range(300):
+        level = np.float32(10.0 ** rng.uniform(-3, 2))
+        s = (rng.random((256, 4), dtype=np.float32) * level).astype(np.float32)
+        if step % 7 == 0:
+            s[rng.integers(0, 256, 5), rng.integers(0, 3, 5)] = [np.nan, np.inf, -np.inf, -3.0, 0.0]
+        if step % 50 == 49:
+            s[:] = 0.0          # black frame: the controller must hold its state
+        if step % 97 == 96:
+            s[:] = np.nan
+        ref.refcontrol_exposure_step(h, s.ctypes.data_as(C.c_void_p), C.byref(rf), C.byref(re_))
+        out = C.c_float(0.0)
+        if lib.vkrtAutoExposureStep(C.byref(mf), s.ctypes.data_as(C.c_void_p), 256, C.c_float(me), C.byref(out)):
+            me = np.float32(out.value)
+        assert bits(rf.value) == bits(mf.value) and bits(re_.value) == bits(me), (step, rf.value, mf.value, re_.value, me)
+    # auto-SPP: frame times that follow the sample count with noise, several targets, 400 steps
+    for target in (1000.0 / 60.0, 1000.0 / 24.0, 5.0, 200.0):
+        rc, mc = C.c_float(0.0), C.c_float(0.0)
+        rspp = mspp = 1
+        cost = 0.35
+        for step in range(400):
+            if step % 80 == 79:
+                cost *= float(rng.choice([0.25, 4.0]))     # the scene got cheaper / more expensive
+            measured = np.float32(max(cost * rspp * rng.uniform(0.85, 1.2) + 0.3, 0.0 if step % 37 else -1.0))
+            rspp = ref.refcontrol_autospp_step(h, C.byref(rc), C.c_float(target), C.c_float(measured), rspp)
+            mspp = lib.vkrtAutoSPPStep(C.byref(mc), C.c_float(target), C.c_float(measured), mspp)
+            assert rspp == mspp and bits(rc.value) == bits(mc.value), (target, step, rspp, mspp, rc.value, mc.value)
+        assert 1 <= rspp <= 2048
