@@ -272,6 +272,8 @@ VKRT_HOST_API int vkrtLoadImageFromFile(const char* path, uint32_t preferredColo
 VKRT_HOST_API int vkrtLoadImageFromMemory(const void* data, size_t size, const char* mimeType, uint32_t preferredColorSpace, VKRT_LoadedImage* outImage);
 VKRT_HOST_API void vkrtFreeLoadedImage(VKRT_LoadedImage* image);
 /* baseline 4:4:4 JPEG writer behind VKRT_saveRenderImage("*.jpg") (src/core/utility/export/image.c:220-263 uses quality 95) */
+/* scanline OpenEXR writer behind VKRT_saveRenderImage("*.exr") (src/core/utility/exr.h:14 vkrtWriteEXRFromRGBA32F): RGBA, 32-bit float, uncompressed */
+VKRT_HOST_API int vkrtWriteEXRFromRGBA32F(const char* path, const float* rgba32f, uint32_t width, uint32_t height);
 VKRT_HOST_API int vkrtWriteJPEGFromRGBA8(const char* path, const uint8_t* rgba8, uint32_t width, uint32_t height, int quality);
 
 /* The host-side stages of a denoised save, exported for the parity tests (tests/test_denoise.py compares them with the reference's own

@@ -150,6 +150,13 @@ static int writePng16(const char* path, const uint16_t* rgba, uint32_t w, uint32
     return ok;
 }
 
+/* src/core/utility/exr.h: vkrtWriteEXRFromRGBA32F (the reference writes through tinyexr; tests/test_reference_pin.py reads this writer's
+ * files back with the reference's tinyexr loader, and the reference's files with this host's reader) */
+int vkrtWriteEXRFromRGBA32F(const char* path, const float* rgba32f, uint32_t width, uint32_t height) {
+    if (!path || !rgba32f || !width || !height) return 0;
+    return writeExr(path, rgba32f, width, height);
+}
+
 static int hasSuffix(const char* s, const char* suffix) {
     size_t n = strlen(s), m = strlen(suffix);
     if (m > n) return 0;
