@@ -831,7 +831,8 @@ def test_exr_reader_and_writer_match_the_reference_codec(tmp_path):
     back through the host's reader."""
     from vkrt_b200 import host
     ref = refpin._load("libvkrt_refexr.so")
-    lib = host.load_host_library()
+    host.load_host_library()
+    lib = C.CDLL(host.HOST_LIB_PATH)   # (a private handle: other test modules set argtypes with their own struct classes on the shared one)
     for fn in (ref.vkrtLoadEXRImageFromMemory, ref.vkrtLoadEXRImageFromFile, lib.vkrtLoadImageFromFile, lib.vkrtLoadImageFromMemory):
         fn.restype = C.c_int
     gold = np.load(os.path.join(H.ROOT, "tests", "golden", "images.npz"))
