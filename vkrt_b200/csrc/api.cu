@@ -733,6 +733,23 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_set_rgb2spec(vkrt_cuda_ctx* ctx, const float
     launchPackRgb2spec(ctx->rgb2spec.p, info.dataOffset, cellCount, ctx->rgb2specCells.p, ctx->smCount * 8, ctx->stream);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(ctx->stream));
+    if (const char* e = getenv("VKRT_L2_PERSIST")) {   // tuning knob (profiles/r02_notes.md): pin the coefficient cells in the persisting part of L2
+        if (atoi(e) != 0) {
+            cudaDeviceProp prop;
+            if (cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
+                const size_t bytes = std::min(std::min(cellCount * sizeof(::float4), (size_t)prop.persistingL2CacheMaxSize), (size_t)prop.accessPolicyMaxWindowSize);
+                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes);
+                cudaStreamAttrValue av = {};
+                av.accessPolicyWindow.base_ptr = ctx->rgb2specCells.p;
+                av.accessPolicyWindow.num_bytes = bytes;
+                av.accessPolicyWindow.hitRatio = 1.0f;
+                av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &av);
+                cudaGetLastError();
+            }
+        }
+    }
     ctx->rgb2specInfo = info;
     ctx->haveRgb2spec = true;
     ctx->memoDirty = true;

@@ -37,6 +37,25 @@ constexpr unsigned long long TRACE_REFILL_BIG_SCENE = 262144ull;
 #define TRACE_MIN_BLOCKS 7   // 72 registers, 28 warps per SM. Measured again once the parameter block stayed in constant memory (profiles/r02z_trace_occupancy.txt):
                              // 5 / 6 / 7 / 8 blocks per SM: cornell 27.3 / 26.2 / 25.7 / 26.7 ms, soup 18.6 / 18.0 / 17.8 / 18.7, 1000 spheres 32.5 / 30.9 / 30.2 / 31.6
 #endif
+// Cache hints for the wavefront queues (path state, rays, hit records, shadow queue): every entry is written once by one kernel and read
+// once or twice by the next, and a launch streams 1 - 5 GB of them through the 126 MB L2 beside the ~30 MB the kernels re-read (BVH,
+// geometry, materials, rgb2spec cells). ld.global.cs / st.global.cs (SASS: LDG.E.EF / STG.E.EF) mark queue lines evict-first; results
+// cannot change. Measured on the same box (profiles/r03i_hints_ab.txt): cornell hero frame 48.0 -> 47.7 ms (trace 25.42 -> 25.25, shade
+// 22.57 -> 22.45), RGB 39.05 -> 38.98 ms. -DNO_TRACE_STREAM_HINTS / -DNO_SHADE_STREAM_HINTS build the plain accesses for an A/B.
+#ifndef NO_TRACE_STREAM_HINTS
+#define TQ_LD(p) __ldcs(p)
+#define TQ_ST(p, v) __stcs((p), (v))
+#else
+#define TQ_LD(p) __ldg(p)
+#define TQ_ST(p, v) (*(p) = (v))
+#endif
+#ifndef NO_SHADE_STREAM_HINTS
+#define SQ_LD(p) __ldcs(p)
+#define SQ_ST(p, v) __stcs((p), (v))
+#else
+#define SQ_LD(p) (*(p))
+#define SQ_ST(p, v) (*(p) = (v))
+#endif
 constexpr uint32_t SHADOW_KIND_SCALAR = 1u << 31;  // in ShadowTarget.statePos: contribution goes to the scalar lane (hero fallback)
 
 struct TraceParams {
@@ -181,9 +200,9 @@ __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS) k_trace(const _
                         R.index = idx;
                         ::float4 ro, rd;
                         if (!R.anyHit) {
-                            ro = __ldg(P.rayO + idx); rd = __ldg(P.rayD + idx);
+                            ro = TQ_LD(P.rayO + idx); rd = TQ_LD(P.rayD + idx);
                         } else {
-                            ro = __ldg(P.shO + (idx - extCount)); rd = __ldg(P.shD + (idx - extCount));
+                            ro = TQ_LD(P.shO + (idx - extCount)); rd = TQ_LD(P.shD + (idx - extCount));
                         }
                         R.o = float3(ro.x, ro.y, ro.z);
                         R.d = float3(rd.x, rd.y, rd.z);
@@ -388,17 +407,17 @@ __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS) k_trace(const _
                 if (sp == 0) {
                     // ---- ray finished: write back ----------------------------------------------------------------
                     if (!R.anyHit) {
-                        P.hitA[R.index] = make_uint4(R.hitInst, R.hitPrim, __float_as_uint(R.hitInst != VKRT_INVALID_INDEX ? R.tBest : 0.0f),
-                                                      __float_as_uint(R.hitU));
+                        TQ_ST(P.hitA + R.index, make_uint4(R.hitInst, R.hitPrim, __float_as_uint(R.hitInst != VKRT_INVALID_INDEX ? R.tBest : 0.0f),
+                                                           __float_as_uint(R.hitU)));
                         P.hitB[(size_t)R.index * P.slotStride] = R.hitV;
                     } else {
                         const uint32_t k = R.index - extCount;
                         const bool occluded = R.hitInst != VKRT_INVALID_INDEX;
                         if (P.shadowResult) P.shadowResult[k] = occluded ? 1u : (R.sawTransmissive ? 2u : 0u);
                         if (P.shTarget) {
-                            const ::uint2 target = __ldg(P.shTarget + k);
+                            const ::uint2 target = TQ_LD(P.shTarget + k);
                             if (!occluded && !R.sawTransmissive) {
-                                const ::float4 c = __ldg(P.shContribution + k);
+                                const ::float4 c = TQ_LD(P.shContribution + k);
                                 if (target.y & SHADOW_KIND_SCALAR) {
                                     atomicAdd(P.radianceScalar + target.x, c.x);
                                 } else {

@@ -449,15 +449,15 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const _
         bool currentVertexNeeAllowed = false;
 
         if (live) {
-            const ::float4 ro = S.rayO[i], rd = S.rayD[i];
-            const ::uint4 ha = fp.hitA[i];
-            const ::uint4 slotMeta = S.meta[i];
+            const ::float4 ro = SQ_LD(S.rayO + i), rd = SQ_LD(S.rayD + i);
+            const ::uint4 ha = SQ_LD(fp.hitA + i);
+            const ::uint4 slotMeta = SQ_LD(S.meta + i);
             rec = slotMeta.x;
             rng = slotMeta.y;
             flags = slotMeta.z;
             hitV = __uint_as_float(slotMeta.w);
             // depth 0: the constant part of a fresh path's state is not stored (k_raygen)
-            const ::float4 thrRaw = (depth == 0u && MODE != MODE_SINGLE) ? make_float4(1.f, 1.f, 1.f, MODE == MODE_RGB ? 0.f : 1.f) : S.thr[i];
+            const ::float4 thrRaw = (depth == 0u && MODE != MODE_SINGLE) ? make_float4(1.f, 1.f, 1.f, MODE == MODE_RGB ? 0.f : 1.f) : SQ_LD(S.thr + i);
             ray.origin = float3(ro.x, ro.y, ro.z);
             ray.direction = float3(rd.x, rd.y, rd.z);
             hitInst = ha.x;
@@ -478,18 +478,18 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const _
                 prevBsdfPdf = thrRaw.z;
             } else {
                 thr4 = fromF4(thrRaw);
-                const ::float4 misc = S.heroMisc[i];
+                const ::float4 misc = SQ_LD(S.heroMisc + i);
                 unit = misc.x;
                 thrScalar = misc.y;
                 prevBsdfPdf = misc.z;
                 wl4 = heroWavelengths(unit);
                 lambdaScalar = wl4.x;
                 heroActive = (flags & PF_HERO_ACTIVE) != 0u;
-                techPdf = depth == 0u ? float4(1.0f) : fromF4(S.techPdf[i]);
+                techPdf = depth == 0u ? float4(1.0f) : fromF4(SQ_LD(S.techPdf + i));
             }
             medium.flags = (flags >> 1) & 3u;
             if (medium.absorptionActive()) {
-                const ::float4 sg = S.sigma[i];
+                const ::float4 sg = SQ_LD(S.sigma + i);
                 medium.absorptionSigma = float3(sg.x, sg.y, sg.z);
                 medium.spectralAbsorptionSigma = fromF4(sg);
                 if (MODE == MODE_SINGLE || (MODE == MODE_HERO && !heroActive)) medium.spectralAbsorptionSigma = float4(sg.x);
@@ -506,7 +506,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const _
                         if ((fp.modeFlags & MODE_NEE_ENABLED) && (flags & PF_PREV_VERTEX_NEE_ALLOWED) && depth > 0u) {
                             const float lp2 = environmentPdf(sc, scene, ray.direction) * sc.env.pEnv;
                             if (MODE == MODE_HERO && heroActive) {
-                                const float4 pv = fromF4(S.prevVertexTechPdf[i]), pb = fromF4(S.prevBsdfTechPdf[i]);
+                                const float4 pv = fromF4(SQ_LD(S.prevVertexTechPdf + i)), pb = fromF4(SQ_LD(S.prevBsdfTechPdf + i));
                                 heroWeight = computeSpectralMISWeight(pv * pb, pv * lp2);
                             } else if (prevBsdfPdf > 0.0f && lp2 > 0.0f) {
                                 env = env * powerHeuristic(prevBsdfPdf, lp2);
@@ -697,7 +697,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const _
                         float misWeight = heroWavelengthBalanceWeight(techPdf);
                         if (misActive) {
                             const float lp2 = lightPdfAreaToSolidAngle(lightPdfArea, geometricNormal, ray.direction, hitT) * (ENVIS ? 1.0f - sc.env.pEnv : 1.0f);
-                            const float4 pv = fromF4(S.prevVertexTechPdf[i]), pb = fromF4(S.prevBsdfTechPdf[i]);
+                            const float4 pv = fromF4(SQ_LD(S.prevVertexTechPdf + i)), pb = fromF4(SQ_LD(S.prevBsdfTechPdf + i));
                             misWeight = computeSpectralMISWeight(pv * pb, pv * lp2);
                         }
                         const float4 c = thr4 * (spectralScalarFromLinearSrgb4(T, spectralMemoOf(T, state, SPECTRAL_MEMO_EMISSION), emission, wl4) * misWeight);
@@ -806,32 +806,32 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(const _
                 newPos = allocSlots(fp.extCount + depth + 1u);
                 const float3 gn = geometricNormal;
                 const float3 off = isTransmission != 0u ? -gn : gn;
-                N.rayO[newPos] = toF4(hitPoint + off * SHADOW_ORIGIN_OFFSET, RAY_T_MIN);
-                N.rayD[newPos] = toF4(wi, RAY_T_MAX);
-                N.meta[newPos] = make_uint4(rec, rng, flags, 0u);
+                SQ_ST(N.rayO + newPos, toF4(hitPoint + off * SHADOW_ORIGIN_OFFSET, RAY_T_MIN));
+                SQ_ST(N.rayD + newPos, toF4(wi, RAY_T_MAX));
+                SQ_ST(N.meta + newPos, make_uint4(rec, rng, flags, 0u));
                 if (MODE == MODE_RGB) {
-                    N.thr[newPos] = toF4(thrRgb, prevBsdfPdf);
-                    if (medium.absorptionActive()) N.sigma[newPos] = toF4(medium.absorptionSigma, 0.0f);
+                    SQ_ST(N.thr + newPos, toF4(thrRgb, prevBsdfPdf));
+                    if (medium.absorptionActive()) SQ_ST(N.sigma + newPos, toF4(medium.absorptionSigma, 0.0f));
                 } else if (MODE == MODE_SINGLE) {
-                    N.thr[newPos] = make_float4(thrScalar, lambdaScalar, prevBsdfPdf, 0.0f);
-                    if (medium.absorptionActive()) N.sigma[newPos] = toF4(medium.absorptionSigma, 0.0f);
+                    SQ_ST(N.thr + newPos, make_float4(thrScalar, lambdaScalar, prevBsdfPdf, 0.0f));
+                    if (medium.absorptionActive()) SQ_ST(N.sigma + newPos, toF4(medium.absorptionSigma, 0.0f));
                 } else {
-                    N.thr[newPos] = toF4(thr4);
-                    N.heroMisc[newPos] = make_float4(unit, thrScalar, prevBsdfPdf, 0.0f);
-                    N.techPdf[newPos] = toF4(techPdf);
-                    N.prevVertexTechPdf[newPos] = toF4(newPrevVertexTechPdf);
-                    N.prevBsdfTechPdf[newPos] = toF4(newPrevBsdfTechPdf);
+                    SQ_ST(N.thr + newPos, toF4(thr4));
+                    SQ_ST(N.heroMisc + newPos, make_float4(unit, thrScalar, prevBsdfPdf, 0.0f));
+                    SQ_ST(N.techPdf + newPos, toF4(techPdf));
+                    SQ_ST(N.prevVertexTechPdf + newPos, toF4(newPrevVertexTechPdf));
+                    SQ_ST(N.prevBsdfTechPdf + newPos, toF4(newPrevBsdfTechPdf));
                     if (medium.absorptionActive())
-                        N.sigma[newPos] = heroActive ? toF4(medium.spectralAbsorptionSigma) : toF4(medium.absorptionSigma, 0.0f);
+                        SQ_ST(N.sigma + newPos, heroActive ? toF4(medium.spectralAbsorptionSigma) : toF4(medium.absorptionSigma, 0.0f));
                 }
             }
             if (shadowPending) {
                 const uint32_t k = allocSlots(fp.shCount + depth);
-                fp.shO[k] = shadowO;
-                fp.shD[k] = shadowD;
-                fp.shContribution[k] = shadowC;
-                fp.shTarget[k] = make_uint2(rec, newPos | (shadowScalarLane ? SHADOW_KIND_SCALAR : 0u));
-                fp.shSeed[k] = shadowSeed;
+                SQ_ST(fp.shO + k, shadowO);
+                SQ_ST(fp.shD + k, shadowD);
+                SQ_ST(fp.shContribution + k, shadowC);
+                SQ_ST(fp.shTarget + k, make_uint2(rec, newPos | (shadowScalarLane ? SHADOW_KIND_SCALAR : 0u)));
+                SQ_ST(fp.shSeed + k, shadowSeed);
             }
         }
     }
