@@ -53,3 +53,52 @@ def test_missing_extension_raises(tmp_path):
     import vkrt_b200
     with pytest.raises(ImportError):
         vkrt_b200.load_library(str(tmp_path / "nope.so"))
+
+
+def test_ctypes_mirrors_have_the_c_struct_sizes(tmp_path):
+    """Every ctypes.Structure the Python callers (bindings, tests, bench) pass by pointer must have the size and the field offsets of the C
+    struct it mirrors: a library call that fills a shorter Python buffer writes past its end (found with an AddressSanitizer build of
+    libvkrt_host.so: VKRT_MeshSnapshot is 16-byte aligned through Material, 624 bytes, its first mirror was 620)."""
+    import subprocess
+
+    import vkrt_b200
+    from vkrt_b200 import host
+    import test_images
+    pairs = [  # (C type, header, ctypes class, fields whose offset is compared)
+        ("vkrt_cuda_create_info", "vkrt_cuda.h", vkrt_b200.CreateInfo, ["flags"]),
+        ("vkrt_cuda_build_stats", "vkrt_cuda.h", vkrt_b200.BuildStats, ["triangleCount", "accelBytes", "plocHierarchies"]),
+        ("vkrt_cuda_frame_stats", "vkrt_cuda.h", vkrt_b200.FrameStats, ["paths", "instancesEntered", "shadeKernelMs"]),
+        ("RGB2SpecTableInfo", "vkrt_cuda.h", vkrt_b200.RGB2SpecInfo, ["dataOffset"]),
+        ("vkrt_cuda_texture", "vkrt_cuda.h", vkrt_b200.TextureDesc, ["colorSpace"]),
+        ("VKRT_CreateInfo", "vkrt_host.h", host.CreateInfo, ["preferredDeviceName", "cudaFlags", "hostOnly"]),
+        ("VKRT_PreparedScene", "vkrt_host.h", host.PreparedScene, ["materials", "triAliasIdx", "sceneData"]),
+        ("VKRT_OfflineRenderResult", "vkrt_host.h", host.OfflineRenderResult, ["samples", "mpathsPerSecond", "shadowRays"]),
+        ("Camera", "vkrt_host.h", host.Camera, ["vfov"]),
+        ("VKRT_SceneSettingsSnapshot", "vkrt_host.h", host.SceneSettings, ["exposure", "autoSPPTargetFPS", "environmentTextureIndex", "selectedMeshIndex"]),
+        ("VKRT_RenderStatusSnapshot", "vkrt_host.h", host.RenderStatus, ["totalSamples", "renderTargetSamples", "displayFrameTimeMs"]),
+        ("VKRT_LoadedImage", "vkrt_host.h", test_images.LoadedImage, ["colorSpace"]),
+        ("VKRT_TextureUpload", "vkrt_host.h", test_images.TextureUpload, ["colorSpace"]),
+        ("VKRT_TextureSnapshot", "vkrt_host.h", test_images.TextureSnapshot, ["name"]),
+    ]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "vkrt_cuda.h"', '#include "vkrt_host.h"', '#include "vkrt_closure.h"', 'int main(void) {']
+    for ctype, _, _, fields in pairs:
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (ctype, ctype))
+        for f in fields:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (ctype, f, ctype, f))
+    for ctype in ("VKRT_MeshSnapshot", "VKRT_MaterialSnapshot", "vkrt_closure_query", "vkrt_closure_result", "Material", "MeshInfo", "SceneData"):
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (ctype, ctype))
+    lines.append('return 0; }')
+    src, exe = tmp_path / "sizes.c", tmp_path / "sizes"
+    src.write_text("\n".join(lines) + "\n")
+    subprocess.check_call(["gcc", "-std=gnu11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    c = dict((k, int(v)) for k, v in (ln.split() for ln in subprocess.check_output([str(exe)]).decode().splitlines()))
+    for ctype, _, cls, fields in pairs:
+        assert C.sizeof(cls) == c[ctype], (ctype, C.sizeof(cls), c[ctype])
+        for f in fields:
+            assert getattr(cls, f).offset == c["%s.%s" % (ctype, f)], (ctype, f)
+    # mirrors declared inside tests as byte arrays / numpy dtypes
+    assert c["VKRT_MeshSnapshot"] == 624 and c["VKRT_MaterialSnapshot"] == 544
+    import harness as H
+    assert H.hr.MATERIAL.itemsize == c["Material"] == 272 and H.hr.MESH_INFO.itemsize == c["MeshInfo"] == 80 and H.hr.SCENE_DATA.itemsize == c["SceneData"] == 240
+    import refpin
+    assert refpin.CLOSURE_QUERY.itemsize == c["vkrt_closure_query"] and refpin.CLOSURE_RESULT.itemsize == c["vkrt_closure_result"]

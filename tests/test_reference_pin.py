@@ -707,7 +707,9 @@ def test_scene_file_reader_matches_the_reference_controller(scene):
 
     class MeshSnapshot(C.Structure):
         _fields_ = [("info", C.c_uint8 * 80), ("material", C.c_uint8 * 272), ("materialIndex", C.c_uint32), ("geometrySource", C.c_uint32),
-                    ("hasMaterialAssignment", C.c_uint8), ("ownsGeometry", C.c_uint8), ("name", C.c_char * 256)]
+                    ("hasMaterialAssignment", C.c_uint8), ("ownsGeometry", C.c_uint8), ("name", C.c_char * 256),
+                    ("tail", C.c_uint8 * 6)]   # the C struct is 16-byte aligned through MeshInfo / Material: sizeof == 624
+    assert C.sizeof(MeshSnapshot) == 624
     for i in range(n):
         info, world, misc, name = np.zeros(1, H.hr.MESH_INFO), (C.c_float * 16)(), (C.c_uint32 * 4)(), C.create_string_buffer(256)
         ref.refscene_mesh(h, i, info.ctypes.data_as(C.c_void_p), world, misc, name, 256)
