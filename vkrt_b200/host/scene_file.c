@@ -198,6 +198,7 @@ VKRT_Result VKRT_appLoadScene(VKRT* vkrt, const char* scenePath) {
     size_t nImports = hj_count(imports);
     importFirst = (uint32_t*)calloc(nImports ? nImports : 1, sizeof(uint32_t));
     importCount = (uint32_t*)calloc(nImports ? nImports : 1, sizeof(uint32_t));
+    if (!pathCopy || !importFirst || !importCount) { free(pathCopy); r = hostFail(vkrt, VKRT_ERROR_OUT_OF_MEMORY, "out of memory"); goto done; }
     for (size_t i = 0; i < nImports && r == VKRT_SUCCESS; i++) {
         const char* rel = hj_string(hj_at(imports, i), NULL);
         if (!rel) { r = hostFail(vkrt, VKRT_ERROR_OPERATION_FAILED, "meshImports[%zu] is not a path", i); break; }
@@ -253,6 +254,7 @@ VKRT_Result VKRT_appLoadScene(VKRT* vkrt, const char* scenePath) {
     size_t nSaved = hj_count(meshes);
     savedToLoaded = (uint32_t*)calloc(nSaved ? nSaved : 1, sizeof(uint32_t));
     unsigned char* keep = (unsigned char*)calloc(vkrt->meshCount ? vkrt->meshCount : 1, 1);
+    if (!savedToLoaded || !keep) { free(keep); r = hostFail(vkrt, VKRT_ERROR_OUT_OF_MEMORY, "out of memory"); goto done; }
     for (size_t k = 0; k < nSaved; k++) {
         const hj_value* jm = hj_at(meshes, k);
         uint32_t ii, li;
