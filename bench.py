@@ -50,6 +50,22 @@ B_SHADE_SURFACE = 12 + 144 + 80 + 32 + 272           # indices, 3 ShaderVertex, 
 B_SHADE_WRITE_PATH_HERO = 32 + 16 + 16 + 16 + 16 + 16 + 16   # ray, meta, thr4, heroMisc, techPdf, prevVertexTechPdf, prevBsdfTechPdf
 B_SHADE_WRITE_SHADOW = 16 + 16 + 16 + 8 + 4
 B_SHADE_FEATURES = 36                                 # featA, featB, follow at depth 0
+B_BUILD_TRIANGLE = 520   # BVH build (DESIGN.md "Build"): 48 vertices + 12 key/index + 8 sort passes x 24 + 2 x 64 binary nodes + 64 refit + ~27 BVH8 + 48 re-pack
+
+
+def derived_roofline_fields(roofline, c3, peak):
+    """SURVEY 8(d) asks for the traversal / shading bytes at two levels and for the build's fraction. Pure arithmetic on numbers measured
+    elsewhere in this run (nothing is timed here): `roofline.dram` = the ncu DRAM bytes per launch of profiles/traffic.json over this run's live
+    launch time, next to the algorithmic figure (their ratio is what L1 / L2 serve); `c3.build_*` = the 10 M-triangle build against the HBM peak."""
+    if roofline and roofline.get("traffic") and roofline.get("avg_launch_ms", 0) > 0 and peak > 0:
+        gbps = roofline["traffic"] / 1e9 / (roofline["avg_launch_ms"] * 1e-3)
+        roofline["dram"] = {"GBps": gbps, "frac": gbps / peak, "algorithmic_over_dram": roofline["algorithmic_bytes_per_launch"] / roofline["traffic"],
+                            "note": "DRAM bytes per launch from the ncu capture named in traffic_source (32 spp per step), divided by this run's live launch time"}
+    if c3 and c3.get("bvh_build_ms", 0) > 0 and peak > 0:
+        gbps = c3["triangles"] * B_BUILD_TRIANGLE / 1e9 / (c3["bvh_build_ms"] * 1e-3)
+        c3["build_algorithmic_bytes_per_triangle"] = B_BUILD_TRIANGLE
+        c3["build_achieved_GBps_algorithmic"] = gbps
+        c3["build_roofline_frac"] = gbps / peak
 
 
 def procedural_sky(width=1024, height=512):
@@ -589,6 +605,13 @@ def _run_ours(args, real_stdout):
         }
         if cpu_base:
             line["cpu_baseline"] = cpu_base
+        try:
+            if args.spp == 32 or not (roofline or {}).get("traffic"):
+                derived_roofline_fields(roofline, c3, peak)
+            else:   # traffic.json was captured at 32 spp per step: per-launch DRAM bytes of another step size are not comparable
+                derived_roofline_fields(None, c3, peak)
+        except Exception as e:   # derived, optional fields must never cost the bench line
+            sys.stderr.write("derived roofline fields skipped: %r\n" % (e,))
         if c3:
             line["config"]["c3"] = c3
         if strong:

@@ -37,3 +37,25 @@ def test_our_arm_refuses_to_run_without_a_device():
     assert r.returncode != 0
     assert "no CPU path" in (r.stderr + r.stdout)
     assert not any(ln.startswith("{") for ln in r.stdout.splitlines())    # no number without a GPU
+
+
+def test_derived_roofline_fields_are_plain_arithmetic_on_the_measured_line():
+    """bench.derived_roofline_fields (bytes at the algorithmic and the DRAM level, build fraction) on the numbers of a committed
+    bench line: DRAM GB/s = ncu bytes per launch / live launch time, build GB/s = 520 B x triangles / build time, both over the measured peak."""
+    sys.path.insert(0, ROOT)
+    import bench
+    d = json.loads(open(os.path.join(ROOT, "profiles", "r03f_bench_n1.json")).read().strip().splitlines()[-1])
+    roofline, c3, peak = d["roofline"], d["config"]["c3"], d["roofline"]["peak"]
+    bench.derived_roofline_fields(roofline, c3, peak)
+    dram = roofline["dram"]
+    assert dram["GBps"] == pytest.approx(roofline["traffic"] / 1e9 / (roofline["avg_launch_ms"] * 1e-3))
+    assert dram["frac"] == pytest.approx(dram["GBps"] / peak) and 0.0 < dram["frac"] < roofline["frac"] < 1.0
+    assert dram["algorithmic_over_dram"] == pytest.approx(roofline["algorithmic_bytes_per_launch"] / roofline["traffic"])
+    assert c3["build_achieved_GBps_algorithmic"] == pytest.approx(c3["triangles"] * 520 / 1e9 / (c3["bvh_build_ms"] * 1e-3))
+    assert c3["build_roofline_frac"] == pytest.approx(c3["build_achieved_GBps_algorithmic"] / peak) and 0.0 < c3["build_roofline_frac"] < 1.0
+    json.dumps(d)   # still serialisable
+    # missing inputs leave the line untouched
+    bench.derived_roofline_fields(None, None, peak)
+    r2 = {"traffic": None, "avg_launch_ms": 1.0, "algorithmic_bytes_per_launch": 1.0}
+    bench.derived_roofline_fields(r2, {"triangles": 10, "bvh_build_ms": 0.0}, peak)
+    assert "dram" not in r2
