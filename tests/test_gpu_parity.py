@@ -167,6 +167,24 @@ def test_debug_views(debug_mode):
     assert c["frac_rel_gt_1e2"] < 0.01, c
 
 
+@pytest.mark.parametrize("debug_mode", [6, 7, 8, 9, 10, 11])
+def test_texture_map_debug_views(debug_mode):
+    """Debug views 6 - 11 on the textured stage: the selection mask (no selection: the 0.05 grey of debug.slang) and the base-colour /
+    metallic / roughness / normal-map / emissive-map views (integrator/path/debug.slang:31-64 through material/textures.slang), which the
+    cornell scene of test_debug_views cannot exercise. Debug pixels carry weight 0 (writeDebugFrameOutputs), the others the sample count."""
+    w, h = 96, 64
+    prep = scenes.textured(w, h, spp=2)
+    prep["sceneData"]["debugMode"] = debug_mode
+    o, g = scenes.both_backends(prep, w, h)
+    o.render(prep["sceneData"], frames=1)
+    g.render(prep["sceneData"], frames=1)
+    a, b = o.read(H.AOV_ACCUM), g.read(H.AOV_ACCUM)
+    assert np.array_equal(a[..., 3], b[..., 3])
+    assert (a[..., 3] == 0).mean() > 0.5          # most of the frame is a debug pixel
+    c = H.compare_images(a[..., :3], b[..., :3])
+    assert c["frac_rel_gt_1e2"] < 0.01, c
+
+
 def test_nee_only_plus_bsdf_only_equals_full():
     """The reference's own validation views (constants.h:39-40): with MIS the two techniques partition the estimator,
     so E[NEE-only] + E[BSDF-only] = E[full]. Checked on the GPU alone at moderate spp."""
