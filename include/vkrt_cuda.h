@@ -161,7 +161,9 @@ VKRT_CUDA_API VKRT_Result vkrt_cuda_set_rgb2spec(vkrt_cuda_ctx* ctx, const float
                                                  RGB2SpecTableInfo info);
 
 /* Replaces recordBottomLevelAccelerationStructureBuilds (blas.c:222-262) + recordTopLevelAccelerationStructureBuilds
- * (tlas.c:535-559): LBVH build + collapse to compressed 8-wide nodes, one BLAS per unique geometry, TLAS over instances. */
+ * (tlas.c:535-559): Morton sort, two binary hierarchies over the sorted primitives (Karras radix tree and PLOC, the one with the lower surface-area
+ * cost is kept: the counterpart of the PREFER_FAST_TRACE flag the reference passes, blas.c:39 / tlas.c:188), collapse to compressed 8-wide nodes;
+ * ONE flat BVH over all instanced triangles when flattening does not multiply memory, otherwise one BLAS per unique geometry + a TLAS over instances. */
 VKRT_CUDA_API VKRT_Result vkrt_cuda_build_accel(vkrt_cuda_ctx* ctx, vkrt_cuda_build_stats* outStats);
 /* vkrt_cuda_build_accel returns the previous build when nothing it depends on changed (geometry, instance matrices / sharing / any-hit
  * flags, the "transmits" bit of a material): like the reference, which rebuilds a BLAS only when blasBuildPending is set
