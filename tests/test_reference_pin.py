@@ -872,3 +872,24 @@ def test_exr_reader_and_writer_match_the_reference_codec(tmp_path):
     want = px.reshape(-1) if b.format == 3 else px.astype(np.float16).reshape(-1).view(np.uint16)
     assert np.array_equal(got.view(np.uint8), want.view(np.uint8))
     lib.vkrtFreeLoadedImage(C.byref(b))
+
+
+# ======================================================================================================================
+# data tables the device code embeds
+# ======================================================================================================================
+def test_sheen_ltc_table_of_the_device_code_is_the_reference_table():
+    """csrc/data/sheen_ltc.inc (what k_shade's sheen lobe reads) and oracle/sheen_ltc.inc are one file, and — where the reference checkout is
+    present — its 3072 values are the ones of src/shaders/bsdf/data/sheen_ltc.slang, value by value in fp32."""
+    import re
+    dev = open(os.path.join(H.ROOT, "vkrt_b200", "csrc", "data", "sheen_ltc.inc")).read()
+    assert dev == open(os.path.join(H.ROOT, "oracle", "sheen_ltc.inc")).read()
+    mine = np.array([float(v.rstrip("f")) for v in re.findall(r"-?\d+\.\d+f?", "\n".join(ln for ln in dev.splitlines() if not ln.startswith("//")))], np.float32)
+    assert mine.shape == (3072,)
+    slang = os.path.join(refpin.REFERENCE, "src", "shaders", "bsdf", "data", "sheen_ltc.slang")
+    if not os.path.exists(slang):
+        pytest.skip("reference checkout not present")
+    src = open(slang).read()
+    body = src[src.index("SHEEN_LTC_TABLE[3072]"):]
+    body = body[body.index("{") + 1: body.index("}")]
+    ref = np.array([float(v.rstrip("f")) for v in re.findall(r"-?\d+\.\d+(?:[eE][-+]?\d+)?f?", body)], np.float32)
+    assert ref.shape == (3072,) and np.array_equal(ref, mine)
