@@ -893,3 +893,24 @@ def test_sheen_ltc_table_of_the_device_code_is_the_reference_table():
     body = body[body.index("{") + 1: body.index("}")]
     ref = np.array([float(v.rstrip("f")) for v in re.findall(r"-?\d+\.\d+(?:[eE][-+]?\d+)?f?", body)], np.float32)
     assert ref.shape == (3072,) and np.array_equal(ref, mine)
+
+
+def test_device_closure_code_carries_the_oracles_constants():
+    """csrc/shading.cuh is the CUDA statement of the closures whose oracle restatement (oracle/shading.h) is pinned bit for bit to the reference
+    shaders above. The GPU tests compare the two per call within 1e-4, which a mistyped constant of a rarely taken branch can survive; this
+    compares the floating-point literals of the two sources: the same set of distinct constants, each the same number of times (the
+    trivial 0 / 1 aside, which initialisers add freely)."""
+    import collections
+    import re
+
+    def literals(path):
+        s = open(path).read()
+        s = re.sub(r"//.*", "", s)
+        s = re.sub(r"/\*.*?\*/", "", s, flags=re.S)
+        return collections.Counter(re.findall(r"(?<![\w.])(?:\d+\.\d*(?:[eE][-+]?\d+)?|\.\d+(?:[eE][-+]?\d+)?|\d+[eE][-+]?\d+)f?", s))
+    dev = literals(os.path.join(H.ROOT, "vkrt_b200", "csrc", "shading.cuh"))
+    ora = literals(os.path.join(H.ROOT, "oracle", "shading.h"))
+    assert len(ora) > 100 and set(dev) == set(ora), (sorted(set(dev) - set(ora)), sorted(set(ora) - set(dev)))
+    for k in ora:
+        if k not in ("0.0f", "1.0f"):
+            assert dev[k] == ora[k], (k, dev[k], ora[k])
