@@ -102,3 +102,26 @@ def test_ctypes_mirrors_have_the_c_struct_sizes(tmp_path):
     assert H.hr.MATERIAL.itemsize == c["Material"] == 272 and H.hr.MESH_INFO.itemsize == c["MeshInfo"] == 80 and H.hr.SCENE_DATA.itemsize == c["SceneData"] == 240
     import refpin
     assert refpin.CLOSURE_QUERY.itemsize == c["vkrt_closure_query"] and refpin.CLOSURE_RESULT.itemsize == c["vkrt_closure_result"]
+
+
+def test_hot_kernels_keep_their_register_and_spill_budget():
+    """Build-time guard of the occupancy the measurements rely on: k_trace at <= 72 registers (7 blocks x 128 threads per SM) with
+    no more than a few spilled words, k_shade at <= 128 registers (2 blocks x 256 threads) with the spill it had when it was measured.
+    Read from the ptxas log the Makefile keeps (vkrt_b200/build/wavefront.ptxas.log, written by build())."""
+    log = os.path.join(ROOT, "vkrt_b200", "build", "wavefront.ptxas.log")
+    if not os.path.exists(log):
+        pytest.skip("no ptxas log: run __graft_entry__.build()")
+    text = open(log).read()
+    found = {}
+    for m in re.finditer(r"Compiling entry function '(\w+)' for 'sm_100a'.*?(\d+) bytes spill stores.*?Used (\d+) registers", text, flags=re.S):
+        found[m.group(1)] = (int(m.group(3)), int(m.group(2)))
+    budget = {   # mangled entry: (registers, spill-store bytes)
+        "_ZN2vk7k_traceILb0ELb1ELi40EEEvNS_11TraceParamsE": (72, 32),     # flat (single-level) walk, default stack
+        "_ZN2vk7k_traceILb0ELb0ELi40EEEvNS_11TraceParamsE": (72, 64),     # two-level walk
+        "_ZN2vk7k_shadeILi0ELb0EEEvNS_11FrameParamsEj": (128, 128),       # RGB
+        "_ZN2vk7k_shadeILi1ELb0EEEvNS_11FrameParamsEj": (128, 160),       # spectral single
+        "_ZN2vk7k_shadeILi2ELb0EEEvNS_11FrameParamsEj": (128, 288),       # spectral hero
+    }
+    for name, (regs, spill) in budget.items():
+        assert name in found, name
+        assert found[name][0] <= regs and found[name][1] <= spill, (name, found[name])
